@@ -1,0 +1,126 @@
+/*
+ * mpcq.h - C ABI of the B200 batched convex-MPC engine (libmpcq.so).
+ *
+ * The reference (yinghansun/pympc-quadruped) has no FFI layer: its boundary for this
+ * path is the Python class `ModelPredictiveController` (linear_mpc/mpc.py:22).  Each
+ * entry point below names the reference method it replaces; the Python host side
+ * (pympc_quadruped_b200/controller.py) binds them with ctypes and keeps the reference's
+ * class API on top (INTEGRATION.md shows the binding a maintainer would add).
+ *
+ * Conventions
+ *   - every array pointer is a DEVICE pointer owned by the caller (contiguous, row-major,
+ *     environment-major) unless the function name ends in `_host`;
+ *   - `real` arrays are float when the handle was created with MPCQ_F32, double with
+ *     MPCQ_F64; the gait table is always float32 like the reference's (gait.py:87);
+ *   - calls are asynchronous on `stream` (a cudaStream_t passed as void*), never
+ *     synchronise, never allocate after mpcq_create, never throw: 0 = success,
+ *     negative = error (text via mpcq_last_error);
+ *   - a handle is bound to one device and is not thread-safe;
+ *   - there is no CPU fallback: without a CUDA device mpcq_create fails.
+ */
+#ifndef MPCQ_H_
+#define MPCQ_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MPCQ_VERSION 100            /* 0.1.0 */
+
+enum { MPCQ_F32 = 0, MPCQ_F64 = 1 };
+
+/* error codes */
+enum {
+    MPCQ_OK = 0,
+    MPCQ_ERR_INVALID = -1,          /* bad argument / configuration */
+    MPCQ_ERR_CUDA = -2,             /* a CUDA runtime call failed */
+    MPCQ_ERR_NO_DEVICE = -3,        /* no usable CUDA device */
+    MPCQ_ERR_UNSUPPORTED = -4       /* size beyond what the kernels support */
+};
+
+/* per-environment status bits written to `status` */
+enum {
+    MPCQ_ST_VERIFIED = 1,           /* KKT conditions verified in fp64 on the returned point */
+    MPCQ_ST_IPM_MAXITER = 2,        /* interior-point phase stopped on the iteration cap */
+    MPCQ_ST_POLISH_MAXROUND = 4,    /* active-face refinement hit the round cap (point is feasible, not verified) */
+    MPCQ_ST_NUMERIC = 8,            /* non-finite input or a failed factorisation */
+    MPCQ_ST_STANCE_OVERFLOW = 16,   /* more stance foot-steps than cfg.max_stance_feet */
+    MPCQ_ST_NO_STANCE = 32          /* every foot-step is swing: u = 0 */
+};
+
+/*
+ * Constants of `ModelPredictiveController._load_parameters` (linear_mpc/mpc.py:35-52) and of
+ * the config classes it reads (config/linear_mpc_configs.py:4-24, config/robot_configs.py:9-56).
+ */
+typedef struct mpcq_config {
+    int32_t horizon;                /* LinearMpcConfig.horizon (1..32) */
+    int32_t dtype;                  /* MPCQ_F32 | MPCQ_F64: factorisation/iteration precision and I/O type */
+    int32_t device;                 /* CUDA device ordinal */
+    int32_t max_stance_feet;        /* cap on stance foot-steps per env (sizes shared memory); 0 = 4*horizon */
+    double dt;                      /* MPC step; the reference hard-codes 0.05 (mpc.py:38) */
+    double mu;                      /* friction_coef */
+    double fz_max;                  /* RobotConfig.fz_max */
+    double mass;                    /* RobotConfig.mass_base */
+    double gravity;                 /* LinearMpcConfig.gravity (positive) */
+    double inertia[9];              /* RobotConfig.base_inertia_base, row-major (float32 values) */
+    double q_diag[13];              /* diag(LinearMpcConfig.Q) */
+    double r_diag[12];              /* diag(LinearMpcConfig.R), all > 0 */
+    /* solver knobs (0 = default) */
+    int32_t max_ipm_iter;           /* default 30 */
+    int32_t max_polish_rounds;      /* default 12 */
+    double ipm_gap_tol;             /* stop the interior-point phase at this complementarity gap; default 1e-4 (f32) / 1e-9 (f64) */
+    double face_ratio;              /* a row is taken active when slack < face_ratio * multiplier; default 100 */
+} mpcq_config;
+
+typedef struct mpcq_handle mpcq_handle;
+
+int mpcq_version(void);
+
+/* replaces ModelPredictiveController.__init__ / _load_parameters (mpc.py:24-52) */
+int mpcq_create(const mpcq_config* cfg, mpcq_handle** out);
+void mpcq_destroy(mpcq_handle* h);
+/* last error text of this handle (or of the failed mpcq_create when h == NULL) */
+const char* mpcq_last_error(const mpcq_handle* h);
+
+/*
+ * replaces ModelPredictiveController._solve_mpc (mpc.py:262-290, drake branch) for B robots:
+ * state-space model (:173-192), discretisation (:194-208), condensed cost (:211-235),
+ * friction/contact rows (:237-260) and the QP solve (:277-286).
+ *
+ *   x0      [B,13]   current_state of update_robot_state (mpc.py:55-79): rpy, pos, omega, vel, -g
+ *   yaw     [B]      optional (NULL -> x0[:,2]); the reference keeps the unrounded float64 yaw (mpc.py:77)
+ *   r_feet  [B,4,3]  pos_base_feet: world-frame base->foot, legs FL,FR,RL,RR (robot_data.py:144-149)
+ *   gait    [B,4H]   float32 contact table, step-major/leg-minor, 1 = stance (gait.py:81-100)
+ *   x_ref   [B,13H]  generate_reference_trajectory output (mpc.py:110-170)
+ *   f_out   [B,12]   first-step ground reaction forces = _solve_mpc(...)[0:12] (mpc.py:99)
+ * optional outputs (NULL to skip):
+ *   u_full  [B,12H]  the whole optimum
+ *   iters   [B,2]    interior-point iterations, polish rounds
+ *   resid   [B,2]    fp64 KKT residuals of the returned point: stationarity, primal violation
+ *   status  [B]      MPCQ_ST_* bits
+ *   active  [B,4H]   per foot-step bit mask of tight rows: bits 0-4 rows 5k..5k+4 at their lower
+ *                    bound, bit 5 the fz row at its upper bound (constraint activity)
+ */
+int mpcq_solve(mpcq_handle* h, int32_t B,
+               const void* x0, const void* yaw, const void* r_feet, const float* gait, const void* x_ref,
+               void* f_out, void* u_full, int32_t* iters, double* resid, int32_t* status, uint8_t* active,
+               void* stream);
+
+/*
+ * Stage entry point for parity tests: the QP data the reference would hand to the solver.
+ *   H_out [B,12H,12H] (_generate_QP_cost :232), g_out [B,12H] (:233), ub_out [B,20H] (:248-258;
+ *   lb is identically 0 and C = kron(I_4H, pyramid(mu)) is constant).  Always float64.
+ */
+int mpcq_build_qp(mpcq_handle* h, int32_t B,
+                  const void* x0, const void* yaw, const void* r_feet, const float* gait, const void* x_ref,
+                  double* H_out, double* g_out, double* ub_out, void* stream);
+
+/* number of kernels the last mpcq_solve / mpcq_build_qp call launched (for bench.py's gpu_launches) */
+int mpcq_last_launch_count(const mpcq_handle* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MPCQ_H_ */
