@@ -12,9 +12,10 @@
  *     environment-major) unless the function name ends in `_host`;
  *   - `real` arrays are float when the handle was created with MPCQ_F32, double with
  *     MPCQ_F64; the gait table is always float32 like the reference's (gait.py:87);
- *   - calls are asynchronous on `stream` (a cudaStream_t passed as void*), never
- *     synchronise, never allocate after mpcq_create, never throw: 0 = success,
- *     negative = error (text via mpcq_last_error);
+ *   - calls are asynchronous on `stream` (a cudaStream_t passed as void*) and never
+ *     synchronise or throw: 0 = success, negative = error (text via mpcq_last_error);
+ *   - all device workspace is allocated by mpcq_create; `*_host` calls additionally keep
+ *     pinned staging buffers that grow to the largest batch seen;
  *   - a handle is bound to one device and is not thread-safe;
  *   - there is no CPU fallback: without a CUDA device mpcq_create fails.
  */
@@ -42,11 +43,10 @@ enum {
 
 /* per-environment status bits written to `status` */
 enum {
-    MPCQ_ST_VERIFIED = 1,           /* KKT conditions verified in fp64 on the returned point */
-    MPCQ_ST_IPM_MAXITER = 2,        /* interior-point phase stopped on the iteration cap */
-    MPCQ_ST_POLISH_MAXROUND = 4,    /* active-face refinement hit the round cap (point is feasible, not verified) */
+    MPCQ_ST_VERIFIED = 1,           /* KKT conditions (primal, dual, stationarity) hold in fp64 on the returned point */
+    MPCQ_ST_FALLBACK = 2,           /* the primal active-set fallback ran (primal-dual rounds cycled) */
+    MPCQ_ST_MAXITER = 4,            /* iteration cap reached: the point is feasible but not verified optimal */
     MPCQ_ST_NUMERIC = 8,            /* non-finite input or a failed factorisation */
-    MPCQ_ST_STANCE_OVERFLOW = 16,   /* more stance foot-steps than cfg.max_stance_feet */
     MPCQ_ST_NO_STANCE = 32          /* every foot-step is swing: u = 0 */
 };
 
@@ -56,9 +56,9 @@ enum {
  */
 typedef struct mpcq_config {
     int32_t horizon;                /* LinearMpcConfig.horizon (1..32) */
-    int32_t dtype;                  /* MPCQ_F32 | MPCQ_F64: factorisation/iteration precision and I/O type */
+    int32_t dtype;                  /* MPCQ_F32 | MPCQ_F64: factorisation precision and I/O type */
     int32_t device;                 /* CUDA device ordinal */
-    int32_t max_stance_feet;        /* cap on stance foot-steps per env (sizes shared memory); 0 = 4*horizon */
+    int32_t reserved0;
     double dt;                      /* MPC step; the reference hard-codes 0.05 (mpc.py:38) */
     double mu;                      /* friction_coef */
     double fz_max;                  /* RobotConfig.fz_max */
@@ -68,10 +68,14 @@ typedef struct mpcq_config {
     double q_diag[13];              /* diag(LinearMpcConfig.Q) */
     double r_diag[12];              /* diag(LinearMpcConfig.R), all > 0 */
     /* solver knobs (0 = default) */
-    int32_t max_ipm_iter;           /* default 30 */
-    int32_t max_polish_rounds;      /* default 12 */
-    double ipm_gap_tol;             /* stop the interior-point phase at this complementarity gap; default 1e-4 (f32) / 1e-9 (f64) */
-    double face_ratio;              /* a row is taken active when slack < face_ratio * multiplier; default 100 */
+    int32_t max_pdas_rounds;        /* primal-dual active-set rounds before the fallback; default 8 */
+    int32_t max_as_iter;            /* fallback active-set iterations; default 12*horizon + 30 */
+    int32_t max_refine;             /* residual-refinement solves per factorisation; default 8 */
+    int32_t reserved1;
+    double tol_primal;              /* relative feasibility tolerance of the face tests; default 1e-7 (f32) / 1e-9 (f64) */
+    double tol_dual;                /* relative multiplier-sign tolerance; default 1e-7 (f32) / 1e-9 (f64) */
+    double tol_residual;            /* reduced-gradient tolerance relative to 1+|g|_inf; default 1e-9 (f32) / 1e-12 (f64) */
+    double tol_active;              /* slack tolerance of the reported activity; default 1e-6 */
 } mpcq_config;
 
 typedef struct mpcq_handle mpcq_handle;
@@ -97,8 +101,8 @@ const char* mpcq_last_error(const mpcq_handle* h);
  *   f_out   [B,12]   first-step ground reaction forces = _solve_mpc(...)[0:12] (mpc.py:99)
  * optional outputs (NULL to skip):
  *   u_full  [B,12H]  the whole optimum
- *   iters   [B,2]    interior-point iterations, polish rounds
- *   resid   [B,2]    fp64 KKT residuals of the returned point: stationarity, primal violation
+ *   iters   [B,2]    factorisations, fallback active-set iterations
+ *   resid   [B,2]    fp64 KKT residuals of the returned point: reduced gradient, primal violation
  *   status  [B]      MPCQ_ST_* bits
  *   active  [B,4H]   per foot-step bit mask of tight rows: bits 0-4 rows 5k..5k+4 at their lower
  *                    bound, bit 5 the fz row at its upper bound (constraint activity)
@@ -109,9 +113,19 @@ int mpcq_solve(mpcq_handle* h, int32_t B,
                void* stream);
 
 /*
+ * Same call with HOST buffers (what a CPU-side simulator loop such as scripts/isaacgym_a1.py:119-164
+ * would hand over): inputs are staged through pinned memory, copied to the device, solved and the
+ * requested outputs copied back; returns after the results are in the caller's buffers.
+ */
+int mpcq_solve_host(mpcq_handle* h, int32_t B,
+                    const void* x0, const void* yaw, const void* r_feet, const float* gait, const void* x_ref,
+                    void* f_out, void* u_full, int32_t* iters, double* resid, int32_t* status, uint8_t* active);
+
+/*
  * Stage entry point for parity tests: the QP data the reference would hand to the solver.
  *   H_out [B,12H,12H] (_generate_QP_cost :232), g_out [B,12H] (:233), ub_out [B,20H] (:248-258;
- *   lb is identically 0 and C = kron(I_4H, pyramid(mu)) is constant).  Always float64.
+ *   lb is identically 0 and C = kron(I_4H, pyramid(mu)) is constant).  Always float64; +inf in
+ *   ub_out marks the one-sided friction rows exactly like the reference.
  */
 int mpcq_build_qp(mpcq_handle* h, int32_t B,
                   const void* x0, const void* yaw, const void* r_feet, const float* gait, const void* x_ref,

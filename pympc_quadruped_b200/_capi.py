@@ -1,0 +1,92 @@
+"""ctypes binding of include/mpcq.h (libmpcq.so).
+
+There is no CPU path: if the CUDA library is not built or no device is present, loading /
+`mpcq_create` raises.  Build with ``python -c "import __graft_entry__ as g; g.build()"`` or
+``python pympc_quadruped_b200/csrc/build.py``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+MPCQ_F32, MPCQ_F64 = 0, 1
+ST_VERIFIED, ST_FALLBACK, ST_MAXITER, ST_NUMERIC, ST_NO_STANCE = 1, 2, 4, 8, 32
+
+LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc", "_build", "libmpcq.so")
+
+
+class MpcqConfig(C.Structure):
+    """mirror of `mpcq_config` (include/mpcq.h)"""
+    _fields_ = [
+        ("horizon", C.c_int32), ("dtype", C.c_int32), ("device", C.c_int32), ("reserved0", C.c_int32),
+        ("dt", C.c_double), ("mu", C.c_double), ("fz_max", C.c_double), ("mass", C.c_double),
+        ("gravity", C.c_double),
+        ("inertia", C.c_double * 9), ("q_diag", C.c_double * 13), ("r_diag", C.c_double * 12),
+        ("max_pdas_rounds", C.c_int32), ("max_as_iter", C.c_int32), ("max_refine", C.c_int32),
+        ("reserved1", C.c_int32),
+        ("tol_primal", C.c_double), ("tol_dual", C.c_double), ("tol_residual", C.c_double),
+        ("tol_active", C.c_double),
+    ]
+
+
+def make_config(consts: dict, dtype: int = MPCQ_F32, device: int = 0, **knobs) -> MpcqConfig:
+    """`consts` is the dict of configs.extract_mpc_constants (what mpc.py:35-52 reads)."""
+    cfg = MpcqConfig()
+    cfg.horizon = int(consts["horizon"])
+    cfg.dtype = int(dtype)
+    cfg.device = int(device)
+    cfg.dt = float(consts["dt"])
+    cfg.mu = float(consts["mu"])
+    cfg.fz_max = float(consts["fz_max"])
+    cfg.mass = float(consts["mass"])
+    cfg.gravity = float(consts["gravity"])
+    cfg.inertia[:] = [float(v) for v in np.asarray(consts["inertia"], dtype=np.float32).reshape(9)]
+    cfg.q_diag[:] = [float(v) for v in consts["q_diag"]]
+    cfg.r_diag[:] = [float(v) for v in consts["r_diag"]]
+    for k, v in knobs.items():
+        if not hasattr(cfg, k):
+            raise TypeError(f"unknown solver knob {k!r}")
+        setattr(cfg, k, v)
+    return cfg
+
+
+_SOLVE_ARGS = [C.c_void_p] * 5 + [C.c_void_p] * 6          # x0,yaw,feet,gait,xref | f,u,iters,resid,status,active
+
+
+def bind(lib: C.CDLL) -> C.CDLL:
+    lib.mpcq_version.restype = C.c_int
+    lib.mpcq_create.argtypes = [C.POINTER(MpcqConfig), C.POINTER(C.c_void_p)]
+    lib.mpcq_create.restype = C.c_int
+    lib.mpcq_destroy.argtypes = [C.c_void_p]
+    lib.mpcq_destroy.restype = None
+    lib.mpcq_last_error.argtypes = [C.c_void_p]
+    lib.mpcq_last_error.restype = C.c_char_p
+    lib.mpcq_solve.argtypes = [C.c_void_p, C.c_int32] + _SOLVE_ARGS + [C.c_void_p]
+    lib.mpcq_solve.restype = C.c_int
+    lib.mpcq_solve_host.argtypes = [C.c_void_p, C.c_int32] + _SOLVE_ARGS
+    lib.mpcq_solve_host.restype = C.c_int
+    lib.mpcq_build_qp.argtypes = [C.c_void_p, C.c_int32] + [C.c_void_p] * 5 + [C.c_void_p] * 3 + [C.c_void_p]
+    lib.mpcq_build_qp.restype = C.c_int
+    lib.mpcq_last_launch_count.argtypes = [C.c_void_p]
+    lib.mpcq_last_launch_count.restype = C.c_int
+    return lib
+
+
+EXPORTS = ("mpcq_version", "mpcq_create", "mpcq_destroy", "mpcq_last_error", "mpcq_solve",
+           "mpcq_solve_host", "mpcq_build_qp", "mpcq_last_launch_count")
+
+_lib = None
+
+
+def load_library() -> C.CDLL:
+    """Load libmpcq.so or fail loudly (the engine has no fallback path)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: the CUDA engine is not built (run __graft_entry__.build()). "
+                "pympc_quadruped_b200 has no CPU fallback.")
+        _lib = bind(C.CDLL(LIB_PATH))
+    return _lib

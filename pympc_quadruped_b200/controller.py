@@ -1,0 +1,217 @@
+"""Controller interface of the reference, batched over environments.
+
+`BatchedModelPredictiveController` keeps the semantics of the reference's
+`ModelPredictiveController` (linear_mpc/mpc.py:22-290) for B robots at once:
+
+  __init__ / _load_parameters       mpc.py:24-52    constructor takes the config CLASSES
+  update_robot_state                mpc.py:55-79    quat -> ZYX angles (kinematics.py:40-49), float32 state
+  update_mpc_if_needed              mpc.py:81-108   command rotation, integrators, 20-tick decimation, cached forces
+  generate_reference_trajectory     mpc.py:110-170  clamp, roll/pitch compensation, X_ref fill
+  _solve_mpc                        mpc.py:262-290  -> MpcqEngine.solve (sm_100a kernels via the C ABI)
+
+The per-env bookkeeping above the solve (O(H) elementwise work) runs as torch ops on the same
+device, with the reference's float32 rounding points reproduced; the hot path - QP build and
+solve - is entirely inside libmpcq.so.  `ModelPredictiveController` is the B = 1 adapter with
+the reference's exact signature (numpy robot_data in, numpy[12] out) so it can replace the
+object constructed at scripts/isaacgym_a1.py:93 / scripts/mujoco_aliengo.py:173.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from .configs import extract_mpc_constants
+from .engine import MpcqEngine
+
+
+class BatchedRobotData:
+    """The five RobotData fields the path reads (utils/robot_data.py:70-76,144-149), batched."""
+
+    def __init__(self, quat_base, pos_base, ang_vel_base, lin_vel_base, pos_base_feet, R_base=None):
+        self.quat_base = quat_base            # [B,4] (w,x,y,z)
+        self.pos_base = pos_base              # [B,3]
+        self.ang_vel_base = ang_vel_base      # [B,3] world
+        self.lin_vel_base = lin_vel_base      # [B,3] world
+        self.pos_base_feet = pos_base_feet    # [B,4,3] world-frame base->foot, FL FR RL RR
+        self.R_base = R_base                  # [B,3,3] or None (derived from the quaternion)
+
+
+def quat_to_matrix(q: torch.Tensor) -> torch.Tensor:
+    """(w,x,y,z) -> R_base, batched (utils/kinematics.py:51-71)."""
+    w, x, y, z = q.unbind(-1)
+    R = torch.stack([
+        w * w + x * x - y * y - z * z, 2 * (x * y - w * z), 2 * (w * y + x * z),
+        2 * (w * z + x * y), w * w - x * x + y * y - z * z, 2 * (y * z - w * x),
+        2 * (x * z - w * y), 2 * (w * x + y * z), w * w - x * x - y * y + z * z], dim=-1)
+    return R.reshape(q.shape[:-1] + (3, 3))
+
+
+def quat_to_zyx(q: torch.Tensor) -> torch.Tensor:
+    """(w,x,y,z) -> [roll, pitch, yaw] float64 (utils/kinematics.py:40-49)."""
+    w, x, y, z = q.unbind(-1)
+    roll = torch.atan2(2 * (w * x + y * z), 1 - 2 * (x * x + y * y))
+    pitch = torch.asin(2 * (w * y - z * x))
+    yaw = torch.atan2(2 * (w * z + x * y), 1 - 2 * (y * y + z * z))
+    return torch.stack([roll, pitch, yaw], dim=-1)
+
+
+class BatchedModelPredictiveController:
+    def __init__(self, mpc_config, robot_config, num_envs: int, device="cuda:0", dtype=torch.float32, engine=None,
+                 **solver_knobs):
+        """`engine` is for dependency injection in tests (an object with MpcqEngine.solve's signature);
+        by default the CUDA engine is created and a missing GPU / library raises."""
+        c = extract_mpc_constants(mpc_config, robot_config)
+        self.num_envs = int(num_envs)
+        self.device = torch.device(device)
+        self.dtype = dtype
+        self.num_state, self.num_input = 13, 12
+        self.dt_control = c["dt_control"]
+        self.iterations_between_mpc = c["iterations_between_mpc"]
+        self.dt = c["dt"]
+        self.horizon = c["horizon"]
+        self.mu = c["mu"]
+        self.fz_max = c["fz_max"]
+        self.gravity = c["gravity"]
+        self.mass = c["mass"]
+        self.com_height_des = c["com_height_des"]
+        self.engine = engine if engine is not None else MpcqEngine(mpc_config, robot_config, dtype=dtype, device=device,
+                                                                   **solver_knobs)
+        B, dev = self.num_envs, self.device
+        f64 = dict(dtype=torch.float64, device=dev)
+        self.is_initialized = False
+        self.is_first_run = True
+        self.current_state = torch.zeros((B, 13), dtype=torch.float32, device=dev)
+        self.yaw = torch.zeros(B, **f64)
+        self.roll_init = torch.zeros(B, **f64)
+        self.pitch_init = torch.zeros(B, **f64)
+        self.xpos_base_desired = torch.zeros(B, **f64)
+        self.ypos_base_desired = torch.zeros(B, **f64)
+        self.yaw_desired = torch.zeros(B, **f64)
+        self.contact_forces = torch.zeros((B, 12), dtype=dtype, device=dev)
+        self.ref_traj = torch.zeros((B, 13 * self.horizon), dtype=torch.float32, device=dev)
+        self.last_result = None
+
+    # ---------------------------------------------------------------------------------------
+    def _t(self, a, shape):
+        t = torch.as_tensor(a, dtype=torch.float64, device=self.device) if not isinstance(a, torch.Tensor) \
+            else a.to(device=self.device, dtype=torch.float64)
+        return t.reshape(shape)
+
+    def update_robot_state(self, robot_data) -> None:
+        """mpc.py:55-79: current_state = [rpy, pos, omega, vel, -g] rounded to float32; yaw kept in float64."""
+        B = self.num_envs
+        quat = self._t(robot_data.quat_base, (B, 4))
+        rpy = quat_to_zyx(quat)
+        st = torch.cat([rpy, self._t(robot_data.pos_base, (B, 3)), self._t(robot_data.ang_vel_base, (B, 3)),
+                        self._t(robot_data.lin_vel_base, (B, 3)),
+                        torch.full((B, 1), -self.gravity, dtype=torch.float64, device=self.device)], dim=1)
+        self.current_state = st.to(torch.float32)
+        self.yaw = rpy[:, 2].clone()
+        self.pos_base_feet = self._t(robot_data.pos_base_feet, (B, 12))
+        R = getattr(robot_data, "R_base", None)
+        self.R_base = quat_to_matrix(quat) if R is None else self._t(R, (B, 3, 3))
+        self.is_initialized = True
+
+    def update_mpc_if_needed(self, iter_counter: int, base_vel_base_des, yaw_turn_rate_des, gait_table,
+                             solver: str = "drake", debug: bool = False, iter_debug=None):
+        """mpc.py:81-108.  `solver` is accepted for signature compatibility; the drake formulation
+        (lb <= Cu <= ub) is the one implemented.  Returns the cached [B,12] forces between MPC updates."""
+        assert solver in ("drake", "qpsolvers")
+        if solver == "qpsolvers":
+            raise NotImplementedError("the reference's qpsolvers branch drops lb and solves a different QP "
+                                      "(mpc.py:289); only the drake formulation is implemented")
+        B = self.num_envs
+        v_body = self._t(base_vel_base_des, (-1, 3)).expand(B, 3)
+        yaw_rate = self._t(yaw_turn_rate_des, (-1,)).expand(B)
+        vel_des = torch.einsum("bij,bj->bi", self.R_base, v_body)
+        if self.is_first_run:
+            self.xpos_base_desired = torch.zeros_like(self.xpos_base_desired)
+            self.ypos_base_desired = torch.zeros_like(self.ypos_base_desired)
+            self.yaw_desired = self.yaw.clone()
+            self.is_first_run = False
+        else:
+            self.xpos_base_desired = self.xpos_base_desired + self.dt_control * vel_des[:, 0]
+            self.ypos_base_desired = self.ypos_base_desired + self.dt_control * vel_des[:, 1]
+            self.yaw_desired = self.yaw + self.dt_control * yaw_rate
+        if iter_counter % self.iterations_between_mpc == 0:
+            self.ref_traj = self.generate_reference_trajectory(vel_des, yaw_rate)
+            self.contact_forces = self._solve_mpc(self.ref_traj, gait_table)
+        return self.contact_forces
+
+    def generate_reference_trajectory(self, vel_des: torch.Tensor, yaw_rate: torch.Tensor) -> torch.Tensor:
+        """mpc.py:110-170 with its float32 storage / float64 scalar arithmetic reproduced."""
+        x = self.current_state.to(torch.float64)            # float32 values
+        H, n, B = self.horizon, 13, self.num_envs
+        lim = 0.1
+        xd, yd = self.xpos_base_desired, self.ypos_base_desired
+        xd = torch.where(xd - x[:, 3] > lim, x[:, 3] + lim, xd)
+        xd = torch.where(x[:, 3] - xd > lim, x[:, 3] - lim, xd)
+        yd = torch.where(yd - x[:, 4] > lim, x[:, 4] + lim, yd)
+        yd = torch.where(x[:, 4] - yd > lim, x[:, 4] - lim, yd)
+        self.xpos_base_desired, self.ypos_base_desired = xd, yd
+        safe = lambda v: torch.where(v == 0, torch.ones_like(v), v)
+        self.pitch_init = torch.where(x[:, 9].abs() > 0.2, self.pitch_init + self.dt * (0.0 - x[:, 1]) / safe(x[:, 9]),
+                                      self.pitch_init)
+        self.roll_init = torch.where(x[:, 10].abs() > 0.1, self.roll_init + self.dt * (0.0 - x[:, 0]) / safe(x[:, 10]),
+                                     self.roll_init)
+        self.roll_init = self.roll_init.clamp(-0.25, 0.25)
+        self.pitch_init = self.pitch_init.clamp(-0.25, 0.25)
+        X = torch.zeros((B, H, n), dtype=torch.float32, device=self.device)
+        X[:, :, 0] = (x[:, 10] * self.roll_init).to(torch.float32)[:, None]
+        X[:, :, 1] = (x[:, 9] * self.pitch_init).to(torch.float32)[:, None]
+        X[:, :, 5] = self.com_height_des
+        X[:, :, 8] = yaw_rate.to(torch.float32)[:, None]
+        X[:, :, 9] = vel_des[:, 0].to(torch.float32)[:, None]
+        X[:, :, 10] = vel_des[:, 1].to(torch.float32)[:, None]
+        X[:, :, 12] = -self.gravity
+        X[:, 0, 2] = self.yaw_desired.to(torch.float32)
+        X[:, 0, 3] = xd.to(torch.float32)
+        X[:, 0, 4] = yd.to(torch.float32)
+        for i in range(1, H):                                # float32 storage, float64 increments
+            X[:, i, 2] = (X[:, i - 1, 2].to(torch.float64) + self.dt * yaw_rate).to(torch.float32)
+            X[:, i, 3] = (X[:, i - 1, 3].to(torch.float64) + self.dt * vel_des[:, 0]).to(torch.float32)
+            X[:, i, 4] = (X[:, i - 1, 4].to(torch.float64) + self.dt * vel_des[:, 1]).to(torch.float32)
+        return X.reshape(B, n * H)
+
+    def _solve_mpc(self, ref_traj: torch.Tensor, gait_table) -> torch.Tensor:
+        B, H = self.num_envs, self.horizon
+        gait = gait_table if isinstance(gait_table, torch.Tensor) else torch.as_tensor(np.asarray(gait_table))
+        gait = gait.to(device=self.device, dtype=torch.float32).reshape(-1, gait.shape[-1])[:, :4 * H]
+        if gait.shape[0] == 1 and B > 1:
+            gait = gait.expand(B, 4 * H)
+        res = self.engine.solve(self.current_state.to(self.dtype), self.pos_base_feet.to(self.dtype),
+                                gait.contiguous(), ref_traj.to(self.dtype), yaw=self.yaw.to(self.dtype))
+        self.last_result = res
+        return res.forces
+
+
+class ModelPredictiveController:
+    """Drop-in for the reference class (same constructor and method signatures, numpy in/out)."""
+
+    def __init__(self, mpc_config, robot_config, device="cuda:0", dtype=torch.float32, engine=None, **solver_knobs):
+        self._b = BatchedModelPredictiveController(mpc_config, robot_config, 1, device=device, dtype=dtype, engine=engine,
+                                                   **solver_knobs)
+        self.num_state, self.num_input = 13, 12
+
+    def __getattr__(self, name):                              # iterations_between_mpc, horizon, dt, ...
+        return getattr(self._b, name)
+
+    @property
+    def ref_traj(self):
+        return self._b.ref_traj[0].cpu().numpy()
+
+    def update_robot_state(self, robot_data) -> None:
+        rd = BatchedRobotData(np.asarray(robot_data.quat_base, dtype=np.float64)[None],
+                              np.asarray(robot_data.pos_base, dtype=np.float64)[None],
+                              np.asarray(robot_data.ang_vel_base, dtype=np.float64)[None],
+                              np.asarray(robot_data.lin_vel_base, dtype=np.float64)[None],
+                              np.stack([np.asarray(p, dtype=np.float64) for p in robot_data.pos_base_feet])[None],
+                              np.asarray(robot_data.R_base, dtype=np.float64)[None])
+        self._b.update_robot_state(rd)
+
+    def update_mpc_if_needed(self, iter_counter, base_vel_base_des, yaw_turn_rate_des, gait_table,
+                             solver="drake", debug=False, iter_debug=None) -> np.ndarray:
+        f = self._b.update_mpc_if_needed(iter_counter, np.asarray(base_vel_base_des, dtype=np.float64)[None],
+                                         np.asarray([yaw_turn_rate_des], dtype=np.float64),
+                                         np.asarray(gait_table, dtype=np.float32)[None], solver=solver)
+        return f[0].to(torch.float64).cpu().numpy()

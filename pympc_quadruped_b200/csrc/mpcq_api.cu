@@ -1,0 +1,338 @@
+// libmpcq.so: sm_100a kernels + the C ABI declared in include/mpcq.h.
+//
+// One warp (a 32-thread CTA) owns one environment; environments are split into size classes by
+// their number of stance foot-steps so that each class gets exactly the shared memory its dense
+// factor needs (occupancy follows the problem size, the hardware block scheduler balances the
+// very uneven per-env work).  A class kernel is launched over the whole batch; CTAs whose env
+// belongs to another class exit after reading its contact table.
+#include <cuda_runtime.h>
+#include <stdio.h>
+
+#include <new>
+#include <string>
+
+#include "mpcq_host.h"
+
+namespace {
+
+using mpcq::Consts;
+using mpcq::IO;
+
+constexpr size_t kMaxSmem = 227 * 1024;
+constexpr int kGlobalCtas = 148 * 2;       // resident CTAs of a class whose factor lives in global memory
+
+template <class T, int NCAP, bool LGLOBAL>
+__global__ void __launch_bounds__(32)
+mpcq_solve_kernel(const __grid_constant__ Consts cs, const __grid_constant__ IO<T> io, T* gws, size_t gws_stride,
+                  int ns_lo, int ns_hi) {
+    extern __shared__ __align__(32) char smem[];
+    T* lg = LGLOBAL ? gws + (size_t)blockIdx.x * gws_stride : nullptr;
+    for (int b = blockIdx.x; b < io.B; b += gridDim.x) {
+        mpcq::solve_env<T, NCAP>(cs, io, b, smem, lg, ns_lo, ns_hi);
+        __syncwarp();
+    }
+}
+
+// stage kernel for parity tests: dense (H, g, ub) exactly as the reference hands them to its solver
+template <class T>
+__global__ void __launch_bounds__(32)
+mpcq_build_qp_kernel(const __grid_constant__ Consts cs, const __grid_constant__ IO<T> io, double* Hout, double* gout,
+                     double* ubout) {
+    extern __shared__ __align__(32) char smem[];
+    const int b = blockIdx.x, lane = threadIdx.x, H = cs.horizon, n = 12 * H;
+    mpcq::Work<T> w;
+    mpcq::carve<T>(w, smem, nullptr, H, 64);
+    const double yaw = io.yaw ? (double)io.yaw[b] : (double)io.x0[(size_t)b * 13 + 2];
+    mpcq::setup_model(cs, w, io.x0 + (size_t)b * 13, yaw, io.r_feet + (size_t)b * 12, io.x_ref + (size_t)b * 13 * H);
+    double* Hb = Hout + (size_t)b * n * n;
+    for (int row = 0; row < n; ++row) {
+        const int i = row / 12, r = row - 12 * i;
+        for (int col = lane; col < n; col += 32) {
+            const int j = col / 12, c = col - 12 * j;
+            const int m = i > j ? i : j;
+            double v = 2.0 * ((double)(H - m) * w.Md[12 * r + c] + w.Sd[i * H + j] * w.Md[144 + 12 * r + c]);
+            if (row == col) v += 2.0 * cs.r[r];
+            Hb[(size_t)row * n + col] = v;
+        }
+    }
+    for (int idx = lane; idx < n; idx += 32) gout[(size_t)b * n + idx] = w.g[idx];
+    const float* gait = io.gait + (size_t)b * 4 * H;
+    for (int k = lane; k < 4 * H; k += 32) {
+        double* ub = ubout + (size_t)b * 20 * H + 5 * k;
+        ub[0] = ub[1] = ub[2] = ub[3] = (double)INFINITY;
+        ub[4] = (double)(float)((double)gait[k] * cs.fz_max);
+    }
+}
+
+}  // namespace
+
+struct mpcq_handle {
+    mpcq_config cfg;
+    Consts cs;
+    int ncls = 0;
+    size_t smem[4] = {0, 0, 0, 0};
+    bool lglobal[4] = {false, false, false, false};
+    void* gws = nullptr;                  // global-memory factors of the largest class
+    size_t gws_stride = 0;                // elements per CTA
+    size_t real_size = 4;
+    int last_launches = 0;
+    std::string err;
+    // staging for mpcq_solve_host
+    char* pin = nullptr;
+    char* dev = nullptr;
+    size_t stage_cap = 0;
+    cudaStream_t stream = nullptr;
+};
+
+namespace {
+thread_local std::string g_create_err;
+
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) {
+        cudaGetDevice(&prev);
+        if (prev != dev) cudaSetDevice(dev);
+    }
+    ~DeviceGuard() {
+        int cur = -1;
+        cudaGetDevice(&cur);
+        if (prev >= 0 && cur != prev) cudaSetDevice(prev);
+    }
+};
+
+bool cuda_ok(mpcq_handle* h, cudaError_t e, const char* what) {
+    if (e == cudaSuccess) return true;
+    char buf[256];
+    snprintf(buf, sizeof buf, "%s: %s", what, cudaGetErrorString(e));
+    if (h) h->err = buf; else g_create_err = buf;
+    return false;
+}
+
+template <class T, int NCAP, bool LG>
+cudaError_t launch_class(mpcq_handle* h, const IO<T>& io, int ci, cudaStream_t st) {
+    auto kern = mpcq_solve_kernel<T, NCAP, LG>;
+    const mpcq::SizeClass& sc = mpcq::kClasses[ci];
+    const int grid = LG ? (io.B < kGlobalCtas ? io.B : kGlobalCtas) : io.B;
+    kern<<<grid, 32, h->smem[ci], st>>>(h->cs, io, static_cast<T*>(h->gws), h->gws_stride, sc.ns_lo, sc.ns_hi);
+    return cudaGetLastError();
+}
+
+template <class T, int NCAP>
+cudaError_t launch_class_lg(mpcq_handle* h, const IO<T>& io, int ci, cudaStream_t st) {
+    return h->lglobal[ci] ? launch_class<T, NCAP, true>(h, io, ci, st) : launch_class<T, NCAP, false>(h, io, ci, st);
+}
+
+template <class T>
+cudaError_t launch_all(mpcq_handle* h, const IO<T>& io, cudaStream_t st) {
+    cudaError_t e = cudaSuccess;
+    h->last_launches = 0;
+    for (int ci = 0; ci < h->ncls && e == cudaSuccess; ++ci) {
+        switch (ci) {
+            case 0: e = launch_class_lg<T, 64>(h, io, ci, st); break;
+            case 1: e = launch_class_lg<T, 128>(h, io, ci, st); break;
+            case 2: e = launch_class_lg<T, 192>(h, io, ci, st); break;
+            default: e = launch_class_lg<T, 384>(h, io, ci, st); break;
+        }
+        ++h->last_launches;
+    }
+    return e;
+}
+
+template <class T, int NCAP>
+cudaError_t set_attr(mpcq_handle* h, int ci) {
+    cudaError_t e = cudaFuncSetAttribute(mpcq_solve_kernel<T, NCAP, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)(h->lglobal[ci] ? 0 : h->smem[ci]));
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(mpcq_solve_kernel<T, NCAP, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)(h->lglobal[ci] ? h->smem[ci] : 0));
+}
+
+template <class T>
+cudaError_t configure(mpcq_handle* h) {
+    const int H = h->cs.horizon;
+    h->ncls = mpcq::num_classes(H);
+    size_t gws_elems = 0;
+    for (int ci = 0; ci < h->ncls; ++ci) {
+        const int ncap = mpcq::kClasses[ci].ncap;
+        size_t s = mpcq::work_bytes<T>(H, ncap, true);
+        h->lglobal[ci] = s > kMaxSmem;
+        if (h->lglobal[ci]) {
+            s = mpcq::work_bytes<T>(H, ncap, false);
+            if (s > kMaxSmem) return cudaErrorInvalidValue;
+            size_t need = (size_t)mpcq::l_elems(ncap);
+            need = (need + 31) / 32 * 32;
+            if (need > gws_elems) gws_elems = need;
+        }
+        h->smem[ci] = s;
+    }
+    cudaError_t e = cudaSuccess;
+    for (int ci = 0; ci < h->ncls && e == cudaSuccess; ++ci) {
+        switch (ci) {
+            case 0: e = set_attr<T, 64>(h, ci); break;
+            case 1: e = set_attr<T, 128>(h, ci); break;
+            case 2: e = set_attr<T, 192>(h, ci); break;
+            default: e = set_attr<T, 384>(h, ci); break;
+        }
+    }
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(mpcq_build_qp_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)mpcq::work_bytes<T>(H, 64, true));
+    if (e != cudaSuccess) return e;
+    if (gws_elems) {
+        h->gws_stride = gws_elems;
+        e = cudaMalloc(&h->gws, gws_elems * sizeof(T) * kGlobalCtas);
+    }
+    return e;
+}
+
+template <class T>
+IO<T> make_io(int B, const void* x0, const void* yaw, const void* r_feet, const float* gait, const void* x_ref, void* f_out,
+              void* u_full, int32_t* iters, double* resid, int32_t* status, uint8_t* active) {
+    IO<T> io;
+    io.x0 = static_cast<const T*>(x0);
+    io.yaw = static_cast<const T*>(yaw);
+    io.r_feet = static_cast<const T*>(r_feet);
+    io.gait = gait;
+    io.x_ref = static_cast<const T*>(x_ref);
+    io.f_out = static_cast<T*>(f_out);
+    io.u_full = static_cast<T*>(u_full);
+    io.iters = iters;
+    io.resid = resid;
+    io.status = status;
+    io.active = active;
+    io.B = B;
+    return io;
+}
+
+}  // namespace
+
+extern "C" {
+
+int mpcq_version(void) { return MPCQ_VERSION; }
+
+const char* mpcq_last_error(const mpcq_handle* h) { return h ? h->err.c_str() : g_create_err.c_str(); }
+
+int mpcq_create(const mpcq_config* cfg, mpcq_handle** out) {
+    if (!cfg || !out) { g_create_err = "null argument"; return MPCQ_ERR_INVALID; }
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        g_create_err = "no CUDA device: libmpcq has no CPU path";
+        return MPCQ_ERR_NO_DEVICE;
+    }
+    if (cfg->device < 0 || cfg->device >= ndev) { g_create_err = "device ordinal out of range"; return MPCQ_ERR_INVALID; }
+    mpcq_handle* h = new (std::nothrow) mpcq_handle;
+    if (!h) { g_create_err = "out of host memory"; return MPCQ_ERR_INVALID; }
+    h->cfg = *cfg;
+    std::string err;
+    if (!mpcq::consts_from_config(*cfg, h->cs, err)) { g_create_err = err; delete h; return MPCQ_ERR_INVALID; }
+    h->real_size = cfg->dtype == MPCQ_F64 ? 8 : 4;
+    DeviceGuard guard(cfg->device);
+    cudaError_t e = cfg->dtype == MPCQ_F64 ? configure<double>(h) : configure<float>(h);
+    if (e == cudaErrorInvalidValue && !h->smem[0]) { g_create_err = "horizon needs more shared memory than one SM has"; delete h; return MPCQ_ERR_UNSUPPORTED; }
+    if (!cuda_ok(nullptr, e, "configure kernels")) { if (h->gws) cudaFree(h->gws); delete h; return MPCQ_ERR_CUDA; }
+    if (!cuda_ok(nullptr, cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking), "cudaStreamCreate")) {
+        if (h->gws) cudaFree(h->gws);
+        delete h;
+        return MPCQ_ERR_CUDA;
+    }
+    *out = h;
+    return MPCQ_OK;
+}
+
+void mpcq_destroy(mpcq_handle* h) {
+    if (!h) return;
+    DeviceGuard guard(h->cfg.device);
+    if (h->stream) { cudaStreamSynchronize(h->stream); cudaStreamDestroy(h->stream); }
+    if (h->gws) cudaFree(h->gws);
+    if (h->dev) cudaFree(h->dev);
+    if (h->pin) cudaFreeHost(h->pin);
+    delete h;
+}
+
+int mpcq_solve(mpcq_handle* h, int32_t B, const void* x0, const void* yaw, const void* r_feet, const float* gait,
+               const void* x_ref, void* f_out, void* u_full, int32_t* iters, double* resid, int32_t* status, uint8_t* active,
+               void* stream) {
+    if (!h) return MPCQ_ERR_INVALID;
+    if (B < 0 || (B > 0 && (!x0 || !r_feet || !gait || !x_ref || !f_out))) { h->err = "null input/output pointer"; return MPCQ_ERR_INVALID; }
+    h->last_launches = 0;
+    if (B == 0) return MPCQ_OK;
+    DeviceGuard guard(h->cfg.device);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    cudaError_t e;
+    if (h->cfg.dtype == MPCQ_F64)
+        e = launch_all<double>(h, make_io<double>(B, x0, yaw, r_feet, gait, x_ref, f_out, u_full, iters, resid, status, active), st);
+    else
+        e = launch_all<float>(h, make_io<float>(B, x0, yaw, r_feet, gait, x_ref, f_out, u_full, iters, resid, status, active), st);
+    return cuda_ok(h, e, "mpcq_solve launch") ? MPCQ_OK : MPCQ_ERR_CUDA;
+}
+
+int mpcq_build_qp(mpcq_handle* h, int32_t B, const void* x0, const void* yaw, const void* r_feet, const float* gait,
+                  const void* x_ref, double* H_out, double* g_out, double* ub_out, void* stream) {
+    if (!h) return MPCQ_ERR_INVALID;
+    if (B < 0 || (B > 0 && (!x0 || !r_feet || !gait || !x_ref || !H_out || !g_out || !ub_out))) { h->err = "null input/output pointer"; return MPCQ_ERR_INVALID; }
+    h->last_launches = 0;
+    if (B == 0) return MPCQ_OK;
+    DeviceGuard guard(h->cfg.device);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int H = h->cs.horizon;
+    if (h->cfg.dtype == MPCQ_F64) {
+        IO<double> io = make_io<double>(B, x0, yaw, r_feet, gait, x_ref, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
+        mpcq_build_qp_kernel<double><<<B, 32, mpcq::work_bytes<double>(H, 64, true), st>>>(h->cs, io, H_out, g_out, ub_out);
+    } else {
+        IO<float> io = make_io<float>(B, x0, yaw, r_feet, gait, x_ref, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
+        mpcq_build_qp_kernel<float><<<B, 32, mpcq::work_bytes<float>(H, 64, true), st>>>(h->cs, io, H_out, g_out, ub_out);
+    }
+    h->last_launches = 1;
+    return cuda_ok(h, cudaGetLastError(), "mpcq_build_qp launch") ? MPCQ_OK : MPCQ_ERR_CUDA;
+}
+
+int mpcq_solve_host(mpcq_handle* h, int32_t B, const void* x0, const void* yaw, const void* r_feet, const float* gait,
+                    const void* x_ref, void* f_out, void* u_full, int32_t* iters, double* resid, int32_t* status,
+                    uint8_t* active) {
+    if (!h) return MPCQ_ERR_INVALID;
+    if (B < 0 || (B > 0 && (!x0 || !r_feet || !gait || !x_ref || !f_out))) { h->err = "null input/output pointer"; return MPCQ_ERR_INVALID; }
+    h->last_launches = 0;
+    if (B == 0) return MPCQ_OK;
+    DeviceGuard guard(h->cfg.device);
+    const size_t rs = h->real_size, H = (size_t)h->cs.horizon, b = (size_t)B;
+    // staging layout: inputs first (one H2D copy), outputs after (one D2H copy)
+    size_t off[12], cur = 0;
+    const size_t sizes[12] = {b * 13 * rs, yaw ? b * rs : 0, b * 12 * rs, b * 4 * H * 4, b * 13 * H * rs,
+                              b * 12 * rs, u_full ? b * 12 * H * rs : 0, iters ? b * 8 : 0, resid ? b * 16 : 0,
+                              status ? b * 4 : 0, active ? b * 4 * H : 0, 0};
+    for (int i = 0; i < 12; ++i) { off[i] = cur; cur += (sizes[i] + 255) / 256 * 256; }
+    const size_t in_bytes = off[5], total = cur;
+    if (total > h->stage_cap) {
+        if (h->dev) cudaFree(h->dev);
+        if (h->pin) cudaFreeHost(h->pin);
+        h->dev = h->pin = nullptr;
+        h->stage_cap = 0;
+        if (!cuda_ok(h, cudaMalloc(&h->dev, total), "cudaMalloc staging")) return MPCQ_ERR_CUDA;
+        if (!cuda_ok(h, cudaMallocHost(&h->pin, total), "cudaMallocHost staging")) return MPCQ_ERR_CUDA;
+        h->stage_cap = total;
+    }
+    const void* src[5] = {x0, yaw, r_feet, gait, x_ref};
+    for (int i = 0; i < 5; ++i)
+        if (sizes[i]) memcpy(h->pin + off[i], src[i], sizes[i]);
+    cudaStream_t st = h->stream;
+    if (!cuda_ok(h, cudaMemcpyAsync(h->dev, h->pin, in_bytes, cudaMemcpyHostToDevice, st), "H2D")) return MPCQ_ERR_CUDA;
+    char* d = h->dev;
+    int rc = mpcq_solve(h, B, d + off[0], yaw ? d + off[1] : nullptr, d + off[2], reinterpret_cast<float*>(d + off[3]), d + off[4],
+                        d + off[5], u_full ? d + off[6] : nullptr, iters ? reinterpret_cast<int32_t*>(d + off[7]) : nullptr,
+                        resid ? reinterpret_cast<double*>(d + off[8]) : nullptr,
+                        status ? reinterpret_cast<int32_t*>(d + off[9]) : nullptr,
+                        active ? reinterpret_cast<uint8_t*>(d + off[10]) : nullptr, st);
+    if (rc != MPCQ_OK) return rc;
+    if (!cuda_ok(h, cudaMemcpyAsync(h->pin + in_bytes, d + in_bytes, total - in_bytes, cudaMemcpyDeviceToHost, st), "D2H")) return MPCQ_ERR_CUDA;
+    if (!cuda_ok(h, cudaStreamSynchronize(st), "mpcq_solve_host sync")) return MPCQ_ERR_CUDA;
+    void* dst[6] = {f_out, u_full, iters, resid, status, active};
+    for (int i = 0; i < 6; ++i)
+        if (sizes[5 + i]) memcpy(dst[i], h->pin + off[5 + i], sizes[5 + i]);
+    return MPCQ_OK;
+}
+
+int mpcq_last_launch_count(const mpcq_handle* h) { return h ? h->last_launches : 0; }
+
+}  // extern "C"

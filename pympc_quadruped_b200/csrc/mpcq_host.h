@@ -1,0 +1,54 @@
+// Host-side helpers shared by the C-ABI (mpcq_api.cu) and the test-only warp emulator:
+// public mpcq_config -> kernel constants, size classes.
+#pragma once
+
+#include <math.h>
+#include <string>
+
+#include "../../include/mpcq.h"
+#include "mpcq_core.cuh"
+
+namespace mpcq {
+
+// size classes by number of stance foot-steps (slot capacity = 3 * stance, rounded to 32 rows/lane)
+struct SizeClass { int ncap, ns_lo, ns_hi; };
+static const SizeClass kClasses[4] = {{64, 0, 21}, {128, 22, 42}, {192, 43, 64}, {384, 65, 128}};
+
+inline int num_classes(int horizon) {
+    int n = 1;
+    while (n < 4 && 4 * horizon >= kClasses[n].ns_lo) ++n;
+    return n;
+}
+
+inline bool consts_from_config(const mpcq_config& c, Consts& k, std::string& err) {
+    if (c.horizon < 1 || c.horizon > 32) { err = "horizon must be in 1..32"; return false; }
+    if (c.dtype != MPCQ_F32 && c.dtype != MPCQ_F64) { err = "dtype must be MPCQ_F32 or MPCQ_F64"; return false; }
+    if (!(c.dt > 0) || !(c.mu > 0) || !(c.fz_max >= 0) || !(c.mass > 0)) { err = "dt, mu, mass must be > 0 and fz_max >= 0"; return false; }
+    for (int i = 0; i < 12; ++i)
+        if (!(c.r_diag[i] > 0)) { err = "r_diag must be > 0 (strict convexity)"; return false; }
+    for (int i = 0; i < 13; ++i)
+        if (!(c.q_diag[i] >= 0)) { err = "q_diag must be >= 0"; return false; }
+    const bool f64 = c.dtype == MPCQ_F64;
+    k.horizon = c.horizon;
+    k.pdas_cap = c.max_pdas_rounds > 0 ? c.max_pdas_rounds : 8;
+    k.as_cap = c.max_as_iter > 0 ? c.max_as_iter : 12 * c.horizon + 30;
+    k.refine_max = c.max_refine > 0 ? c.max_refine : 8;
+    k.dt = c.dt; k.mu = c.mu; k.fz_max = c.fz_max;
+    k.inv_mass = (double)(float)(1.0 / c.mass);            // Bc[9:12] = I/m is stored in float32 (mpc.py:190)
+    for (int i = 0; i < 9; ++i) k.inertia[i] = c.inertia[i];
+    for (int i = 0; i < 13; ++i) k.q[i] = c.q_diag[i];
+    for (int i = 0; i < 12; ++i) k.r[i] = c.r_diag[i];
+    k.tol_p = c.tol_primal > 0 ? c.tol_primal : (f64 ? 1e-9 : 1e-7);
+    k.tol_d = c.tol_dual > 0 ? c.tol_dual : (f64 ? 1e-9 : 1e-7);
+    k.tol_r_tight = c.tol_residual > 0 ? c.tol_residual : (f64 ? 1e-12 : 1e-9);
+    k.tol_r_loose = f64 ? 1e-9 : 1e-6;
+    if (k.tol_r_loose < k.tol_r_tight) k.tol_r_loose = k.tol_r_tight;
+    k.tol_active = c.tol_active > 0 ? c.tol_active : 1e-6;
+    double det = c.inertia[0] * (c.inertia[4] * c.inertia[8] - c.inertia[5] * c.inertia[7]) -
+                 c.inertia[1] * (c.inertia[3] * c.inertia[8] - c.inertia[5] * c.inertia[6]) +
+                 c.inertia[2] * (c.inertia[3] * c.inertia[7] - c.inertia[4] * c.inertia[6]);
+    if (!(det > 0)) { err = "inertia must be positive definite"; return false; }
+    return true;
+}
+
+}  // namespace mpcq

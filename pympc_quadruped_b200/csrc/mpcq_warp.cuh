@@ -1,0 +1,95 @@
+// Warp-level primitives of the MPC QP engine.
+//
+// The solver is written warp-synchronously: one 32-lane warp owns one environment and all
+// cross-lane traffic goes through the handful of collectives below.  Under nvcc they are the
+// sm_100a intrinsics.  When the same source is compiled by g++ with MPCQ_HOST_EMU (tests/emu
+// only - a debugging harness for the device code, never linked into libmpcq.so) the 32 lanes
+// run as cooperative coroutines and the collectives are a lock-step exchange, so the kernel
+// logic can be unit-tested in the CPU-only build container.
+#pragma once
+
+#include <math.h>
+#include <stdint.h>
+#include <string.h>
+
+#ifdef MPCQ_HOST_EMU
+#define MPCQ_DEV inline
+#define MPCQ_HD inline
+#define MPCQ_UNROLL
+namespace mpcq_emu {
+int lane_id();
+uint64_t exchange(uint64_t v, int src);   // every lane publishes v, returns the value of lane `src`
+}
+#else
+#include <cuda_runtime.h>
+#define MPCQ_DEV __device__ __forceinline__
+#define MPCQ_HD __host__ __device__ inline
+#define MPCQ_UNROLL _Pragma("unroll")
+#endif
+
+namespace wp {
+
+constexpr unsigned FULL = 0xffffffffu;
+
+#ifdef MPCQ_HOST_EMU
+MPCQ_DEV int lane() { return mpcq_emu::lane_id(); }
+MPCQ_DEV void sync() { mpcq_emu::exchange(0, 0); }
+template <class V> MPCQ_DEV V shfl(V v, int src) {
+    static_assert(sizeof(V) <= 8, "shfl payload");
+    uint64_t raw = 0;
+    memcpy(&raw, &v, sizeof(V));
+    raw = mpcq_emu::exchange(raw, src & 31);
+    V out;
+    memcpy(&out, &raw, sizeof(V));
+    return out;
+}
+template <class V> MPCQ_DEV V shfl_xor(V v, int m) { return shfl(v, lane() ^ m); }
+MPCQ_DEV unsigned ballot(bool p) {
+    unsigned out = 0;
+    for (int l = 0; l < 32; ++l) out |= (shfl<int>(p ? 1 : 0, l) ? 1u : 0u) << l;
+    return out;
+}
+MPCQ_DEV int popc(unsigned x) { return __builtin_popcount(x); }
+MPCQ_DEV float rsqrt_(float x) { return 1.0f / sqrtf(x); }
+MPCQ_DEV double rsqrt_(double x) { return 1.0 / sqrt(x); }
+#else
+MPCQ_DEV int lane() { return threadIdx.x & 31; }
+MPCQ_DEV void sync() { __syncwarp(); }
+template <class V> MPCQ_DEV V shfl(V v, int src) { return __shfl_sync(FULL, v, src); }
+template <class V> MPCQ_DEV V shfl_xor(V v, int m) { return __shfl_xor_sync(FULL, v, m); }
+MPCQ_DEV unsigned ballot(bool p) { return __ballot_sync(FULL, p); }
+MPCQ_DEV int popc(unsigned x) { return __popc(x); }
+// full-precision reciprocal square roots (the approximate rsqrtf is 2 ulp: not good enough
+// for a factor whose condition number is 1e5)
+MPCQ_DEV float rsqrt_(float x) { return 1.0f / sqrtf(x); }
+MPCQ_DEV double rsqrt_(double x) { return 1.0 / sqrt(x); }
+#endif
+
+MPCQ_DEV bool any(bool p) { return ballot(p) != 0u; }
+MPCQ_DEV bool all(bool p) { return ballot(p) == FULL; }
+
+template <class V> MPCQ_DEV V reduce_max(V v) {
+    MPCQ_UNROLL
+    for (int m = 16; m > 0; m >>= 1) {
+        V o = shfl_xor(v, m);
+        v = o > v ? o : v;
+    }
+    return v;
+}
+template <class V> MPCQ_DEV V reduce_sum(V v) {
+    MPCQ_UNROLL
+    for (int m = 16; m > 0; m >>= 1) v += shfl_xor(v, m);
+    return v;
+}
+// (value, payload) arg-min; ties resolved towards the smaller payload so the result is
+// independent of lane order
+MPCQ_DEV void reduce_argmin(double& v, int& tag) {
+    MPCQ_UNROLL
+    for (int m = 16; m > 0; m >>= 1) {
+        double ov = shfl_xor(v, m);
+        int ot = shfl_xor(tag, m);
+        if (ov < v || (ov == v && ot < tag)) { v = ov; tag = ot; }
+    }
+}
+
+}  // namespace wp

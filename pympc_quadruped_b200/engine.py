@@ -1,0 +1,153 @@
+"""Device-side engine handle: torch tensors in, torch tensors out, through the C ABI.
+
+`MpcqEngine.solve` is the batched replacement of `ModelPredictiveController._solve_mpc`
+(reference linear_mpc/mpc.py:262-290).  torch is used for device memory and streams only;
+all arithmetic happens inside libmpcq.so (sm_100a kernels).  No CPU path exists.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+import numpy as np
+import torch
+
+from . import _capi
+from .configs import extract_mpc_constants
+
+
+@dataclass
+class SolveResult:
+    forces: torch.Tensor          # [B,12]  first-step GRFs  (= _solve_mpc(...)[0:12])
+    u: torch.Tensor | None        # [B,12H] whole optimum
+    iters: torch.Tensor | None    # [B,2]   factorisations, fallback iterations
+    resid: torch.Tensor | None    # [B,2]   reduced gradient, primal violation (fp64)
+    status: torch.Tensor | None   # [B]     MPCQ_ST_* bits
+    active: torch.Tensor | None   # [B,4H]  constraint-activity bit masks
+
+
+def _ptr(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+class MpcqEngine:
+    """One handle per (config, robot, dtype, device)."""
+
+    def __init__(self, mpc_config, robot_config, dtype=torch.float32, device="cuda:0", **knobs):
+        if dtype not in (torch.float32, torch.float64):
+            raise ValueError("dtype must be torch.float32 or torch.float64")
+        self.lib = _capi.load_library()
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError("MpcqEngine needs a CUDA device: the engine has no CPU fallback")
+        self.dtype = dtype
+        self.consts = extract_mpc_constants(mpc_config, robot_config)
+        self.horizon = self.consts["horizon"]
+        cfg = _capi.make_config(self.consts, _capi.MPCQ_F64 if dtype == torch.float64 else _capi.MPCQ_F32,
+                                self.device.index or 0, **knobs)
+        self._h = C.c_void_p()
+        rc = self.lib.mpcq_create(C.byref(cfg), C.byref(self._h))
+        if rc != 0:
+            raise RuntimeError(f"mpcq_create failed ({rc}): {self.lib.mpcq_last_error(None).decode()}")
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            self.lib.mpcq_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---------------------------------------------------------------------------------------
+    def _check(self, name, t, shape, dtype):
+        if not isinstance(t, torch.Tensor):
+            raise TypeError(f"{name} must be a torch.Tensor")
+        if t.device != self.device:
+            raise ValueError(f"{name} is on {t.device}, engine is on {self.device}")
+        if t.dtype != dtype:
+            raise TypeError(f"{name} must be {dtype}, got {t.dtype}")
+        if tuple(t.shape) != tuple(shape):
+            raise ValueError(f"{name} must have shape {tuple(shape)}, got {tuple(t.shape)}")
+        return t.contiguous()
+
+    def _err(self, rc, what):
+        if rc != 0:
+            raise RuntimeError(f"{what} failed ({rc}): {self.lib.mpcq_last_error(self._h).decode()}")
+
+    def solve(self, x0, r_feet, gait, x_ref, yaw=None, want=("u", "iters", "resid", "status", "active"), out=None):
+        """x0 [B,13], r_feet [B,12] or [B,4,3], gait float32 [B,4H], x_ref [B,13H], yaw [B] optional."""
+        B, H = x0.shape[0], self.horizon
+        x0 = self._check("x0", x0, (B, 13), self.dtype)
+        r_feet = self._check("r_feet", r_feet.reshape(B, 12), (B, 12), self.dtype)
+        gait = self._check("gait", gait, (B, 4 * H), torch.float32)
+        x_ref = self._check("x_ref", x_ref, (B, 13 * H), self.dtype)
+        if yaw is not None:
+            yaw = self._check("yaw", yaw, (B,), self.dtype)
+        if out is None:
+            mk = lambda shape, dt: torch.empty(shape, dtype=dt, device=self.device)
+            out = SolveResult(
+                forces=mk((B, 12), self.dtype),
+                u=mk((B, 12 * H), self.dtype) if "u" in want else None,
+                iters=mk((B, 2), torch.int32) if "iters" in want else None,
+                resid=mk((B, 2), torch.float64) if "resid" in want else None,
+                status=mk((B,), torch.int32) if "status" in want else None,
+                active=mk((B, 4 * H), torch.uint8) if "active" in want else None)
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        rc = self.lib.mpcq_solve(self._h, B, _ptr(x0), _ptr(yaw), _ptr(r_feet), _ptr(gait), _ptr(x_ref),
+                                 _ptr(out.forces), _ptr(out.u), _ptr(out.iters), _ptr(out.resid), _ptr(out.status),
+                                 _ptr(out.active), C.c_void_p(stream))
+        self._err(rc, "mpcq_solve")
+        return out
+
+    def solve_host(self, x0, r_feet, gait, x_ref, yaw=None, want=("status",)):
+        """numpy in / numpy out through `mpcq_solve_host` (H2D + solve + D2H inside the call)."""
+        rt = np.float64 if self.dtype == torch.float64 else np.float32
+        B, H = x0.shape[0], self.horizon
+        x0 = np.ascontiguousarray(x0, dtype=rt).reshape(B, 13)
+        r_feet = np.ascontiguousarray(r_feet, dtype=rt).reshape(B, 12)
+        gait = np.ascontiguousarray(gait, dtype=np.float32).reshape(B, 4 * H)
+        x_ref = np.ascontiguousarray(x_ref, dtype=rt).reshape(B, 13 * H)
+        yaw = None if yaw is None else np.ascontiguousarray(yaw, dtype=rt).reshape(B)
+        res = dict(forces=np.empty((B, 12), rt))
+        if "u" in want:
+            res["u"] = np.empty((B, 12 * H), rt)
+        if "iters" in want:
+            res["iters"] = np.empty((B, 2), np.int32)
+        if "resid" in want:
+            res["resid"] = np.empty((B, 2), np.float64)
+        if "status" in want:
+            res["status"] = np.empty(B, np.int32)
+        if "active" in want:
+            res["active"] = np.empty((B, 4 * H), np.uint8)
+        p = lambda a: None if a is None else a.ctypes.data_as(C.c_void_p)
+        rc = self.lib.mpcq_solve_host(self._h, B, p(x0), p(yaw), p(r_feet), p(gait), p(x_ref), p(res["forces"]),
+                                      p(res.get("u")), p(res.get("iters")), p(res.get("resid")), p(res.get("status")),
+                                      p(res.get("active")))
+        self._err(rc, "mpcq_solve_host")
+        return res
+
+    def build_qp(self, x0, r_feet, gait, x_ref, yaw=None):
+        """Dense (H [B,n,n], g [B,n], ub [B,20H]) in float64 - the data the reference hands to its solver."""
+        B, H = x0.shape[0], self.horizon
+        n = 12 * H
+        x0 = self._check("x0", x0, (B, 13), self.dtype)
+        r_feet = self._check("r_feet", r_feet.reshape(B, 12), (B, 12), self.dtype)
+        gait = self._check("gait", gait, (B, 4 * H), torch.float32)
+        x_ref = self._check("x_ref", x_ref, (B, 13 * H), self.dtype)
+        if yaw is not None:
+            yaw = self._check("yaw", yaw, (B,), self.dtype)
+        Hm = torch.empty((B, n, n), dtype=torch.float64, device=self.device)
+        g = torch.empty((B, n), dtype=torch.float64, device=self.device)
+        ub = torch.empty((B, 20 * H), dtype=torch.float64, device=self.device)
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        rc = self.lib.mpcq_build_qp(self._h, B, _ptr(x0), _ptr(yaw), _ptr(r_feet), _ptr(gait), _ptr(x_ref),
+                                    _ptr(Hm), _ptr(g), _ptr(ub), C.c_void_p(stream))
+        self._err(rc, "mpcq_build_qp")
+        return Hm, g, ub
+
+    @property
+    def last_launch_count(self) -> int:
+        return int(self.lib.mpcq_last_launch_count(self._h))

@@ -1,0 +1,141 @@
+// TEST HARNESS ONLY - lock-step host emulation of one warp, for unit-testing the device code of
+// pympc_quadruped_b200/csrc/mpcq_core.cuh in the CPU-only build container.  The product
+// (libmpcq.so) never contains or loads this file: it has no CPU path.  Built by tests/emu/build.py
+// into tests/emu/_build/libmpcq_emu.so and used only by `-m "not gpu"` tests.
+//
+// The 32 lanes of a warp run as coroutines (ucontext) on one thread, switched round-robin at
+// every warp collective; values are exchanged through a double-buffered slot array.
+#define MPCQ_HOST_EMU 1
+#include <stdint.h>
+#include <stdlib.h>
+#include <ucontext.h>
+
+#include <vector>
+
+#include "../../pympc_quadruped_b200/csrc/mpcq_host.h"
+
+namespace mpcq_emu {
+static ucontext_t main_ctx, ctx[32];
+static int cur = 0;
+static uint64_t slots[2][32];
+static long gen[32];
+static bool finished[32];
+static void (*lane_fn)(void*) = nullptr;
+static void* lane_arg = nullptr;
+
+int lane_id() { return cur; }
+
+static void yield_next() {
+    int old = cur;
+    for (int step = 1; step <= 32; ++step) {
+        int nxt = (old + step) & 31;
+        if (!finished[nxt]) {
+            if (nxt == old) return;
+            cur = nxt;
+            swapcontext(&ctx[old], &ctx[nxt]);
+            return;
+        }
+    }
+    // everyone finished
+    cur = old;
+    swapcontext(&ctx[old], &main_ctx);
+}
+
+uint64_t exchange(uint64_t v, int src) {
+    const long g = gen[cur];
+    slots[g & 1][cur] = v;
+    gen[cur] = g + 1;
+    for (;;) {
+        bool all = true;
+        for (int l = 0; l < 32; ++l)
+            if (!finished[l] && gen[l] <= g) { all = false; break; }
+        if (all) break;
+        yield_next();
+    }
+    return slots[g & 1][src];
+}
+
+static void trampoline() {
+    lane_fn(lane_arg);
+    finished[cur] = true;
+    for (;;) yield_next();
+}
+
+void run_warp(void (*fn)(void*), void* arg) {
+    static std::vector<char> stacks;
+    const size_t STK = 512 * 1024;
+    if (stacks.empty()) stacks.resize(32 * STK);
+    lane_fn = fn;
+    lane_arg = arg;
+    for (int l = 0; l < 32; ++l) {
+        finished[l] = false;
+        gen[l] = 0;
+        getcontext(&ctx[l]);
+        ctx[l].uc_stack.ss_sp = stacks.data() + l * STK;
+        ctx[l].uc_stack.ss_size = STK;
+        ctx[l].uc_link = &main_ctx;
+        makecontext(&ctx[l], trampoline, 0);
+    }
+    cur = 0;
+    swapcontext(&main_ctx, &ctx[0]);
+}
+}  // namespace mpcq_emu
+
+namespace {
+template <class T> struct Job {
+    mpcq::Consts cs;
+    mpcq::IO<T> io;
+    int b;
+    char* smem;
+    T* lglobal;
+    int ncap;
+};
+
+template <class T> void lane_entry(void* p) {
+    Job<T>* j = static_cast<Job<T>*>(p);
+    const mpcq::SizeClass& sc = mpcq::kClasses[j->ncap];
+    switch (j->ncap) {
+        case 0: mpcq::solve_env<T, 64>(j->cs, j->io, j->b, j->smem, j->lglobal, sc.ns_lo, sc.ns_hi); break;
+        case 1: mpcq::solve_env<T, 128>(j->cs, j->io, j->b, j->smem, j->lglobal, sc.ns_lo, sc.ns_hi); break;
+        case 2: mpcq::solve_env<T, 192>(j->cs, j->io, j->b, j->smem, j->lglobal, sc.ns_lo, sc.ns_hi); break;
+        default: mpcq::solve_env<T, 384>(j->cs, j->io, j->b, j->smem, j->lglobal, sc.ns_lo, sc.ns_hi); break;
+    }
+}
+
+template <class T>
+int run(const mpcq_config* cfg, int B, const T* x0, const T* yaw, const T* feet, const float* gait, const T* xref,
+        T* f_out, T* u_full, int32_t* iters, double* resid, int32_t* status, uint8_t* active) {
+    mpcq::Consts consts;
+    std::string err;
+    if (!mpcq::consts_from_config(*cfg, consts, err)) return MPCQ_ERR_INVALID;
+    const mpcq::Consts* cs = &consts;
+    for (int ci = 0; ci < mpcq::num_classes(cs->horizon); ++ci) {
+        const int ncap = mpcq::kClasses[ci].ncap;
+        std::vector<char> smem(mpcq::work_bytes<T>(cs->horizon, ncap, true) + 64);
+        for (int b = 0; b < B; ++b) {
+            Job<T> j;
+            j.cs = *cs;
+            j.io = mpcq::IO<T>{x0, yaw, feet, gait, xref, f_out, u_full, iters, resid, status, active, B};
+            j.b = b;
+            j.smem = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(smem.data()) + 31) & ~uintptr_t(31));
+            j.lglobal = nullptr;
+            j.ncap = ci;
+            mpcq_emu::run_warp(lane_entry<T>, &j);
+        }
+    }
+    return 0;
+}
+}  // namespace
+
+extern "C" {
+int mpcq_emu_solve_f32(const mpcq_config* cs, int B, const float* x0, const float* yaw, const float* feet, const float* gait,
+                       const float* xref, float* f_out, float* u_full, int32_t* iters, double* resid, int32_t* status,
+                       uint8_t* active) {
+    return run<float>(cs, B, x0, yaw, feet, gait, xref, f_out, u_full, iters, resid, status, active);
+}
+int mpcq_emu_solve_f64(const mpcq_config* cs, int B, const double* x0, const double* yaw, const double* feet, const float* gait,
+                       const double* xref, double* f_out, double* u_full, int32_t* iters, double* resid, int32_t* status,
+                       uint8_t* active) {
+    return run<double>(cs, B, x0, yaw, feet, gait, xref, f_out, u_full, iters, resid, status, active);
+}
+}

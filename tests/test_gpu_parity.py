@@ -1,0 +1,177 @@
+"""GPU parity: the sm_100a path (through the C ABI) against the oracle on identical seeded inputs.
+
+Tolerance (BASELINE.json north_star): |df| <= 1e-3 N or 1e-4 relative, KKT residual <= 1e-6 in
+fp64 mode, constraint activity identical.  The oracle is the reference's own QP construction
+(restated, pinned in test_oracle_golden.py) + an exact fp64 solve.
+"""
+import numpy as np
+import pytest
+import torch
+
+from helpers import make_batch
+from oracle.qp_exact import kkt_report
+from pympc_quadruped_b200 import A1Config, AliengoConfig, Gait
+from pympc_quadruped_b200 import _capi
+from pympc_quadruped_b200.synth import GAIT_MIX
+
+pytestmark = pytest.mark.gpu
+
+ABS_TOL, REL_TOL = 1e-3, 1e-4
+
+CASES = [
+    # name, robot, horizon, B, regime, gaits, dtype, seed
+    ("a1_trot_h10_f32", A1Config, 10, 96, "mixed", (Gait.TROTTING10,), torch.float32, 11),
+    ("aliengo_mix_h10_f64", AliengoConfig, 10, 96, "mixed", GAIT_MIX, torch.float64, 12),
+    ("aliengo_mix_h10_f32_aggr", AliengoConfig, 10, 64, "aggressive", GAIT_MIX, torch.float32, 13),
+    ("a1_stand_h10_f32", A1Config, 10, 48, "mixed", (Gait.STANDING,), torch.float32, 14),
+    ("a1_h16_gaits_f32", A1Config, 16, 32, "mixed", (Gait.TROTTING16, Gait.STANDING, Gait.JUMPING16, Gait.PACING16), torch.float32, 15),
+    ("a1_trot_h30_f32", A1Config, 30, 24, "mixed", (Gait.TROTTING10,), torch.float32, 16),
+    ("a1_trot_h30_f64", A1Config, 30, 16, "mixed", (Gait.TROTTING10,), torch.float64, 17),
+    ("a1_stand_h30_f64", A1Config, 30, 6, "mixed", (Gait.STANDING,), torch.float64, 18),
+]
+
+
+def _engine(batch, robot, dtype):
+    from pympc_quadruped_b200.engine import MpcqEngine
+    return MpcqEngine(batch["cfg"], robot, dtype=dtype, device="cuda:0")
+
+
+def _to_dev(batch, dtype):
+    dev = "cuda:0"
+    t = lambda a, dt: torch.as_tensor(a).to(device=dev, dtype=dt)
+    return (t(batch["x0"], dtype), t(batch["feet"], dtype), t(batch["gait"], torch.float32), t(batch["xref"], dtype),
+            t(batch["yaw"], dtype))
+
+
+def _activity(active_row, H):
+    lo = ((active_row[:, None] >> np.arange(5)[None, :]) & 1).astype(bool).reshape(-1)
+    up = np.zeros(20 * H, dtype=bool)
+    up[4::5] = (active_row >> 5) & 1
+    return lo, up
+
+
+@pytest.mark.parametrize("name,robot,H,B,regime,gaits,dtype,seed", CASES, ids=[c[0] for c in CASES])
+def test_solve_matches_oracle(name, robot, H, B, regime, gaits, dtype, seed):
+    batch = make_batch(robot, H, B, regime, gaits, seed)
+    eng = _engine(batch, robot, dtype)
+    x0, feet, gait, xref, yaw = _to_dev(batch, dtype)
+    res = eng.solve(x0, feet, gait, xref, yaw=yaw)
+    torch.cuda.synchronize()
+    u = res.u.double().cpu().numpy()
+    f = res.forces.double().cpu().numpy()
+    status = res.status.cpu().numpy()
+    active = res.active.cpu().numpy()
+    resid = res.resid.cpu().numpy()
+    assert np.all(status & _capi.ST_VERIFIED), f"unverified envs: {np.flatnonzero(~(status & 1).astype(bool))} status {status}"
+    assert not np.any(status & (_capi.ST_NUMERIC | _capi.ST_MAXITER))
+    worst = 0.0
+    for b in range(B):
+        sol = batch["sols"][b]
+        assert np.array_equal(f[b], u[b, :12])
+        tol = np.maximum(ABS_TOL, REL_TOL * np.abs(sol.u).max())
+        err = np.abs(u[b] - sol.u).max()
+        worst = max(worst, err / tol)
+        assert err <= tol, f"env {b}: |du| = {err:.3e} > {tol:.3e}"
+        lo, up = _activity(active[b], H)
+        assert np.array_equal(lo, sol.active_lower), f"env {b}: lower-bound activity differs"
+        assert np.array_equal(up, sol.active_upper), f"env {b}: upper-bound activity differs"
+        # independent KKT check of the GPU point against the REFERENCE-constructed (H, g)
+        Hm, g, ub = batch["qps"][b]
+        stat, prim, _, _ = kkt_report(Hm, g, 0.7, ub[4::5], u[b])
+        assert prim <= (1e-9 if dtype == torch.float64 else 1e-5)      # f32: output rounding of ~50 N forces
+        assert stat <= (1e-6 if dtype == torch.float64 else 2e-5) * (1.0 + np.abs(g).max())
+    if dtype == torch.float64:
+        assert resid[:, 0].max() <= 1e-6 and resid[:, 1].max() <= 1e-9
+    print(f"{name}: worst err/tol = {worst:.3f}, factorisations mean {res.iters[:, 0].float().mean():.2f} "
+          f"max {int(res.iters[:, 0].max())}, fallback envs {int((status & 2).astype(bool).sum())}")
+
+
+def test_build_qp_matches_reference_construction():
+    batch = make_batch(A1Config, 10, 16, "mixed", (Gait.TROTTING10, Gait.STANDING), 21)
+    for dtype in (torch.float32, torch.float64):
+        eng = _engine(batch, A1Config, dtype)
+        x0, feet, gait, xref, yaw = _to_dev(batch, dtype)
+        Hm, g, ub = eng.build_qp(x0, feet, gait, xref, yaw=yaw)
+        torch.cuda.synchronize()
+        Hm, g, ub = Hm.cpu().numpy(), g.cpu().numpy(), ub.cpu().numpy()
+        for b in range(batch["B"]):
+            Href, gref, ubref = batch["qps"][b]
+            assert np.abs(Hm[b] - Href).max() <= 2e-6 * np.abs(Href).max()
+            assert np.abs(g[b] - gref).max() <= 2e-6 * np.abs(gref).max()
+            assert np.array_equal(ub[b], ubref.astype(np.float64))
+            assert np.array_equal(Hm[b], Hm[b].T)
+
+
+def test_golden_known_answers():
+    """SURVEY 8c.3 known-answer states stored in tests/golden (generated from the unmodified reference)."""
+    import os
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_h10.npz"))
+    from pympc_quadruped_b200 import with_horizon
+    from pympc_quadruped_b200.engine import MpcqEngine
+    for robot_name, robot in (("A1", A1Config), ("Aliengo", AliengoConfig)):
+        tags = sorted({k.split("/")[1] for k in z.keys() if k.startswith(robot_name + "/")} - {"seq"})
+        for dtype in (torch.float32, torch.float64):
+            eng = MpcqEngine(with_horizon(10), robot, dtype=dtype)
+            t = lambda a, dt=dtype: torch.as_tensor(np.stack(a)).to(device="cuda:0", dtype=dt)
+            x0 = t([z[f"{robot_name}/{g}/current_state"] for g in tags])
+            feet = t([z[f"{robot_name}/{g}/pos_base_feet"].reshape(12) for g in tags])
+            gait = t([z[f"{robot_name}/{g}/gait_table"][:40] for g in tags], torch.float32)
+            xref = t([z[f"{robot_name}/{g}/x_ref"] for g in tags])
+            yaw = t([z[f"{robot_name}/{g}/yaw"] for g in tags])
+            res = eng.solve(x0, feet, gait, xref, yaw=yaw)
+            u = res.u.double().cpu().numpy()
+            for i, g in enumerate(tags):
+                ustar = z[f"{robot_name}/{g}/u_star__oracle"]
+                tol = max(ABS_TOL, REL_TOL * np.abs(ustar).max())
+                assert np.abs(u[i] - ustar).max() <= tol, (robot_name, g)
+
+
+def test_host_entry_point_equals_device_entry_point():
+    batch = make_batch(A1Config, 10, 33, "mixed", (Gait.TROTTING10,), 31, solve=False)
+    eng = _engine(batch, A1Config, torch.float32)
+    x0, feet, gait, xref, yaw = _to_dev(batch, torch.float32)
+    res = eng.solve(x0, feet, gait, xref, yaw=yaw)
+    host = eng.solve_host(batch["x0"], batch["feet"], batch["gait"], batch["xref"], yaw=batch["yaw"],
+                          want=("u", "iters", "resid", "status", "active"))
+    assert np.array_equal(host["forces"], res.forces.cpu().numpy())
+    assert np.array_equal(host["u"], res.u.cpu().numpy())
+    assert np.array_equal(host["status"], res.status.cpu().numpy())
+    assert np.array_equal(host["active"], res.active.cpu().numpy())
+    assert np.array_equal(host["iters"], res.iters.cpu().numpy())
+
+
+def test_edge_cases_empty_batch_all_swing_and_errors():
+    from pympc_quadruped_b200 import with_horizon
+    from pympc_quadruped_b200.engine import MpcqEngine
+    eng = MpcqEngine(with_horizon(10), A1Config)
+    dev = "cuda:0"
+    z = lambda *s: torch.zeros(s, device=dev)
+    res = eng.solve(z(0, 13), z(0, 12), z(0, 40), z(0, 130))
+    assert res.forces.shape == (0, 12)
+    # all-swing contact table: u = 0, flagged
+    batch = make_batch(A1Config, 10, 4, "nominal", (Gait.TROTTING10,), 41, solve=False)
+    x0, feet, gait, xref, yaw = _to_dev(batch, torch.float32)
+    res = eng.solve(x0, feet, torch.zeros_like(gait), xref, yaw=yaw)
+    assert torch.all(res.forces == 0) and torch.all(res.status & _capi.ST_NO_STANCE)
+    assert torch.all(res.active == 0x3F)
+    with pytest.raises(ValueError):
+        eng.solve(x0, feet, gait[:, :20], xref)
+    with pytest.raises(TypeError):
+        eng.solve(x0.double(), feet, gait, xref)
+    with pytest.raises(ValueError):
+        MpcqEngine(with_horizon(40), A1Config)
+
+
+def test_batch_permutation_and_split_invariance():
+    """Environments are independent: any split / order of the batch gives bitwise-equal results
+    (this is what makes the multi-GPU sharding exact)."""
+    batch = make_batch(A1Config, 10, 64, "mixed", (Gait.TROTTING10, Gait.STANDING), 51, solve=False)
+    eng = _engine(batch, A1Config, torch.float32)
+    x0, feet, gait, xref, yaw = _to_dev(batch, torch.float32)
+    full = eng.solve(x0, feet, gait, xref, yaw=yaw).u.clone()
+    perm = torch.randperm(64, device="cuda:0", generator=torch.Generator(device="cuda:0").manual_seed(0))
+    p = eng.solve(x0[perm], feet[perm], gait[perm], xref[perm], yaw=yaw[perm]).u
+    assert torch.equal(p, full[perm])
+    lo = eng.solve(x0[:20], feet[:20], gait[:20], xref[:20], yaw=yaw[:20]).u.clone()
+    hi = eng.solve(x0[20:], feet[20:], gait[20:], xref[20:], yaw=yaw[20:]).u
+    assert torch.equal(torch.cat([lo, hi]), full)

@@ -1,0 +1,91 @@
+"""CPU tests of the DEVICE code: pympc_quadruped_b200/csrc/mpcq_core.cuh compiled by g++ with the
+warp emulated as 32 lock-step coroutines (tests/emu).  Same source, same arithmetic as the sm_100a
+kernels apart from the lane scheduling, so these tests pin the kernel logic (model assembly,
+panel Cholesky, triangular solves, face updates, fallback) against the oracle without a GPU.
+The emulator is test infrastructure: the package never loads it."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from helpers import make_batch
+from pympc_quadruped_b200 import A1Config, AliengoConfig, Gait, _capi
+from pympc_quadruped_b200.configs import extract_mpc_constants
+from pympc_quadruped_b200.synth import GAIT_MIX
+
+
+def emu_solve(lib, batch, robot, f64, **knobs):
+    B, H = batch["B"], batch["horizon"]
+    cfg = _capi.make_config(extract_mpc_constants(batch["cfg"], robot), _capi.MPCQ_F64 if f64 else _capi.MPCQ_F32, **knobs)
+    rt = np.float64 if f64 else np.float32
+    x0, yaw, feet, xref = (batch[k].astype(rt) for k in ("x0", "yaw", "feet", "xref"))
+    gait = np.ascontiguousarray(batch["gait"], dtype=np.float32)
+    out = dict(f=np.zeros((B, 12), rt), u=np.zeros((B, 12 * H), rt), iters=np.zeros((B, 2), np.int32),
+               resid=np.zeros((B, 2)), status=np.zeros(B, np.int32), active=np.zeros((B, 4 * H), np.uint8))
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    fn = lib.mpcq_emu_solve_f64 if f64 else lib.mpcq_emu_solve_f32
+    rc = fn(C.byref(cfg), B, p(x0), p(yaw), p(feet), p(gait), p(xref), p(out["f"]), p(out["u"]), p(out["iters"]),
+            p(out["resid"]), p(out["status"]), p(out["active"]))
+    assert rc == 0
+    return out
+
+
+def check_against_oracle(out, batch, f64):
+    H = batch["horizon"]
+    assert np.all(out["status"] & _capi.ST_VERIFIED)
+    for b, sol in enumerate(batch["sols"]):
+        tol = max(1e-3, 1e-4 * np.abs(sol.u).max())
+        assert np.abs(out["u"][b].astype(np.float64) - sol.u).max() <= tol, b
+        assert np.array_equal(out["f"][b], out["u"][b, :12])
+        a = out["active"][b]
+        lo = ((a[:, None] >> np.arange(5)[None, :]) & 1).astype(bool).reshape(-1)
+        up = np.zeros(20 * H, dtype=bool)
+        up[4::5] = (a >> 5) & 1
+        assert np.array_equal(lo, sol.active_lower) and np.array_equal(up, sol.active_upper), b
+    assert out["resid"][:, 1].max() <= 1e-9
+    assert out["resid"][:, 0].max() <= (1e-9 if f64 else 1e-6)
+
+
+CASES = [
+    ("a1_trot_h10_f32", A1Config, 10, 24, "mixed", (Gait.TROTTING10,), False, 101),
+    ("aliengo_mix_h10_f64", AliengoConfig, 10, 24, "mixed", GAIT_MIX, True, 102),
+    ("aliengo_mix_h10_f32_aggressive", AliengoConfig, 10, 16, "aggressive", GAIT_MIX, False, 103),
+    ("a1_stand_h10_f32", A1Config, 10, 8, "mixed", (Gait.STANDING,), False, 104),
+    ("a1_h16_gaits_f64", A1Config, 16, 8, "mixed", (Gait.TROTTING16, Gait.JUMPING16, Gait.PACING16), True, 105),
+    ("a1_trot_h30_f64", A1Config, 30, 3, "mixed", (Gait.TROTTING10,), True, 106),
+]
+
+
+@pytest.mark.parametrize("name,robot,H,B,regime,gaits,f64,seed", CASES, ids=[c[0] for c in CASES])
+def test_device_code_matches_oracle(emu_lib, name, robot, H, B, regime, gaits, f64, seed):
+    batch = make_batch(robot, H, B, regime, gaits, seed)
+    out = emu_solve(emu_lib, batch, robot, f64)
+    check_against_oracle(out, batch, f64)
+
+
+def test_fallback_path_is_exact(emu_lib):
+    """Force the primal active-set fallback (no primal-dual rounds allowed): same optimum."""
+    batch = make_batch(A1Config, 10, 8, "aggressive", (Gait.TROTTING10,), 111)
+    out = emu_solve(emu_lib, batch, A1Config, True, max_pdas_rounds=1)
+    check_against_oracle(out, batch, True)
+    assert np.any(out["status"] & _capi.ST_FALLBACK)
+
+
+def test_all_swing_and_single_stance(emu_lib):
+    batch = make_batch(A1Config, 10, 3, "nominal", (Gait.TROTTING10,), 112, solve=False)
+    batch["gait"][0] = 0.0                      # no stance at all
+    batch["gait"][1] = 0.0
+    batch["gait"][1, 4 * 3 + 2] = 1.0           # one single stance foot-step
+    out = emu_solve(emu_lib, batch, A1Config, False)
+    assert out["status"][0] & _capi.ST_NO_STANCE and np.all(out["u"][0] == 0) and np.all(out["active"][0] == 0x3F)
+    assert out["status"][1] & _capi.ST_VERIFIED
+    nz = np.flatnonzero(out["u"][1])
+    assert set(nz) <= {3 * 14, 3 * 14 + 1, 3 * 14 + 2}
+
+
+def test_iteration_cap_is_reported(emu_lib):
+    batch = make_batch(A1Config, 10, 6, "aggressive", (Gait.STANDING,), 113, solve=False)
+    out = emu_solve(emu_lib, batch, A1Config, False, max_pdas_rounds=1, max_as_iter=1)
+    bad = ~(out["status"] & _capi.ST_VERIFIED).astype(bool)
+    assert bad.any() and np.all(out["status"][bad] & _capi.ST_MAXITER)
+    assert out["resid"][:, 1].max() <= 1e-9      # the returned point is still feasible
