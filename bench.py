@@ -1,0 +1,354 @@
+#!/usr/bin/env python
+"""Benchmark of the batched convex-MPC hot path (BASELINE.json metric: MPC QP solves/sec at
+4096 robots x H=10 on 1/2/4/8 B200; p50 step latency).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]            our arm (CUDA engine through the C ABI)
+  python bench.py --impl reference ...                           the reference's per-robot CPU loop on the host cores
+  torchrun --nproc-per-node N bench.py --gpus N ...              one rank per GPU (weak scaling: --envs per GPU)
+
+A step = one pass of the hot path (QP build + solve, 12 GRFs out) over one batch of --envs synthetic
+robots per GPU.  Consecutive steps use different input sets (--sets of them, > L2 in total).
+Prints ONE JSON line (rank 0).  Nothing here reads /root/reference.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "mpc_qp_solves_per_sec"
+UNIT = "solves/s"
+# algorithmic HBM bytes of one solve: 4*(13 x0 + 1 yaw + 12 feet + 13H x_ref) + 4*4H gait + 4*12 out
+ALGO_BYTES = lambda H: 4 * (13 + 1 + 12 + 13 * H) + 16 * H + 48
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", choices=("ours", "reference"), default="ours")
+    ap.add_argument("--envs", type=int, default=4096, help="robots per GPU per step")
+    ap.add_argument("--sets", type=int, default=64, help="distinct input sets rotated through (64 x 4096 x 708 B = 186 MB > L2)")
+    ap.add_argument("--horizon", type=int, default=10)
+    ap.add_argument("--robot", default="A1Config")
+    ap.add_argument("--regime", default="mixed", choices=("mixed", "nominal", "aggressive"))
+    ap.add_argument("--gait", default="trot", choices=("trot", "mix", "stand"))
+    ap.add_argument("--dtype", default="f32", choices=("f32", "f64"))
+    ap.add_argument("--gather", action="store_true", help="include the optional NCCL all-gather of GRFs in the step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-sample", type=int, default=0, help="envs in the CPU-baseline sample (0 = ~20 s of CPU work)")
+    return ap.parse_args()
+
+
+def gaits_for(name):
+    from pympc_quadruped_b200.gait import Gait
+    from pympc_quadruped_b200.synth import GAIT_MIX
+    return {"trot": (Gait.TROTTING10,), "mix": GAIT_MIX, "stand": (Gait.STANDING,)}[name]
+
+
+def workload_name(a):
+    return (f"{a.robot[:-6]} {a.gait} {a.regime} states, {a.envs} envs/GPU, horizon {a.horizon}, {a.dtype} "
+            f"(BASELINE configs[1])")
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.idx}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+            out, _ = self.proc.communicate()
+        sm, mx, reasons = [], [], set()
+        for line in out.strip().splitlines():
+            p = [x.strip() for x in line.split(",")]
+            if len(p) < 8:
+                continue
+            try:
+                sm.append(float(p[1])); mx.append(float(p[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), p[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        # the first samples may precede the load; take the median of the upper half
+        sm_sorted = sorted(sm)
+        load = sm_sorted[len(sm_sorted) // 2:] if sm_sorted else []
+        return {"sm_mhz": statistics.median(load) if load else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def host_states(a, seed):
+    from pympc_quadruped_b200 import configs
+    from pympc_quadruped_b200.synth import synth_gait_tables, synth_states
+    robot = getattr(configs, a.robot)
+    n = a.envs * a.sets
+    st = synth_states(n, robot, a.regime, seed=seed)
+    tabs = synth_gait_tables(n, a.horizon, gaits_for(a.gait), seed=seed)
+    return robot, st, tabs
+
+
+def run_reference(a):
+    """The reference's Python loop (restated; Drake replaced by the exact oracle solver) on all host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import multiprocessing as mp
+    from oracle.cpu_baseline import run_parallel
+    from pympc_quadruped_b200.synth import SEED_BASE
+    cores = os.cpu_count() or 1
+    per_step = max(cores * 24, 96)                                  # bounded sample of the workload per step
+    a2 = argparse.Namespace(**vars(a))
+    a2.envs, a2.sets = per_step, a.steps + a.warmup
+    robot, st, tabs = host_states(a2, SEED_BASE + 2)
+    keys = ("quat_base", "pos_base", "ang_vel_base", "lin_vel_base", "pos_base_feet", "vel_cmd_body", "yaw_rate_cmd")
+    times = []
+    with mp.get_context("spawn").Pool(cores) as pool:
+        for s in range(a.warmup + a.steps):
+            sl = slice(s * per_step, (s + 1) * per_step)
+            _, wall, tb, ts = run_parallel(pool, a.horizon, a.robot, {k: st[k][sl] for k in keys}, tabs[sl], cores)
+            if s >= a.warmup:
+                times.append(wall)
+    total = sum(times)
+    value = per_step * a.steps / total
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
+        "warmup": a.warmup, "ms_per_step": 1e3 * total / a.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload_name(a), "sample_per_step": per_step,
+                   "note": "reference construction restated in numpy (pinned bit-for-bit to the reference) + exact fp64 "
+                           "solver; Drake/OSQP is not installable offline"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{per_step} envs per step x {a.steps} steps of the same seeded workload"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(a):
+    import torch
+    import torch.distributed as dist
+    from pympc_quadruped_b200.controller import BatchedModelPredictiveController, BatchedRobotData
+    from pympc_quadruped_b200.configs import with_horizon
+    from pympc_quadruped_b200.synth import SEED_BASE
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py (our arm) needs a CUDA device: the engine has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    tdt = torch.float64 if a.dtype == "f64" else torch.float32
+    H, B, S = a.horizon, a.envs, a.sets
+
+    # ---- synthetic inputs: seeded states -> the controller's own state / reference-trajectory code (device)
+    robot, st, tabs = host_states(a, SEED_BASE + 2 + 1000 * rank)
+    n = B * S
+    ctrl = BatchedModelPredictiveController(with_horizon(H), robot, n, device=dev, dtype=tdt)
+    eng = ctrl.engine
+    ctrl.update_robot_state(BatchedRobotData(st["quat_base"], st["pos_base"], st["ang_vel_base"], st["lin_vel_base"],
+                                             st["pos_base_feet"], st["R_base"]))
+    ctrl.is_first_run = False
+    ctrl.xpos_base_desired = ctrl.current_state[:, 3].double()
+    ctrl.ypos_base_desired = ctrl.current_state[:, 4].double()
+    ctrl.yaw_desired = ctrl.yaw.clone()
+    vel = torch.einsum("bij,bj->bi", ctrl.R_base, torch.as_tensor(st["vel_cmd_body"], device=dev))
+    xref = ctrl.generate_reference_trajectory(vel, torch.as_tensor(st["yaw_rate_cmd"], device=dev))
+    x0 = ctrl.current_state.to(tdt).reshape(S, B, 13).contiguous()
+    yaw = ctrl.yaw.to(tdt).reshape(S, B).contiguous()
+    feet = ctrl.pos_base_feet.to(tdt).reshape(S, B, 12).contiguous()
+    xref = xref.to(tdt).reshape(S, B, 13 * H).contiguous()
+    gait = torch.as_tensor(tabs, device=dev).reshape(S, B, 4 * H).contiguous()
+    from pympc_quadruped_b200.engine import SolveResult
+    out = SolveResult(forces=torch.empty((B, 12), dtype=tdt, device=dev), u=None,
+                      iters=torch.empty((B, 2), dtype=torch.int32, device=dev), resid=None,
+                      status=torch.empty((B,), dtype=torch.int32, device=dev), active=None)
+    gathered = torch.empty((world * B, 12), dtype=tdt, device=dev) if (a.gather and world > 1) else None
+
+    def step(s):
+        k = s % S
+        eng.solve(x0[k], feet[k], gait[k], xref[k], yaw=yaw[k], out=out)
+        if gathered is not None:
+            dist.all_gather_into_tensor(gathered, out.forces)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    # ---- device-resident timing
+    for s in range(a.warmup):
+        step(s)
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(a.steps)]
+    sampler = ClockSampler(local)
+    barrier()
+    sampler.start()
+    t_all0, t_all1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_all0.record()
+    for s in range(a.steps):
+        ev[s][0].record()
+        step(a.warmup + s)
+        ev[s][1].record()
+    t_all1.record()
+    barrier()
+    clocks = sampler.stop()
+    total_ms = t_all0.elapsed_time(t_all1)
+    lat = sorted(e0.elapsed_time(e1) for e0, e1 in ev)
+    launches_per_step = eng.last_launch_count
+    tmax = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    total_ms = float(tmax.item())
+    value = world * B * a.steps / (total_ms * 1e-3)
+
+    # ---- solver statistics over every input set (outside the timed region)
+    facts, fallback, unverified = [], 0, 0
+    for k in range(S):
+        eng.solve(x0[k], feet[k], gait[k], xref[k], yaw=yaw[k], out=out)
+        it = out.iters[:, 0].double()
+        facts.append(it.cpu().numpy())
+        fallback += int(((out.status & 2) != 0).sum())
+        unverified += int(((out.status & 1) == 0).sum())
+    facts = np.concatenate(facts)
+
+    # ---- dominant-kernel duration: CUDA events on the launching stream around each class launch
+    eng.set_profiling(True)
+    kms = []
+    for s in range(a.steps):
+        step(a.warmup + s)
+        kms.append(eng.last_kernel_ms())
+    eng.set_profiling(False)
+    kms = np.array(kms)                                            # [steps, classes]
+    kmean = kms.mean(axis=0)
+    dom = int(np.argmax(kmean))
+
+    # ---- end to end through the C ABI with HOST buffers (mpcq_solve_host: pinned staging, H2D, solve, D2H)
+    hx0, hyaw, hfeet, hxref, hgait = (t.cpu().numpy() for t in (x0, yaw, feet, xref, gait))
+    rs = 8 if a.dtype == "f64" else 4
+    h2d = B * (rs * (13 + 1 + 12 + 13 * H) + 16 * H)
+    d2h = B * (12 * rs + 4)
+    for s in range(a.warmup):
+        eng.solve_host(hx0[s % S], hfeet[s % S], hgait[s % S], hxref[s % S], yaw=hyaw[s % S])
+    barrier()
+    t0 = time.perf_counter()
+    for s in range(a.steps):
+        k = (a.warmup + s) % S
+        r = eng.solve_host(hx0[k], hfeet[k], hgait[k], hxref[k], yaw=hyaw[k])
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = world * B * a.steps / float(te.item())
+
+    # ---- roofline of the dominant kernel
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        hbm_peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    else:
+        hbm_peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    kern_s = float(kmean[dom]) * 1e-3
+    achieved = ALGO_BYTES(H) * (rs / 4) * B / kern_s / 1e9
+    # executed arithmetic of the dominant kernel (model: factorisations x (n^3/6 + assembly) FMAs)
+    nred = 3.0 * tabs.reshape(S, B, -1).sum(axis=2).mean()
+    fma_per_fact = nred ** 3 / 6 + 2.5 * nred ** 2 * 4 + 8 * nred ** 2 / 2
+    exec_flops = 2.0 * fma_per_fact * facts.mean() * B / kern_s
+
+    cpu = None
+    if rank == 0 and world == 1 and not a.no_cpu_baseline:
+        cpu = cpu_baseline(a, st, tabs, out, eng, (x0, yaw, feet, xref, gait))
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+            "ms_per_step": total_ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": a.dtype, "data": "synthetic",
+            "config": {"workload": workload_name(a), "envs_per_gpu": B, "horizon": H, "robot": a.robot, "gait": a.gait,
+                       "regime": a.regime, "parallelism": f"env-sharded x{world}, no collective in the solve loop"
+                                                          + (" + all-gather of GRFs" if gathered is not None else ""),
+                       "l2": f"{S} distinct input sets rotated ({S * B * ALGO_BYTES(H) * rs // 4 / 1e6:.0f} MB total > 126 MB L2)",
+                       "precision": "Cholesky/triangular solves in " + a.dtype + ", residuals + KKT tests in f64"},
+            "latency_ms": {"p50": lat[len(lat) // 2], "p90": lat[int(len(lat) * 0.9)], "max": lat[-1]},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "api": "mpcq_solve_host (C ABI, host buffers)"},
+            "gpu_launches": launches_per_step * a.steps,
+            "kernel_ms": {"per_class_mean": [float(v) for v in kmean], "dominant_class": dom,
+                          "share_of_step": float(kmean[dom] / (total_ms / a.steps))},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+                         "traffic": None, "peak_source": peak_src,
+                         "note": "the path is not HBM-bound (708 B/solve): latency/shared-memory bound, see roofline_compute"},
+            "roofline_compute": {"executed_gflops_model": exec_flops / 1e9, "factorisations_per_solve_mean": float(facts.mean()),
+                                 "factorisations_p50": float(np.median(facts)), "factorisations_max": float(facts.max()),
+                                 "reduced_dim_mean": float(nred)},
+            "solver": {"fallback_envs": fallback, "unverified_envs": unverified, "envs_checked": int(S * B)},
+            "clocks": clocks,
+        }
+        if cpu is not None:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def cpu_baseline(a, st, tabs, out, eng, dev_inputs):
+    """Oracle port on the host cores over a bounded sample of the same workload; also cross-checks the GPU forces."""
+    import multiprocessing as mp
+    import torch
+    from oracle.cpu_baseline import run_parallel
+    cores = os.cpu_count() or 1
+    sample = min(a.cpu_sample or 3072, a.envs)                  # ~20 s of CPU work at ~6.5 ms per solve
+    keys = ("quat_base", "pos_base", "ang_vel_base", "lin_vel_base", "pos_base_feet", "vel_cmd_body", "yaw_rate_cmd")
+    sub = {k: st[k][:sample] for k in keys}
+    with mp.get_context("spawn").Pool(cores) as pool:
+        run_parallel(pool, a.horizon, a.robot, {k: v[:cores * 2] for k, v in sub.items()}, tabs[:cores * 2], cores)   # warm the workers
+        f_cpu, wall, tb, ts = run_parallel(pool, a.horizon, a.robot, sub, tabs[:sample], cores)
+    x0, yaw, feet, xref, gait = dev_inputs
+    eng.solve(x0[0], feet[0], gait[0], xref[0], yaw=yaw[0], out=out)
+    f_gpu = out.forces[:sample].double().cpu().numpy()
+    err = np.abs(f_gpu - f_cpu).max(axis=1)
+    tol = np.maximum(1e-3, 1e-4 * np.abs(f_cpu).max(axis=1))
+    return {"value": sample / wall, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"first {sample} envs of input set 0 (same seeded workload), one pass, {cores} worker processes",
+            "cpu_ms_per_solve": {"build": 1e3 * tb / sample, "solve": 1e3 * ts / sample},
+            "gpu_vs_cpu_max_abs_df_N": float(err.max()), "gpu_vs_cpu_within_tolerance": bool(np.all(err <= tol))}
+
+
+if __name__ == "__main__":
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)

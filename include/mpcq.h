@@ -134,6 +134,15 @@ int mpcq_build_qp(mpcq_handle* h, int32_t B,
 /* number of kernels the last mpcq_solve / mpcq_build_qp call launched (for bench.py's gpu_launches) */
 int mpcq_last_launch_count(const mpcq_handle* h);
 
+/*
+ * Measurement hooks (no reference counterpart; the reference only prints time.time() deltas, mpc.py:98-101).
+ * With profiling on, mpcq_solve brackets every kernel launch with CUDA events on the launching stream.
+ * mpcq_last_kernel_ms synchronises on those events and writes the duration of each launch of the last
+ * mpcq_solve call (one per size class, in class order) into ms[0..cap); returns the number of launches.
+ */
+int mpcq_set_profiling(mpcq_handle* h, int32_t enable);
+int mpcq_last_kernel_ms(mpcq_handle* h, float* ms, int32_t cap);
+
 #ifdef __cplusplus
 }
 #endif

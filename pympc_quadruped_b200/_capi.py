@@ -71,11 +71,16 @@ def bind(lib: C.CDLL) -> C.CDLL:
     lib.mpcq_build_qp.restype = C.c_int
     lib.mpcq_last_launch_count.argtypes = [C.c_void_p]
     lib.mpcq_last_launch_count.restype = C.c_int
+    lib.mpcq_set_profiling.argtypes = [C.c_void_p, C.c_int32]
+    lib.mpcq_set_profiling.restype = C.c_int
+    lib.mpcq_last_kernel_ms.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.c_int32]
+    lib.mpcq_last_kernel_ms.restype = C.c_int
     return lib
 
 
 EXPORTS = ("mpcq_version", "mpcq_create", "mpcq_destroy", "mpcq_last_error", "mpcq_solve",
-           "mpcq_solve_host", "mpcq_build_qp", "mpcq_last_launch_count")
+           "mpcq_solve_host", "mpcq_build_qp", "mpcq_last_launch_count", "mpcq_set_profiling",
+           "mpcq_last_kernel_ms")
 
 _lib = None
 

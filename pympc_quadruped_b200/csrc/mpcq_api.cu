@@ -82,6 +82,10 @@ struct mpcq_handle {
     char* dev = nullptr;
     size_t stage_cap = 0;
     cudaStream_t stream = nullptr;
+    // measurement hooks
+    bool profiling = false;
+    cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    int ev_launches = 0;
 };
 
 namespace {
@@ -126,13 +130,16 @@ template <class T>
 cudaError_t launch_all(mpcq_handle* h, const IO<T>& io, cudaStream_t st) {
     cudaError_t e = cudaSuccess;
     h->last_launches = 0;
+    h->ev_launches = 0;
     for (int ci = 0; ci < h->ncls && e == cudaSuccess; ++ci) {
+        if (h->profiling) cudaEventRecord(h->ev[2 * ci], st);
         switch (ci) {
             case 0: e = launch_class_lg<T, 64>(h, io, ci, st); break;
             case 1: e = launch_class_lg<T, 128>(h, io, ci, st); break;
             case 2: e = launch_class_lg<T, 192>(h, io, ci, st); break;
             default: e = launch_class_lg<T, 384>(h, io, ci, st); break;
         }
+        if (h->profiling) { cudaEventRecord(h->ev[2 * ci + 1], st); ++h->ev_launches; }
         ++h->last_launches;
     }
     return e;
@@ -245,6 +252,8 @@ void mpcq_destroy(mpcq_handle* h) {
     if (!h) return;
     DeviceGuard guard(h->cfg.device);
     if (h->stream) { cudaStreamSynchronize(h->stream); cudaStreamDestroy(h->stream); }
+    for (int i = 0; i < 8; ++i)
+        if (h->ev[i]) cudaEventDestroy(h->ev[i]);
     if (h->gws) cudaFree(h->gws);
     if (h->dev) cudaFree(h->dev);
     if (h->pin) cudaFreeHost(h->pin);
@@ -334,5 +343,27 @@ int mpcq_solve_host(mpcq_handle* h, int32_t B, const void* x0, const void* yaw, 
 }
 
 int mpcq_last_launch_count(const mpcq_handle* h) { return h ? h->last_launches : 0; }
+
+int mpcq_set_profiling(mpcq_handle* h, int32_t enable) {
+    if (!h) return MPCQ_ERR_INVALID;
+    DeviceGuard guard(h->cfg.device);
+    if (enable)
+        for (int i = 0; i < 8; ++i)
+            if (!h->ev[i] && !cuda_ok(h, cudaEventCreate(&h->ev[i]), "cudaEventCreate")) return MPCQ_ERR_CUDA;
+    h->profiling = enable != 0;
+    h->ev_launches = 0;
+    return MPCQ_OK;
+}
+
+int mpcq_last_kernel_ms(mpcq_handle* h, float* ms, int32_t cap) {
+    if (!h || !ms) return MPCQ_ERR_INVALID;
+    DeviceGuard guard(h->cfg.device);
+    const int n = h->ev_launches;
+    for (int i = 0; i < n && i < cap; ++i) {
+        if (!cuda_ok(h, cudaEventSynchronize(h->ev[2 * i + 1]), "cudaEventSynchronize")) return MPCQ_ERR_CUDA;
+        if (!cuda_ok(h, cudaEventElapsedTime(&ms[i], h->ev[2 * i], h->ev[2 * i + 1]), "cudaEventElapsedTime")) return MPCQ_ERR_CUDA;
+    }
+    return n;
+}
 
 }  // extern "C"

@@ -151,3 +151,14 @@ class MpcqEngine:
     @property
     def last_launch_count(self) -> int:
         return int(self.lib.mpcq_last_launch_count(self._h))
+
+    def set_profiling(self, enable: bool) -> None:
+        self._err(self.lib.mpcq_set_profiling(self._h, int(bool(enable))), "mpcq_set_profiling")
+
+    def last_kernel_ms(self):
+        """Per-launch durations (ms) of the last `solve`, one per size class (needs set_profiling(True))."""
+        buf = (C.c_float * 8)()
+        n = self.lib.mpcq_last_kernel_ms(self._h, buf, 8)
+        if n < 0:
+            self._err(n, "mpcq_last_kernel_ms")
+        return [float(buf[i]) for i in range(min(n, 8))]
