@@ -76,6 +76,7 @@ typedef struct mpcq_config {
     double tol_dual;                /* relative multiplier-sign tolerance; default 1e-7 (f32) / 1e-9 (f64) */
     double tol_residual;            /* reduced-gradient tolerance relative to 1+|g|_inf; default 1e-9 (f32) / 1e-12 (f64) */
     double tol_active;              /* slack tolerance of the reported activity; default 1e-6 */
+    double tol_residual_loose;      /* reduced-gradient tolerance of intermediate active-set rounds; default 1e-6 (f32) / 1e-9 (f64) */
 } mpcq_config;
 
 typedef struct mpcq_handle mpcq_handle;

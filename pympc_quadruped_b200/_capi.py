@@ -27,7 +27,7 @@ class MpcqConfig(C.Structure):
         ("max_pdas_rounds", C.c_int32), ("max_as_iter", C.c_int32), ("max_refine", C.c_int32),
         ("reserved1", C.c_int32),
         ("tol_primal", C.c_double), ("tol_dual", C.c_double), ("tol_residual", C.c_double),
-        ("tol_active", C.c_double),
+        ("tol_active", C.c_double), ("tol_residual_loose", C.c_double),
     ]
 
 

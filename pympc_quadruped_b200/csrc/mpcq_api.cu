@@ -41,7 +41,7 @@ mpcq_build_qp_kernel(const __grid_constant__ Consts cs, const __grid_constant__ 
     extern __shared__ __align__(32) char smem[];
     const int b = blockIdx.x, lane = threadIdx.x, H = cs.horizon, n = 12 * H;
     mpcq::Work<T> w;
-    mpcq::carve<T>(w, smem, nullptr, H, 64);
+    mpcq::carve<T>(w, smem, nullptr, H, 64, true);
     const double yaw = io.yaw ? (double)io.yaw[b] : (double)io.x0[(size_t)b * 13 + 2];
     mpcq::setup_model(cs, w, io.x0 + (size_t)b * 13, yaw, io.r_feet + (size_t)b * 12, io.x_ref + (size_t)b * 13 * H);
     double* Hb = Hout + (size_t)b * n * n;
@@ -121,9 +121,17 @@ cudaError_t launch_class(mpcq_handle* h, const IO<T>& io, int ci, cudaStream_t s
     return cudaGetLastError();
 }
 
+// which (capacity, factor-in-global) combinations exist: the two small classes always fit in shared
+// memory, the largest never does (fp32 348 KB); only the 192-slot class can go either way (fp64, long horizons)
 template <class T, int NCAP>
 cudaError_t launch_class_lg(mpcq_handle* h, const IO<T>& io, int ci, cudaStream_t st) {
-    return h->lglobal[ci] ? launch_class<T, NCAP, true>(h, io, ci, st) : launch_class<T, NCAP, false>(h, io, ci, st);
+    if constexpr (NCAP <= 128) {
+        return launch_class<T, NCAP, false>(h, io, ci, st);
+    } else if constexpr (NCAP >= 384) {
+        return launch_class<T, NCAP, true>(h, io, ci, st);
+    } else {
+        return h->lglobal[ci] ? launch_class<T, NCAP, true>(h, io, ci, st) : launch_class<T, NCAP, false>(h, io, ci, st);
+    }
 }
 
 template <class T>
@@ -147,11 +155,17 @@ cudaError_t launch_all(mpcq_handle* h, const IO<T>& io, cudaStream_t st) {
 
 template <class T, int NCAP>
 cudaError_t set_attr(mpcq_handle* h, int ci) {
-    cudaError_t e = cudaFuncSetAttribute(mpcq_solve_kernel<T, NCAP, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)(h->lglobal[ci] ? 0 : h->smem[ci]));
-    if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(mpcq_solve_kernel<T, NCAP, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                (int)(h->lglobal[ci] ? h->smem[ci] : 0));
+    if constexpr (NCAP <= 128) {
+        if (h->lglobal[ci]) return cudaErrorInvalidValue;
+        return cudaFuncSetAttribute(mpcq_solve_kernel<T, NCAP, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem[ci]);
+    } else if constexpr (NCAP >= 384) {
+        if (!h->lglobal[ci]) return cudaErrorInvalidValue;
+        return cudaFuncSetAttribute(mpcq_solve_kernel<T, NCAP, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem[ci]);
+    } else {
+        if (h->lglobal[ci])
+            return cudaFuncSetAttribute(mpcq_solve_kernel<T, NCAP, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem[ci]);
+        return cudaFuncSetAttribute(mpcq_solve_kernel<T, NCAP, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem[ci]);
+    }
 }
 
 template <class T>
@@ -162,7 +176,7 @@ cudaError_t configure(mpcq_handle* h) {
     for (int ci = 0; ci < h->ncls; ++ci) {
         const int ncap = mpcq::kClasses[ci].ncap;
         size_t s = mpcq::work_bytes<T>(H, ncap, true);
-        h->lglobal[ci] = s > kMaxSmem;
+        h->lglobal[ci] = s > kMaxSmem || ncap >= 384;
         if (h->lglobal[ci]) {
             s = mpcq::work_bytes<T>(H, ncap, false);
             if (s > kMaxSmem) return cudaErrorInvalidValue;
@@ -183,7 +197,7 @@ cudaError_t configure(mpcq_handle* h) {
     }
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(mpcq_build_qp_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)mpcq::work_bytes<T>(H, 64, true));
+                             (int)mpcq::work_bytes<T>(H, 64, true, true));
     if (e != cudaSuccess) return e;
     if (gws_elems) {
         h->gws_stride = gws_elems;
@@ -288,10 +302,10 @@ int mpcq_build_qp(mpcq_handle* h, int32_t B, const void* x0, const void* yaw, co
     const int H = h->cs.horizon;
     if (h->cfg.dtype == MPCQ_F64) {
         IO<double> io = make_io<double>(B, x0, yaw, r_feet, gait, x_ref, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
-        mpcq_build_qp_kernel<double><<<B, 32, mpcq::work_bytes<double>(H, 64, true), st>>>(h->cs, io, H_out, g_out, ub_out);
+        mpcq_build_qp_kernel<double><<<B, 32, mpcq::work_bytes<double>(H, 64, true, true), st>>>(h->cs, io, H_out, g_out, ub_out);
     } else {
         IO<float> io = make_io<float>(B, x0, yaw, r_feet, gait, x_ref, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
-        mpcq_build_qp_kernel<float><<<B, 32, mpcq::work_bytes<float>(H, 64, true), st>>>(h->cs, io, H_out, g_out, ub_out);
+        mpcq_build_qp_kernel<float><<<B, 32, mpcq::work_bytes<float>(H, 64, true, true), st>>>(h->cs, io, H_out, g_out, ub_out);
     }
     h->last_launches = 1;
     return cuda_ok(h, cudaGetLastError(), "mpcq_build_qp launch") ? MPCQ_OK : MPCQ_ERR_CUDA;

@@ -64,31 +64,34 @@ enum : int { ST_VERIFIED = 1, ST_FALLBACK = 2, ST_MAXITER = 4, ST_NUMERIC = 8, S
 // ---------------------------------------------------------------------------------------------
 // per-warp workspace
 MPCQ_HD constexpr size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
-MPCQ_HD constexpr int l_elems(int n) { return n * n / 2 + 2 * n; }
+MPCQ_HD constexpr int l_elems(int n) { return n * n / 2 + 2 * n + 32; }   // +32: unpredicated row sweeps may overrun
 
 template <class T> struct Work {
     // fp64
-    double *Md, *Sd, *GW, *g, *u, *gam, *P0, *P1, *ucur, *fmax;
+    double *Md, *Sd, *GW, *g, *u, *gam, *P0, *P1, *ucur, *utrial, *fmax;
     // precision T
     T *L, *dblk, *vec, *cw, *zt, *Mf, *St;
+    int32_t* sinf;         // per slot: step | leg << 8 | foot << 16 | dead << 30
     // bytes
     uint8_t *fk;           // stance list: full foot-step index k = 4*step + leg
     int8_t* face;          // 3 per stance foot-step
+    int8_t* face2;         // trial faces of the fallback
+    int8_t* facef;         // faces the current factor was built for
     int n, ns, H;
 };
 
 template <class T>
-MPCQ_HD constexpr size_t work_bytes(int H, int ncap, bool l_in_smem) {
-    size_t nd = 288 + (size_t)H * H + 72 + 6 * 12 * (size_t)H + ncap / 3 + 1;
-    size_t nt = (l_in_smem ? l_elems(ncap) : 0) + 3 * (ncap / 4) * 4 + ncap + 96 + 3 * ncap + 288 + (size_t)H * H;
-    size_t nb = (ncap / 3 + 1) * 4;
+MPCQ_HD constexpr size_t work_bytes(int H, int ncap, bool l_in_smem, bool with_md = false) {
+    size_t nd = (with_md ? 288 : 0) + (size_t)H * H + 72 + 7 * 12 * (size_t)H + ncap / 3 + 1;
+    size_t nt = (l_in_smem ? l_elems(ncap) : 0) + 3 * (ncap / 4) * 4 + ncap + 128 + 3 * ncap + 288 + (size_t)H * H;
+    size_t nb = (ncap / 3 + 1) * 10 + 16 + 4 * (size_t)ncap;
     return align_up(nd * 8, 16) + align_up(nt * sizeof(T), 16) + align_up(nb, 16);
 }
 
 template <class T>
-MPCQ_DEV void carve(Work<T>& w, char* base, T* l_global, int H, int ncap) {
+MPCQ_DEV void carve(Work<T>& w, char* base, T* l_global, int H, int ncap, bool with_md = false) {
     double* d = reinterpret_cast<double*>(base);
-    w.Md = d; d += 288;
+    w.Md = with_md ? d : nullptr; d += with_md ? 288 : 0;
     w.Sd = d; d += H * H;
     w.GW = d; d += 72;
     w.g = d; d += 12 * H;
@@ -97,8 +100,9 @@ MPCQ_DEV void carve(Work<T>& w, char* base, T* l_global, int H, int ncap) {
     w.P0 = d; d += 12 * H;
     w.P1 = d; d += 12 * H;
     w.ucur = d; d += 12 * H;
+    w.utrial = d; d += 12 * H;
     w.fmax = d; d += ncap / 3 + 1;
-    size_t nd = 288 + (size_t)H * H + 72 + 6 * 12 * (size_t)H + ncap / 3 + 1;
+    size_t nd = (with_md ? 288 : 0) + (size_t)H * H + 72 + 7 * 12 * (size_t)H + ncap / 3 + 1;
     T* t = reinterpret_cast<T*>(base + align_up(nd * 8, 16));
     size_t used = 0;
     if (l_global) {
@@ -108,13 +112,16 @@ MPCQ_DEV void carve(Work<T>& w, char* base, T* l_global, int H, int ncap) {
     }
     w.dblk = t; t += 3 * (ncap / 4) * 4; used += 3 * (ncap / 4) * 4;
     w.vec = t; t += ncap; used += ncap;
-    w.cw = t; t += 96; used += 96;
+    w.cw = t; t += 128; used += 128;
     w.zt = t; t += 3 * ncap; used += 3 * ncap;
     w.Mf = t; t += 288; used += 288;
     w.St = t; t += H * H; used += (size_t)H * H;
     uint8_t* b = reinterpret_cast<uint8_t*>(base + align_up(nd * 8, 16) + align_up(used * sizeof(T), 16));
     w.fk = b; b += ncap / 3 + 1;
-    w.face = reinterpret_cast<int8_t*>(b);
+    w.face = reinterpret_cast<int8_t*>(b); b += 3 * (ncap / 3 + 1);
+    w.face2 = reinterpret_cast<int8_t*>(b); b += 3 * (ncap / 3 + 1);
+    w.facef = reinterpret_cast<int8_t*>(b); b += 3 * (ncap / 3 + 1);
+    w.sinf = reinterpret_cast<int32_t*>(reinterpret_cast<uintptr_t>(b + 15) & ~uintptr_t(15));
     w.H = H;
 }
 
@@ -243,7 +250,7 @@ MPCQ_DEV void setup_model(const Consts& cs, Work<T>& w, const T* x0p, double yaw
         }
         if (x == y) { m0 += cs.q[9 + x] * im2; m1 += cs.q[3 + x] * im2; }
         m0 *= dt2; m1 *= dt4;
-        w.Md[idx] = m0; w.Md[144 + idx] = m1;
+        if (w.Md) { w.Md[idx] = m0; w.Md[144 + idx] = m1; }
         w.Mf[idx] = (T)m0; w.Mf[144 + idx] = (T)m1;
     }
     // --- suffix sums E0, E1 of Q e_k (free response minus reference), one lane per state component
@@ -286,30 +293,51 @@ MPCQ_DEV void setup_model(const Consts& cs, Work<T>& w, const T* x0p, double yaw
     wp::sync();
 }
 
-// gam = H u + g, fp64, through the Kronecker structure (u, gam in full [H][12] layout)
+// gam = H u + g in fp64 through the factored structure H = 2 (N (x) B0'QB0 + S (x) B1'QB1 + R):
+//   1. y_i = (G u_i, W u_i, sum_legs u_i / m)  per step      2. mix over steps with N and S
+//   3. project back with G', W'.   u, gam in full [H][12] layout; P0 / P1 are scratch.
 template <class T>
 MPCQ_DEV void hess_apply(const Consts& cs, Work<T>& w) {
     const int lane = wp::lane();
     const int H = cs.horizon;
-    for (int idx = lane; idx < 12 * H; idx += 32) {
-        const int i = idx / 12, r = idx - 12 * i;
+    for (int idx = lane; idx < 9 * H; idx += 32) {
+        const int i = idx / 9, k = idx - 9 * i;
         const double* ui = w.u + 12 * i;
-        const double* m0 = w.Md + 12 * r;
-        const double* m1 = w.Md + 144 + 12 * r;
-        double p0 = 0, p1 = 0;
-        MPCQ_UNROLL
-        for (int c = 0; c < 12; ++c) { p0 += m0[c] * ui[c]; p1 += m1[c] * ui[c]; }
-        w.P0[idx] = p0; w.P1[idx] = p1;
+        double y = 0;
+        if (k < 6) {
+            const double* gw = w.GW + (k < 3 ? 3 * k : 9 + 3 * (k - 3));
+            MPCQ_UNROLL
+            for (int a = 0; a < 4; ++a) y += gw[18 * a] * ui[3 * a] + gw[18 * a + 1] * ui[3 * a + 1] + gw[18 * a + 2] * ui[3 * a + 2];
+            y *= k < 3 ? cs.q[6 + k] : cs.q[k - 3];
+        } else {
+            const int x = k - 6;
+            y = cs.inv_mass * (ui[x] + ui[3 + x] + ui[6 + x] + ui[9 + x]);
+        }
+        w.P0[idx] = y;
     }
     wp::sync();
     for (int idx = lane; idx < 12 * H; idx += 32) {
-        const int j = idx / 12, r = idx - 12 * j;
+        const int j = idx / 12, c = idx - 12 * j;
+        const bool useN = c < 6;
+        const int src = c < 3 ? c : c < 6 ? 3 + c : c < 9 ? c - 3 : c - 3;     // y0r | fs | y1r | fs
         double acc = 0;
         for (int i = 0; i < H; ++i) {
-            const double Nij = (double)(H - (i > j ? i : j));
-            acc += Nij * w.P0[12 * i + r] + w.Sd[i * H + j] * w.P1[12 * i + r];
+            const double wgt = useN ? (double)(H - (i > j ? i : j)) : w.Sd[i * H + j];
+            acc += wgt * w.P0[9 * i + src];
         }
-        w.gam[idx] = w.g[idx] + 2.0 * (acc + cs.r[r] * w.u[idx]);
+        if (c >= 3 && c < 6) acc *= cs.q[9 + (c - 3)];
+        if (c >= 9) acc *= cs.q[3 + (c - 9)];
+        w.P1[idx] = acc;
+    }
+    wp::sync();
+    const double dt2 = cs.dt * cs.dt, dt4 = dt2 * dt2;
+    for (int idx = lane; idx < 12 * H; idx += 32) {
+        const int j = idx / 12, r = idx - 12 * j, a = r / 3, y = r - 3 * a;
+        const double* Y = w.P1 + 12 * j;
+        const double* gw = w.GW + 18 * a + y;
+        const double t0 = cs.inv_mass * Y[3 + y] + gw[0] * Y[0] + gw[3] * Y[1] + gw[6] * Y[2];
+        const double t1 = cs.inv_mass * Y[9 + y] + gw[9] * Y[6] + gw[12] * Y[7] + gw[15] * Y[8];
+        w.gam[idx] = w.g[idx] + 2.0 * (cs.r[r] * w.u[idx] + dt2 * t0 + dt4 * t1);
     }
     wp::sync();
 }
@@ -343,6 +371,13 @@ MPCQ_DEV bool build_slots(const Consts& cs, Work<T>& w) {
         MPCQ_UNROLL
         for (int c = 0; c < 9; ++c)
             if (3 * p + c / 3 < w.n) w.zt[9 * p + c] = z[c];
+        MPCQ_UNROLL
+        for (int c = 0; c < 3; ++c)
+            if (3 * p + c < w.n) {
+                const bool dead = z[3 * c] == 0 && z[3 * c + 1] == 0 && z[3 * c + 2] == 0;
+                const int k = p < w.ns ? w.fk[p] : 0;
+                w.sinf[3 * p + c] = (k >> 2) | ((k & 3) << 8) | (p << 16) | (dead ? (1 << 30) : 0);
+            }
     }
     wp::sync();
     return wp::any(nonzero_c);
@@ -351,125 +386,148 @@ MPCQ_DEV bool build_slots(const Consts& cs, Work<T>& w) {
 // ---------------------------------------------------------------------------------------------
 // K2 + K4a: assemble K = Z'HZ column panel by column panel (never materialised) and factor it.
 // Left-looking, 4-column panels; lane owns rows lane, lane+32, ... ; returns false on a bad pivot.
+// The inner sweeps are unpredicated: rows above the panel / beyond n compute garbage that is never stored.
 template <class T, int NSLOT>
-MPCQ_DEV bool chol_factor(const Consts& cs, Work<T>& w) {
+MPCQ_DEV bool chol_factor(const Consts& cs, Work<T>& w, int k_start) {
     const int lane = wp::lane();
     const int n = w.n, H = cs.horizon;
     T* L = w.L;
     bool ok = true;
+    // row data of this lane, fixed for the whole factorisation
+    T zr[NSLOT][3];
+    int ri[NSLOT];
+    MPCQ_UNROLL
+    for (int m = 0; m < NSLOT; ++m) {
+        const int v = lane + 32 * m;
+        const bool in = v < n;
+        ri[m] = in ? w.sinf[v] : (1 << 30);
+        zr[m][0] = in ? w.zt[3 * v] : (T)0;
+        zr[m][1] = in ? w.zt[3 * v + 1] : (T)0;
+        zr[m][2] = in ? w.zt[3 * v + 2] : (T)0;
+    }
+    const T* colg = L;            // base of the current group of 4 previous columns (used incrementally below)
+    // Rows < k_start keep their factor (leading block unchanged since the previous factorisation, see
+    // reorder_feet): for panels k0 < k_start only the rows >= k_start are recomputed (L21 = K21 L11^-T, using the
+    // stored diagonal blocks); from k_start on it is the plain left-looking factorisation.
     for (int k0 = 0; k0 < n; k0 += 4) {
-        // ---- cw[c][mat*12 + r] = sum_y M_mat[r][3b+y] z_w[y] for the 4 panel columns
+        const bool keep_diag = k0 < k_start;
+        const int row_lo = keep_diag ? k_start : k0;
+        // ---- panel columns: info + cw[c][mat][leg][x] = sum_y M_mat[3 leg + x][3 b_c + y] z_c[y]; one (c,mat,leg) per lane
+        int ci[4];
         MPCQ_UNROLL
-        for (int t = 0; t < 3; ++t) {
-            const int idx = lane + 32 * t;
-            const int c = idx / 24, rem = idx - 24 * c;
-            const int wv = k0 + c, pw = wv / 3;
-            T val = 0;
-            if (pw < w.ns) {
-                const int b = w.fk[pw] & 3;
-                const T* z = w.zt + 3 * wv;
-                const T* mrow = w.Mf + (rem / 12) * 144 + (rem % 12) * 12 + 3 * b;
-                val = mrow[0] * z[0] + mrow[1] * z[1] + mrow[2] * z[2];
-            }
-            w.cw[idx] = val;
+        for (int c = 0; c < 4; ++c) ci[c] = w.sinf[k0 + c];
+        {
+            const int c = lane >> 3, mat = (lane >> 2) & 1, leg = lane & 3;
+            const int info = w.sinf[k0 + c];
+            const int b = (info >> 8) & 3;
+            const T* z = w.zt + 3 * (k0 + c);
+            const T z0 = z[0], z1 = z[1], z2 = z[2];
+            const T* mrow = w.Mf + mat * 144 + (3 * leg) * 12 + 3 * b;
+            T* dst = w.cw + 4 * lane;
+            dst[0] = mrow[0] * z0 + mrow[1] * z1 + mrow[2] * z2;
+            dst[1] = mrow[12] * z0 + mrow[13] * z1 + mrow[14] * z2;
+            dst[2] = mrow[24] * z0 + mrow[25] * z1 + mrow[26] * z2;
+            dst[3] = 0;
         }
         wp::sync();
         // ---- initial entries of the panel
         T acc[NSLOT][4];
-        const int m0 = k0 >> 5;
+        const int m0 = row_lo >> 5;
         MPCQ_UNROLL
         for (int m = 0; m < NSLOT; ++m) {
-            MPCQ_UNROLL
-            for (int c = 0; c < 4; ++c) acc[m][c] = 0;
+            if (m < m0) continue;
+            const int iv = ri[m] & 0xff, av = (ri[m] >> 8) & 3;
+            const bool dead = (ri[m] >> 30) != 0;
             const int v = lane + 32 * m;
-            if (m >= m0 && v >= k0 && v < n) {
-                const int pv = v / 3;
-                const T z0 = w.zt[3 * v], z1 = w.zt[3 * v + 1], z2 = w.zt[3 * v + 2];
-                const bool dead = (z0 == 0 && z1 == 0 && z2 == 0);
-                int iv = 0, av = 0;
-                if (pv < w.ns) { iv = w.fk[pv] >> 2; av = w.fk[pv] & 3; }
-                MPCQ_UNROLL
-                for (int c = 0; c < 4; ++c) {
-                    const int wv = k0 + c;
-                    if (wv > v) continue;
-                    const int pw = wv / 3;
-                    T e = 0;
-                    if (!dead && pw < w.ns) {
-                        const int jw = w.fk[pw] >> 2;
-                        const T* cwc = w.cw + 24 * c + 3 * av;
-                        const T t0 = z0 * cwc[0] + z1 * cwc[1] + z2 * cwc[2];
-                        const T t1 = z0 * cwc[12] + z1 * cwc[13] + z2 * cwc[14];
-                        const int mx = iv > jw ? iv : jw;
-                        e = (T)2 * ((T)(H - mx) * t0 + w.St[iv * H + jw] * t1);
-                        if (pw == pv) {
-                            const T* zw = w.zt + 3 * wv;
-                            e += (T)2 * (z0 * zw[0] * (T)cs.r[3 * av] + z1 * zw[1] * (T)cs.r[3 * av + 1] +
-                                         z2 * zw[2] * (T)cs.r[3 * av + 2]);
-                        }
-                    }
-                    if (dead && wv == v) e = 1;
-                    acc[m][c] = e;
+            MPCQ_UNROLL
+            for (int c = 0; c < 4; ++c) {
+                const int jw = ci[c] & 0xff;
+                T q0, q1, q2, q3, s0, s1, s2, s3;
+                load4(w.cw + 4 * (8 * c + av), q0, q1, q2, q3);
+                load4(w.cw + 4 * (8 * c + 4 + av), s0, s1, s2, s3);
+                const T t0 = zr[m][0] * q0 + zr[m][1] * q1 + zr[m][2] * q2;
+                const T t1 = zr[m][0] * s0 + zr[m][1] * s1 + zr[m][2] * s2;
+                const int mx = iv > jw ? iv : jw;
+                T e = (T)2 * ((T)(H - mx) * t0 + w.St[iv * H + jw] * t1);
+                if (((ri[m] ^ ci[c]) >> 16) == 0) {          // same foot-step (and same dead flag): R term / unit diagonal
+                    const T* zw = w.zt + 3 * (k0 + c);
+                    e += (T)2 * (zr[m][0] * zw[0] * (T)cs.r[3 * av] + zr[m][1] * zw[1] * (T)cs.r[3 * av + 1] +
+                                 zr[m][2] * zw[2] * (T)cs.r[3 * av + 2]);
+                    if (dead && v == k0 + c) e = 1;
                 }
+                acc[m][c] = e;
             }
         }
         // ---- left-looking update with all previous columns
-        for (int g = 0; g < (k0 >> 2); ++g) {
-            const int stride = n - 4 * g;
-            const int cb = 4 * g * n - 8 * g * (g - 1) - 4 * g;
-            MPCQ_UNROLL
-            for (int t = 0; t < 4; ++t) {
-                const T* col = L + cb + t * stride;
-                T p0, p1, p2, p3;
-                load4(col + k0, p0, p1, p2, p3);
+        {
+            const T* col = L;
+            int stride = n;
+            for (int g = 0; g < (k0 >> 2); ++g) {
                 MPCQ_UNROLL
-                for (int m = 0; m < NSLOT; ++m) {
-                    const int v = lane + 32 * m;
-                    if (m >= m0 && v >= k0 && v < n) {
-                        const T lr = col[v];
+                for (int t = 0; t < 4; ++t) {
+                    T p0, p1, p2, p3;
+                    load4(col + k0, p0, p1, p2, p3);
+                    MPCQ_UNROLL
+                    for (int m = 0; m < NSLOT; ++m) {
+                        if (m < m0) continue;
+                        const T lr = col[lane + 32 * m];
                         acc[m][0] -= lr * p0; acc[m][1] -= lr * p1; acc[m][2] -= lr * p2; acc[m][3] -= lr * p3;
                     }
+                    col += stride;
                 }
+                col -= 4;
+                stride -= 4;
             }
+            colg = col;                                       // == L + colbase(k0, n)
         }
-        // ---- 4x4 diagonal block: fetched from its owner lanes, factored redundantly by every lane
-        const int ld = k0 & 31;
-        T a0 = acc[0][0], a1 = acc[0][1], a2 = acc[0][2], a3 = acc[0][3];
-        MPCQ_UNROLL
-        for (int m = 1; m < NSLOT; ++m)
-            if (m == m0) { a0 = acc[m][0]; a1 = acc[m][1]; a2 = acc[m][2]; a3 = acc[m][3]; }
-        const T d00 = wp::shfl(a0, ld);
-        const T d10 = wp::shfl(a0, ld + 1), d11 = wp::shfl(a1, ld + 1);
-        const T d20 = wp::shfl(a0, ld + 2), d21 = wp::shfl(a1, ld + 2), d22 = wp::shfl(a2, ld + 2);
-        const T d30 = wp::shfl(a0, ld + 3), d31 = wp::shfl(a1, ld + 3), d32 = wp::shfl(a2, ld + 3), d33 = wp::shfl(a3, ld + 3);
-        T piv = d00;
-        ok = ok && (piv > (T)0);
-        const T i0 = wp::rsqrt_(piv > (T)0 ? piv : (T)1);
-        const T l10 = d10 * i0, l20 = d20 * i0, l30 = d30 * i0;
-        piv = d11 - l10 * l10;
-        ok = ok && (piv > (T)0);
-        const T i1 = wp::rsqrt_(piv > (T)0 ? piv : (T)1);
-        const T l21 = (d21 - l20 * l10) * i1, l31 = (d31 - l30 * l10) * i1;
-        piv = d22 - l20 * l20 - l21 * l21;
-        ok = ok && (piv > (T)0);
-        const T i2 = wp::rsqrt_(piv > (T)0 ? piv : (T)1);
-        const T l32 = (d32 - l30 * l20 - l31 * l21) * i2;
-        piv = d33 - l30 * l30 - l31 * l31 - l32 * l32;
-        ok = ok && (piv > (T)0);
-        const T i3 = wp::rsqrt_(piv > (T)0 ? piv : (T)1);
-        if (lane == 0) {
-            T* db = w.dblk + 3 * k0;          // 12 values per block of 4 columns
-            db[0] = l10; db[1] = l20; db[2] = l21; db[3] = l30;
-            db[4] = l31; db[5] = l32; db[6] = i0; db[7] = i1;
-            db[8] = i2; db[9] = i3; db[10] = 0; db[11] = 0;
+        // ---- 4x4 diagonal block: kept, or fetched from its owner lanes and factored redundantly by every lane
+        T l10, l20, l21, l30, l31, l32, i0, i1, i2, i3;
+        if (keep_diag) {
+            T pad0, pad1;
+            const T* db = w.dblk + 3 * k0;
+            load4(db, l10, l20, l21, l30);
+            load4(db + 4, l31, l32, i0, i1);
+            load4(db + 8, i2, i3, pad0, pad1);
+        } else {
+            const int ld = k0 & 31, md = k0 >> 5;
+            T a0 = acc[0][0], a1 = acc[0][1], a2 = acc[0][2], a3 = acc[0][3];
+            MPCQ_UNROLL
+            for (int m = 1; m < NSLOT; ++m)
+                if (m == md) { a0 = acc[m][0]; a1 = acc[m][1]; a2 = acc[m][2]; a3 = acc[m][3]; }
+            const T d00 = wp::shfl(a0, ld);
+            const T d10 = wp::shfl(a0, ld + 1), d11 = wp::shfl(a1, ld + 1);
+            const T d20 = wp::shfl(a0, ld + 2), d21 = wp::shfl(a1, ld + 2), d22 = wp::shfl(a2, ld + 2);
+            const T d30 = wp::shfl(a0, ld + 3), d31 = wp::shfl(a1, ld + 3), d32 = wp::shfl(a2, ld + 3), d33 = wp::shfl(a3, ld + 3);
+            T piv = d00;
+            ok = ok && (piv > (T)0);
+            i0 = wp::rsqrt_(piv > (T)0 ? piv : (T)1);
+            l10 = d10 * i0; l20 = d20 * i0; l30 = d30 * i0;
+            piv = d11 - l10 * l10;
+            ok = ok && (piv > (T)0);
+            i1 = wp::rsqrt_(piv > (T)0 ? piv : (T)1);
+            l21 = (d21 - l20 * l10) * i1; l31 = (d31 - l30 * l10) * i1;
+            piv = d22 - l20 * l20 - l21 * l21;
+            ok = ok && (piv > (T)0);
+            i2 = wp::rsqrt_(piv > (T)0 ? piv : (T)1);
+            l32 = (d32 - l30 * l20 - l31 * l21) * i2;
+            piv = d33 - l30 * l30 - l31 * l31 - l32 * l32;
+            ok = ok && (piv > (T)0);
+            i3 = wp::rsqrt_(piv > (T)0 ? piv : (T)1);
+            if (lane == 0) {
+                T* db = w.dblk + 3 * k0;          // 12 values per block of 4 columns
+                db[0] = l10; db[1] = l20; db[2] = l21; db[3] = l30;
+                db[4] = l31; db[5] = l32; db[6] = i0; db[7] = i1;
+                db[8] = i2; db[9] = i3; db[10] = 0; db[11] = 0;
+            }
         }
         // ---- panel rows: x = acc * inv(Ld)'
         {
             const int stride = n - k0;
-            T* c0 = L + colbase(k0, n);
+            T* c0 = const_cast<T*>(colg);
             MPCQ_UNROLL
             for (int m = 0; m < NSLOT; ++m) {
                 const int v = lane + 32 * m;
-                if (m >= m0 && v >= k0 && v < n) {
+                if (m >= m0 && v >= row_lo && v < n) {
                     const T x0 = acc[m][0] * i0;
                     const T x1 = (acc[m][1] - x0 * l10) * i1;
                     const T x2 = (acc[m][2] - x0 * l20 - x1 * l21) * i2;
@@ -692,11 +750,62 @@ MPCQ_DEV FaceCheck pdas_update(const Consts& cs, Work<T>& w, bool write) {
     return fc;
 }
 
+// Stable partition of the stance list: foot-steps whose face is the one the current factor was built for
+// stay in front (same relative order), the changed ones move to the back.  The leading principal block of
+// K = Z'HZ - and therefore the leading columns of its Cholesky factor - is then unchanged, so the
+// factorisation restarts at the first changed column instead of column 0.  Returns that column (multiple of 4).
+template <class T, int NFS>
+MPCQ_DEV int reorder_feet(Work<T>& w) {
+    const int lane = wp::lane();
+    const int ns = w.ns;
+    unsigned balc[NFS];
+    int fc[NFS], ff[NFS], fkv[NFS];
+    double fm[NFS];
+    int n_changed = 0, first_changed = ns;
+    MPCQ_UNROLL
+    for (int t = 0; t < NFS; ++t) {
+        const int p = lane + 32 * t;
+        const bool valid = p < ns;
+        fc[t] = valid ? ((w.face[3 * p] & 0xff) | ((w.face[3 * p + 1] & 0xff) << 8) | ((w.face[3 * p + 2] & 0xff) << 16)) : 0;
+        ff[t] = valid ? ((w.facef[3 * p] & 0xff) | ((w.facef[3 * p + 1] & 0xff) << 8) | ((w.facef[3 * p + 2] & 0xff) << 16)) : 0;
+        fkv[t] = valid ? w.fk[p] : 0;
+        fm[t] = valid ? w.fmax[p] : 0.0;
+        balc[t] = wp::ballot(valid && fc[t] != ff[t]);
+        if (balc[t] != 0u && first_changed == ns) {
+            int b = 0;
+            while (!((balc[t] >> b) & 1u)) ++b;
+            first_changed = 32 * t + b;
+        }
+        n_changed += wp::popc(balc[t]);
+    }
+    if (n_changed == 0) return w.n;
+    const int n_unchanged = ns - n_changed;
+    wp::sync();
+    int cb_base = 0;
+    MPCQ_UNROLL
+    for (int t = 0; t < NFS; ++t) {
+        const int p = lane + 32 * t;
+        if (p < ns) {
+            const int cb = cb_base + wp::popc(balc[t] & ((1u << lane) - 1u));
+            const bool changed = (balc[t] >> lane) & 1u;
+            const int q = changed ? n_unchanged + cb : p - cb;
+            w.fk[q] = (uint8_t)fkv[t];
+            w.fmax[q] = fm[t];
+            w.face[3 * q] = (int8_t)(fc[t] & 0xff); w.face[3 * q + 1] = (int8_t)((fc[t] >> 8) & 0xff); w.face[3 * q + 2] = (int8_t)((fc[t] >> 16) & 0xff);
+            w.facef[3 * q] = (int8_t)(fc[t] & 0xff); w.facef[3 * q + 1] = (int8_t)((fc[t] >> 8) & 0xff); w.facef[3 * q + 2] = (int8_t)((fc[t] >> 16) & 0xff);
+        }
+        cb_base += wp::popc(balc[t]);
+    }
+    wp::sync();
+    return (3 * first_changed) & ~3;
+}
+
 // one factor-and-solve on the current faces: u = argmin on the faces (to tol), gam = Hu+g
-template <class T, int NSLOT>
+template <class T, int NSLOT, int NFS>
 MPCQ_DEV bool face_solve(const Consts& cs, Work<T>& w, double tol_abs, double& rmax) {
+    const int k_start = reorder_feet<T, NFS>(w);
     const bool cnz = build_slots(cs, w);
-    const bool ok = chol_factor<T, NSLOT>(cs, w);
+    const bool ok = k_start < w.n ? chol_factor<T, NSLOT>(cs, w, k_start) : true;
     rmax = refine<T, NSLOT>(cs, w, tol_abs, !cnz);
     return ok;
 }
@@ -706,14 +815,14 @@ MPCQ_DEV bool face_solve(const Consts& cs, Work<T>& w, double tol_abs, double& r
 // The start point and its faces are derived from the point alone: every foot is moved into K and
 // a row is taken active when the point sits on it (or beyond it) within the primal tolerance.
 template <class T>
-MPCQ_DEV void clamp_to_feasible(const Consts& cs, Work<T>& w) {
+MPCQ_DEV void clamp_into(const Consts& cs, Work<T>& w, const double* src, double* dst, int8_t* fdst) {
     const int lane = wp::lane();
     const double mu = cs.mu;
-    for (int idx = lane; idx < 12 * cs.horizon; idx += 32) w.ucur[idx] = 0.0;
+    for (int idx = lane; idx < 12 * cs.horizon; idx += 32) dst[idx] = 0.0;
     wp::sync();
     for (int p = lane; p < w.ns; p += 32) {
-        const double* f = w.u + 3 * w.fk[p];
-        double* o = w.ucur + 3 * w.fk[p];
+        const double* f = src + 3 * w.fk[p];
+        double* o = dst + 3 * w.fk[p];
         const double fm = w.fmax[p];
         const double tp = cs.tol_p * (1.0 + dmax(dabs(f[0]), dmax(dabs(f[1]), dabs(f[2]))));
         int sx = 0, sy = 0, sz = 0;
@@ -728,9 +837,28 @@ MPCQ_DEV void clamp_to_feasible(const Consts& cs, Work<T>& w) {
             if (fy >= mu * fz - tp) { fy = mu * fz; sy = 1; } else if (fy <= -mu * fz + tp) { fy = -mu * fz; sy = -1; }
             o[0] = fx; o[1] = fy; o[2] = fz;
         }
-        w.face[3 * p] = (int8_t)sx; w.face[3 * p + 1] = (int8_t)sy; w.face[3 * p + 2] = (int8_t)sz;
+        fdst[3 * p] = (int8_t)sx; fdst[3 * p + 1] = (int8_t)sy; fdst[3 * p + 2] = (int8_t)sz;
     }
     wp::sync();
+}
+
+// phi(v) = 1/2 v'Hv + g'v = 1/2 v'(gam + g) for the vector v currently in w.u with w.gam = Hv + g
+template <class T>
+MPCQ_DEV double objective(const Consts& cs, Work<T>& w) {
+    double s = 0.0;
+    for (int idx = wp::lane(); idx < 12 * cs.horizon; idx += 32) s += w.u[idx] * (w.gam[idx] + w.g[idx]);
+    return 0.5 * wp::reduce_sum(s);
+}
+
+// objective of an arbitrary vector (temporarily viewed as w.u); clobbers w.gam
+template <class T>
+MPCQ_DEV double objective_of(const Consts& cs, Work<T>& w, double* v) {
+    double* keep = w.u;
+    w.u = v;
+    hess_apply(cs, w);
+    const double phi = objective(cs, w);
+    w.u = keep;
+    return phi;
 }
 
 MPCQ_DEV void row_slacks(const double* f, double mu, double fm, double (&s)[6]) {
@@ -739,14 +867,14 @@ MPCQ_DEV void row_slacks(const double* f, double mu, double fm, double (&s)[6]) 
     s[4] = f[2]; s[5] = fm - f[2];
 }
 
-// returns: 0 = moved / face changed, keep going; 1 = optimal
+// ratio test from the feasible point ucur towards the face minimiser u: largest alpha in [0,1] keeping every
+// inactive row satisfied, and the (foot, row) that blocks (tag = 8*p + row, 0x7fffffff if none)
 template <class T>
-MPCQ_DEV int active_set_step(const Consts& cs, Work<T>& w) {
+MPCQ_DEV void ratio_test(const Consts& cs, Work<T>& w, double& alpha, int& tag) {
     const int lane = wp::lane();
     const double mu = cs.mu;
-    // --- ratio test from ucur towards the face minimiser u
-    double alpha = 1.0;
-    int tag = 0x7fffffff;
+    alpha = 1.0;
+    tag = 0x7fffffff;
     for (int p = lane; p < w.ns; p += 32) {
         const int sx = w.face[3 * p], sy = w.face[3 * p + 1], sz = w.face[3 * p + 2];
         if (sz < 0) continue;
@@ -768,64 +896,71 @@ MPCQ_DEV int active_set_step(const Consts& cs, Work<T>& w) {
         }
     }
     wp::reduce_argmin(alpha, tag);
-    const bool blocked = tag != 0x7fffffff;
-    if (!blocked) alpha = 1.0;
-#if defined(MPCQ_HOST_EMU) && defined(MPCQ_TRACE)
-    if (lane == 0 && blocked) printf("  AS block p=%d (k=%d) row=%d alpha=%.3e\n", tag >> 3, w.fk[tag >> 3], tag & 7, alpha);
-#endif
+    if (tag == 0x7fffffff) alpha = 1.0;
+}
+
+// degenerate case alpha = 0: ucur cannot move because rows it already sits on would be violated.  Make ALL of
+// them part of their faces at once (instead of one factorisation per row).
+template <class T>
+MPCQ_DEV void block_all_at_zero(const Consts& cs, Work<T>& w) {
+    const int lane = wp::lane();
+    const double mu = cs.mu;
+    for (int p = lane; p < w.ns; p += 32) {
+        int sx = w.face[3 * p], sy = w.face[3 * p + 1], sz = w.face[3 * p + 2];
+        if (sz < 0) continue;
+        double* f0 = w.ucur + 3 * w.fk[p];
+        const double* f1 = w.u + 3 * w.fk[p];
+        double s0[6], s1[6];
+        row_slacks(f0, mu, w.fmax[p], s0);
+        row_slacks(f1, mu, w.fmax[p], s1);
+        const double sc = 1.0 + dmax(dabs(f1[0]), dmax(dabs(f1[1]), dabs(f1[2])));
+        const bool act[6] = {sx == -1, sx == 1, sy == -1, sy == 1, false, sz == 1};
+        bool hit[6];
+        bool any_hit = false;
+        MPCQ_UNROLL
+        for (int r = 0; r < 6; ++r) {
+            const double ds = s1[r] - s0[r];
+            hit[r] = !act[r] && s1[r] < -cs.tol_p * sc && ds < 0 && s0[r] <= 1e-12 * sc;
+            any_hit = any_hit || hit[r];
+        }
+        if (!any_hit) continue;
+        const bool apex = hit[4] || (hit[0] && (sx == 1 || hit[1])) || (hit[1] && sx == -1) ||
+                          (hit[2] && (sy == 1 || hit[3])) || (hit[3] && sy == -1);
+        if (hit[0]) sx = -1; else if (hit[1]) sx = 1;
+        if (hit[2]) sy = -1; else if (hit[3]) sy = 1;
+        if (hit[5]) sz = 1;
+        if (apex || !(f0[2] > 0.0)) { sz = -1; f0[0] = f0[1] = f0[2] = 0.0; }
+        else {
+            if (sz == 1) f0[2] = w.fmax[p];
+            if (sx != 0) f0[0] = sx * mu * f0[2];
+            if (sy != 0) f0[1] = sy * mu * f0[2];
+        }
+        w.face[3 * p] = (int8_t)sx; w.face[3 * p + 1] = (int8_t)sy; w.face[3 * p + 2] = (int8_t)sz;
+    }
+    wp::sync();
+}
+
+// move ucur by alpha towards u and make the blocking row part of its foot's face
+template <class T>
+MPCQ_DEV void blocked_step(const Consts& cs, Work<T>& w, double alpha, int tag) {
+    const int lane = wp::lane();
     for (int idx = lane; idx < 12 * cs.horizon; idx += 32) w.ucur[idx] += alpha * (w.u[idx] - w.ucur[idx]);
     wp::sync();
-    if (blocked) {
-        if (lane == 0) {
-            const int p = tag >> 3, r = tag & 7;
-            int sx = w.face[3 * p], sy = w.face[3 * p + 1], sz = w.face[3 * p + 2];
-            bool apex = (r == 4) || (r == 0 && sx == 1) || (r == 1 && sx == -1) || (r == 2 && sy == 1) || (r == 3 && sy == -1);
-            if (r == 0) sx = -1; else if (r == 1) sx = 1; else if (r == 2) sy = -1; else if (r == 3) sy = 1; else if (r == 5) sz = 1;
-            double* f = w.ucur + 3 * w.fk[p];
-            if (apex || !(f[2] > 0.0)) { sz = -1; f[0] = f[1] = f[2] = 0.0; }
-            w.face[3 * p] = (int8_t)sx; w.face[3 * p + 1] = (int8_t)sy; w.face[3 * p + 2] = (int8_t)sz;
-        }
-        wp::sync();
-        return 0;
-    }
-    // --- at the face minimiser (gam is current): release the most negative multiplier
-    double worst = 0.0;
-    int rel = 0x7fffffff;
-    for (int p = lane; p < w.ns; p += 32) {
-        const int sx = w.face[3 * p], sy = w.face[3 * p + 1], sz = w.face[3 * p + 2];
-        const double* ga = w.gam + 3 * w.fk[p];
-        const double gs = 1.0 + dmax(dabs(ga[0]), dmax(dabs(ga[1]), dabs(ga[2])));
-        if (sz < 0) {
-            const double v = (ga[2] - mu * (dabs(ga[0]) + dabs(ga[1]))) / gs;
-            if (v < -cs.tol_d && v < worst) { worst = v; rel = p * 8 + 4; }
-        } else {
-            const double lx = sx != 0 ? -sx * ga[0] : 0.0, ly = sy != 0 ? -sy * ga[1] : 0.0;
-            if (sx != 0 && lx / gs < -cs.tol_d && lx / gs < worst) { worst = lx / gs; rel = p * 8 + 0; }
-            if (sy != 0 && ly / gs < -cs.tol_d && ly / gs < worst) { worst = ly / gs; rel = p * 8 + 2; }
-            if (sz > 0) {
-                const double lt = (-ga[2] + mu * (lx + ly)) / gs;
-                if (lt < -cs.tol_d && lt < worst) { worst = lt; rel = p * 8 + 5; }
-            }
-        }
-    }
-    wp::reduce_argmin(worst, rel);
-#if defined(MPCQ_HOST_EMU) && defined(MPCQ_TRACE)
-    if (lane == 0 && rel != 0x7fffffff) printf("  AS release p=%d (k=%d) row=%d mult=%.3e\n", rel >> 3, w.fk[rel >> 3], rel & 7, worst);
-#endif
-    if (rel == 0x7fffffff) return 1;
     if (lane == 0) {
-        const int p = rel >> 3, r = rel & 7;
-        const double* ga = w.gam + 3 * w.fk[p];
-        if (r == 4) {
-            w.face[3 * p] = (int8_t)(ga[0] > 0 ? -1 : (ga[0] < 0 ? 1 : 0));
-            w.face[3 * p + 1] = (int8_t)(ga[1] > 0 ? -1 : (ga[1] < 0 ? 1 : 0));
-            w.face[3 * p + 2] = 0;
-        } else if (r == 0) w.face[3 * p] = 0;
-        else if (r == 2) w.face[3 * p + 1] = 0;
-        else w.face[3 * p + 2] = 0;
+        const int p = tag >> 3, r = tag & 7;
+        int sx = w.face[3 * p], sy = w.face[3 * p + 1], sz = w.face[3 * p + 2];
+        const bool apex = (r == 4) || (r == 0 && sx == 1) || (r == 1 && sx == -1) || (r == 2 && sy == 1) || (r == 3 && sy == -1);
+        if (r == 0) sx = -1; else if (r == 1) sx = 1; else if (r == 2) sy = -1; else if (r == 3) sy = 1; else if (r == 5) sz = 1;
+        double* f = w.ucur + 3 * w.fk[p];
+        if (apex || !(f[2] > 0.0)) { sz = -1; f[0] = f[1] = f[2] = 0.0; }
+        else {                                              // put the point exactly on the new face
+            if (sz == 1) f[2] = w.fmax[p];
+            if (sx != 0) f[0] = sx * cs.mu * f[2];
+            if (sy != 0) f[1] = sy * cs.mu * f[2];
+        }
+        w.face[3 * p] = (int8_t)sx; w.face[3 * p + 1] = (int8_t)sy; w.face[3 * p + 2] = (int8_t)sz;
     }
     wp::sync();
-    return 0;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -833,6 +968,7 @@ MPCQ_DEV int active_set_step(const Consts& cs, Work<T>& w) {
 template <class T, int NCAP>
 MPCQ_DEV void solve_env(const Consts& cs, const IO<T>& io, int b, char* smem, T* l_global, int ns_lo, int ns_hi) {
     constexpr int NSLOT = NCAP / 32;
+    constexpr int NFS = (NCAP / 3 + 31) / 32;
     const int lane = wp::lane();
     const int H = cs.horizon;
     Work<T> w;
@@ -846,7 +982,8 @@ MPCQ_DEV void solve_env(const Consts& cs, const IO<T>& io, int b, char* smem, T*
         const bool st = fm > 0.0;
         const unsigned bal = wp::ballot(st);
         const int pos = ns + wp::popc(bal & ((1u << lane) - 1u));
-        if (st && pos < NCAP / 3) { w.fk[pos] = (uint8_t)k; w.fmax[pos] = fm; w.face[3 * pos] = 0; w.face[3 * pos + 1] = 0; w.face[3 * pos + 2] = 0; }
+        if (st && pos < NCAP / 3) { w.fk[pos] = (uint8_t)k; w.fmax[pos] = fm; w.face[3 * pos] = 0; w.face[3 * pos + 1] = 0; w.face[3 * pos + 2] = 0;
+                                      w.facef[3 * pos] = 99; w.facef[3 * pos + 1] = 99; w.facef[3 * pos + 2] = 99; }
         ns += wp::popc(bal);
     }
     if (ns < ns_lo || ns > ns_hi) return;                       // another size class owns this env
@@ -870,7 +1007,7 @@ MPCQ_DEV void solve_env(const Consts& cs, const IO<T>& io, int b, char* smem, T*
         bool done = false;
         // ---- primal-dual active-set rounds
         for (int round = 0; round <= cs.pdas_cap && numeric_ok && !done; ++round) {
-            numeric_ok = face_solve<T, NSLOT>(cs, w, tol_loose, rmax) && numeric_ok;
+            numeric_ok = face_solve<T, NSLOT, NFS>(cs, w, tol_loose, rmax) && numeric_ok;
             ++nfac;
             FaceCheck fc = pdas_update(cs, w, false);
             if (fc.n_primal == 0 && fc.n_dual == 0) {
@@ -883,15 +1020,50 @@ MPCQ_DEV void solve_env(const Consts& cs, const IO<T>& io, int b, char* smem, T*
 #endif
             pdas_update(cs, w, true);
         }
-        // ---- fallback: feasible primal active set (monotone, cannot cycle)
+        // ---- fallback: monotone projected active-set method.  Keeps a FEASIBLE iterate ucur whose objective
+        // strictly decreases: from the face minimiser u either (a) u is feasible -> take it and release every
+        // wrong-signed multiplier, or (b) the clamped point clamp(u) lowers the objective -> take it with the
+        // faces it lands on (many rows change at once), or (c) step to the first blocking row (ratio test).
         if (!done && numeric_ok) {
             status |= ST_FALLBACK;
-            clamp_to_feasible(cs, w);
+            clamp_into(cs, w, w.u, w.ucur, w.face);
+            double phi_cur = objective_of(cs, w, w.ucur);
             for (nas = 1; nas <= cs.as_cap; ++nas) {
-                numeric_ok = face_solve<T, NSLOT>(cs, w, tol_tight, rmax) && numeric_ok;
+                numeric_ok = face_solve<T, NSLOT, NFS>(cs, w, tol_tight, rmax) && numeric_ok;
                 ++nfac;
                 if (!numeric_ok) break;
-                if (active_set_step(cs, w) == 1) { done = true; break; }
+                double alpha;
+                int tag;
+                ratio_test(cs, w, alpha, tag);
+#if defined(MPCQ_HOST_EMU) && defined(MPCQ_TRACE)
+                if (lane == 0) printf("  AS it %d: alpha %.3e tag %d phi_cur %.10e rmax %.2e\n", nas, alpha, tag, phi_cur, rmax);
+#endif
+                if (tag == 0x7fffffff) {                    // (a)
+                    for (int idx = lane; idx < 12 * H; idx += 32) w.ucur[idx] = w.u[idx];
+                    phi_cur = objective(cs, w);
+                    const FaceCheck fc = pdas_update(cs, w, true);
+#if defined(MPCQ_HOST_EMU) && defined(MPCQ_TRACE)
+                    if (lane == 0) printf("     feasible minimiser: primal %d dual %d\n", fc.n_primal, fc.n_dual);
+#endif
+                    if (fc.n_primal == 0 && fc.n_dual == 0) { done = true; break; }
+                    continue;
+                }
+                clamp_into(cs, w, w.u, w.utrial, w.face2);
+                const double phi_t = objective_of(cs, w, w.utrial);
+#if defined(MPCQ_HOST_EMU) && defined(MPCQ_TRACE)
+                if (lane == 0) printf("     trial phi %.10e -> %s\n", phi_t, phi_t < phi_cur - 1e-12 * dabs(phi_cur) ? "accept" : "ratio step");
+#endif
+                if (phi_t < phi_cur - 1e-12 * dabs(phi_cur)) {   // (b)
+                    for (int idx = lane; idx < 12 * H; idx += 32) w.ucur[idx] = w.utrial[idx];
+                    for (int idx = lane; idx < 3 * w.ns; idx += 32) w.face[idx] = w.face2[idx];
+                    wp::sync();
+                    phi_cur = phi_t;
+                } else if (alpha <= 1e-13) {                // (c0) degenerate: no move possible, fix every such row
+                    block_all_at_zero(cs, w);
+                } else {                                    // (c)
+                    blocked_step(cs, w, alpha, tag);
+                    phi_cur = objective_of(cs, w, w.ucur);
+                }
             }
             if (!done) {                                   // return the feasible iterate
                 for (int idx = lane; idx < 12 * H; idx += 32) w.u[idx] = w.ucur[idx];

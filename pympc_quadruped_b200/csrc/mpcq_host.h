@@ -41,7 +41,7 @@ inline bool consts_from_config(const mpcq_config& c, Consts& k, std::string& err
     k.tol_p = c.tol_primal > 0 ? c.tol_primal : (f64 ? 1e-9 : 1e-7);
     k.tol_d = c.tol_dual > 0 ? c.tol_dual : (f64 ? 1e-9 : 1e-7);
     k.tol_r_tight = c.tol_residual > 0 ? c.tol_residual : (f64 ? 1e-12 : 1e-9);
-    k.tol_r_loose = f64 ? 1e-9 : 1e-6;
+    k.tol_r_loose = c.tol_residual_loose > 0 ? c.tol_residual_loose : (f64 ? 1e-9 : 1e-6);
     if (k.tol_r_loose < k.tol_r_tight) k.tol_r_loose = k.tol_r_tight;
     k.tol_active = c.tol_active > 0 ? c.tol_active : 1e-6;
     double det = c.inertia[0] * (c.inertia[4] * c.inertia[8] - c.inertia[5] * c.inertia[7]) -

@@ -48,7 +48,8 @@ class MpcqEngine:
         self._h = C.c_void_p()
         rc = self.lib.mpcq_create(C.byref(cfg), C.byref(self._h))
         if rc != 0:
-            raise RuntimeError(f"mpcq_create failed ({rc}): {self.lib.mpcq_last_error(None).decode()}")
+            msg = f"mpcq_create failed ({rc}): {self.lib.mpcq_last_error(None).decode()}"
+            raise ValueError(msg) if rc in (-1, -4) else RuntimeError(msg)     # invalid / unsupported configuration
 
     def close(self):
         if getattr(self, "_h", None) and self._h.value:

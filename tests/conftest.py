@@ -11,6 +11,15 @@ os.environ.setdefault("OMP_NUM_THREADS", "1")
 os.environ.setdefault("OPENBLAS_NUM_THREADS", "1")
 
 
+def load_module(name, path):
+    """import a build script by path (both build scripts are called build.py)"""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location(name, path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
 
@@ -19,9 +28,7 @@ def pytest_configure(config):
 def emu_lib():
     """TEST-ONLY host emulation of the device code (see tests/emu/mpcq_emu.cpp)."""
     import ctypes
-    sys.path.insert(0, os.path.join(ROOT, "tests", "emu"))
-    import build as emu_build
-    return ctypes.CDLL(emu_build.build())
+    return ctypes.CDLL(load_module("mpcq_emu_build", os.path.join(ROOT, "tests", "emu", "build.py")).build())
 
 
 @pytest.fixture(scope="session", autouse=True)

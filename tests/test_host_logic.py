@@ -24,15 +24,13 @@ def test_c_abi_library_exports_every_declared_symbol():
     header = open(os.path.join(ROOT, "include", "mpcq.h")).read()
     declared = set(re.findall(r"^\s*(?:const\s+char\*|int|void)\s+(mpcq_\w+)\s*\(", header, flags=re.M))
     assert declared == set(_capi.EXPORTS), declared ^ set(_capi.EXPORTS)
-    import sys
-    sys.path.insert(0, os.path.join(ROOT, "pympc_quadruped_b200", "csrc"))
-    import build as build_mod
-    lib = ctypes.CDLL(build_mod.build())
+    from conftest import load_module
+    lib = ctypes.CDLL(load_module("mpcq_lib_build", os.path.join(ROOT, "pympc_quadruped_b200", "csrc", "build.py")).build())
     for name in declared:
         assert hasattr(lib, name), name
     assert lib.mpcq_version() == 100
     # struct mirror has the C layout's size: 4 ints + 5 doubles + 34 doubles + 4 ints + 4 doubles
-    assert ctypes.sizeof(_capi.MpcqConfig) == 16 + 8 * 5 + 8 * 34 + 16 + 32
+    assert ctypes.sizeof(_capi.MpcqConfig) == 16 + 8 * 5 + 8 * 34 + 16 + 40
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="CPU-only check")
