@@ -41,7 +41,13 @@ mpcq_build_qp_kernel(const __grid_constant__ Consts cs, const __grid_constant__ 
     extern __shared__ __align__(32) char smem[];
     const int b = blockIdx.x, lane = threadIdx.x, H = cs.horizon, n = 12 * H;
     mpcq::Work<T> w;
-    mpcq::carve<T>(w, smem, nullptr, H, 64, true);
+    mpcq::carve<T>(w, smem, reinterpret_cast<T*>(smem), H, 384, true);   // no factor needed: vectors only
+    // every foot-step counts as stance here so that g comes out in the full [H][12] layout
+    for (int k = lane; k < 4 * H; k += 32) { w.fk[k] = (uint8_t)k; w.fo[k] = (uint8_t)k; w.cidx[k] = (uint8_t)k; }
+    w.ns = 4 * H;
+    w.nv = 12 * H;
+    w.n = 12 * H;
+    __syncwarp();
     const double yaw = io.yaw ? (double)io.yaw[b] : (double)io.x0[(size_t)b * 13 + 2];
     mpcq::setup_model(cs, w, io.x0 + (size_t)b * 13, yaw, io.r_feet + (size_t)b * 12, io.x_ref + (size_t)b * 13 * H);
     double* Hb = Hout + (size_t)b * n * n;
@@ -50,7 +56,7 @@ mpcq_build_qp_kernel(const __grid_constant__ Consts cs, const __grid_constant__ 
         for (int col = lane; col < n; col += 32) {
             const int j = col / 12, c = col - 12 * j;
             const int m = i > j ? i : j;
-            double v = 2.0 * ((double)(H - m) * w.Md[12 * r + c] + w.Sd[i * H + j] * w.Md[144 + 12 * r + c]);
+            double v = 2.0 * ((double)(H - m) * w.Md[12 * r + c] + (double)w.St[i * H + j] * w.Md[144 + 12 * r + c]);
             if (row == col) v += 2.0 * cs.r[r];
             Hb[(size_t)row * n + col] = v;
         }
@@ -175,10 +181,11 @@ cudaError_t configure(mpcq_handle* h) {
     size_t gws_elems = 0;
     for (int ci = 0; ci < h->ncls; ++ci) {
         const int ncap = mpcq::kClasses[ci].ncap;
-        size_t s = mpcq::work_bytes<T>(H, ncap, true);
+        const int nmax = mpcq::class_nmax(mpcq::kClasses[ci]);
+        size_t s = mpcq::work_bytes<T>(H, ncap, true, false, nmax);
         h->lglobal[ci] = s > kMaxSmem || ncap >= 384;
         if (h->lglobal[ci]) {
-            s = mpcq::work_bytes<T>(H, ncap, false);
+            s = mpcq::work_bytes<T>(H, ncap, false, false, nmax);
             if (s > kMaxSmem) return cudaErrorInvalidValue;
             size_t need = (size_t)mpcq::l_elems(ncap);
             need = (need + 31) / 32 * 32;
@@ -197,7 +204,7 @@ cudaError_t configure(mpcq_handle* h) {
     }
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(mpcq_build_qp_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)mpcq::work_bytes<T>(H, 64, true, true));
+                             (int)mpcq::work_bytes<T>(H, 384, false, true));
     if (e != cudaSuccess) return e;
     if (gws_elems) {
         h->gws_stride = gws_elems;
@@ -302,10 +309,10 @@ int mpcq_build_qp(mpcq_handle* h, int32_t B, const void* x0, const void* yaw, co
     const int H = h->cs.horizon;
     if (h->cfg.dtype == MPCQ_F64) {
         IO<double> io = make_io<double>(B, x0, yaw, r_feet, gait, x_ref, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
-        mpcq_build_qp_kernel<double><<<B, 32, mpcq::work_bytes<double>(H, 64, true, true), st>>>(h->cs, io, H_out, g_out, ub_out);
+        mpcq_build_qp_kernel<double><<<B, 32, mpcq::work_bytes<double>(H, 384, false, true), st>>>(h->cs, io, H_out, g_out, ub_out);
     } else {
         IO<float> io = make_io<float>(B, x0, yaw, r_feet, gait, x_ref, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
-        mpcq_build_qp_kernel<float><<<B, 32, mpcq::work_bytes<float>(H, 64, true, true), st>>>(h->cs, io, H_out, g_out, ub_out);
+        mpcq_build_qp_kernel<float><<<B, 32, mpcq::work_bytes<float>(H, 384, false, true), st>>>(h->cs, io, H_out, g_out, ub_out);
     }
     h->last_launches = 1;
     return cuda_ok(h, cudaGetLastError(), "mpcq_build_qp launch") ? MPCQ_OK : MPCQ_ERR_CUDA;

@@ -68,47 +68,50 @@ MPCQ_HD constexpr int l_elems(int n) { return n * n / 2 + 2 * n + 32; }   // +32
 
 template <class T> struct Work {
     // fp64
-    double *Md, *Sd, *GW, *g, *u, *gam, *P0, *P1, *ucur, *utrial, *fmax;
+    double *Md, *GW, *g, *u, *gam, *P0, *P1, *ucur, *utrial, *fmax;
     // precision T
     T *L, *dblk, *vec, *cw, *zt, *Mf, *St;
     int32_t* sinf;         // per slot: step | leg << 8 | foot << 16 | dead << 30
     // bytes
     uint8_t *fk;           // stance list: full foot-step index k = 4*step + leg
+    uint8_t *fo;           // stance index (position in the ORIGINAL stance list) of the foot now at position p;
+                           // the fp64 vectors g, u, gam, ucur, utrial are stored in that fixed compact order
+    uint8_t *cidx;         // full foot-step k -> stance index, 255 = swing
     int8_t* face;          // 3 per stance foot-step
     int8_t* face2;         // trial faces of the fallback
     int8_t* facef;         // faces the current factor was built for
-    int n, ns, H;
+    int n, ns, H, nv;      // nv = 3 * ns: live length of the compact vectors
 };
 
 template <class T>
-MPCQ_HD constexpr size_t work_bytes(int H, int ncap, bool l_in_smem, bool with_md = false) {
-    size_t nd = (with_md ? 288 : 0) + (size_t)H * H + 72 + 7 * 12 * (size_t)H + ncap / 3 + 1;
-    size_t nt = (l_in_smem ? l_elems(ncap) : 0) + 3 * (ncap / 4) * 4 + ncap + 128 + 3 * ncap + 288 + (size_t)H * H;
-    size_t nb = (ncap / 3 + 1) * 10 + 16 + 4 * (size_t)ncap;
+MPCQ_HD constexpr size_t work_bytes(int H, int ncap, bool l_in_smem, bool with_md = false, int nmax = 0) {
+    size_t nd = (with_md ? 288 : 0) + 72 + 2 * 12 * (size_t)H + 5 * (size_t)ncap + ncap / 3 + 1;
+    size_t nt = (l_in_smem ? l_elems(nmax > 0 ? nmax : ncap) : 0) + 3 * (ncap / 4) * 4 + ncap + 128 + 3 * ncap + 288 + (size_t)H * H;
+    size_t nb = (ncap / 3 + 1) * 11 + 4 * (size_t)H + 16 + 4 * (size_t)ncap;
     return align_up(nd * 8, 16) + align_up(nt * sizeof(T), 16) + align_up(nb, 16);
 }
 
 template <class T>
-MPCQ_DEV void carve(Work<T>& w, char* base, T* l_global, int H, int ncap, bool with_md = false) {
+MPCQ_DEV void carve(Work<T>& w, char* base, T* l_global, int H, int ncap, bool with_md = false, int nmax = 0) {
     double* d = reinterpret_cast<double*>(base);
     w.Md = with_md ? d : nullptr; d += with_md ? 288 : 0;
-    w.Sd = d; d += H * H;
     w.GW = d; d += 72;
-    w.g = d; d += 12 * H;
-    w.u = d; d += 12 * H;
-    w.gam = d; d += 12 * H;
-    w.P0 = d; d += 12 * H;
+    w.g = d; d += ncap;
+    w.u = d; d += ncap;
+    w.gam = d; d += ncap;
+    w.P0 = d; d += 12 * H;       // 9H used by hess_apply, 12H by setup_model
     w.P1 = d; d += 12 * H;
-    w.ucur = d; d += 12 * H;
-    w.utrial = d; d += 12 * H;
+    w.ucur = d; d += ncap;
+    w.utrial = d; d += ncap;
     w.fmax = d; d += ncap / 3 + 1;
-    size_t nd = (with_md ? 288 : 0) + (size_t)H * H + 72 + 7 * 12 * (size_t)H + ncap / 3 + 1;
+    size_t nd = (with_md ? 288 : 0) + 72 + 2 * 12 * (size_t)H + 5 * (size_t)ncap + ncap / 3 + 1;
     T* t = reinterpret_cast<T*>(base + align_up(nd * 8, 16));
     size_t used = 0;
     if (l_global) {
         w.L = l_global;
     } else {
-        w.L = t; t += l_elems(ncap); used += l_elems(ncap);
+        const int le = l_elems(nmax > 0 ? nmax : ncap);
+        w.L = t; t += le; used += le;
     }
     w.dblk = t; t += 3 * (ncap / 4) * 4; used += 3 * (ncap / 4) * 4;
     w.vec = t; t += ncap; used += ncap;
@@ -118,6 +121,8 @@ MPCQ_DEV void carve(Work<T>& w, char* base, T* l_global, int H, int ncap, bool w
     w.St = t; t += H * H; used += (size_t)H * H;
     uint8_t* b = reinterpret_cast<uint8_t*>(base + align_up(nd * 8, 16) + align_up(used * sizeof(T), 16));
     w.fk = b; b += ncap / 3 + 1;
+    w.fo = b; b += ncap / 3 + 1;
+    w.cidx = b; b += 4 * H;
     w.face = reinterpret_cast<int8_t*>(b); b += 3 * (ncap / 3 + 1);
     w.face2 = reinterpret_cast<int8_t*>(b); b += 3 * (ncap / 3 + 1);
     w.facef = reinterpret_cast<int8_t*>(b); b += 3 * (ncap / 3 + 1);
@@ -227,14 +232,13 @@ MPCQ_DEV void setup_model(const Consts& cs, Work<T>& w, const T* x0p, double yaw
                 w.GW[18 * a + 9 + 3 * k + y] = acc;
             }
     }
-    // --- horizon table S (fp64 and T)
+    // --- horizon table S
     for (int idx = lane; idx < H * H; idx += 32) {
         const int i = idx / H, j = idx - i * H;
         const int m = i > j ? i : j;
         const double a = m - i + 0.5, b = m - j + 0.5, Ln = H - m;
         const double sv = Ln * a * b + (a + b) * Ln * (Ln - 1) * 0.5 + (Ln - 1) * Ln * (2 * Ln - 1) / 6.0;
-        w.Sd[idx] = sv;
-        w.St[idx] = (T)sv;
+        w.St[idx] = (T)sv;                                  // multiples of 1/4 below 2^17: exact in float
     }
     wp::sync();
     // --- M00 = B0'QB0, M11 = B1'QB1
@@ -278,8 +282,8 @@ MPCQ_DEV void setup_model(const Consts& cs, Work<T>& w, const T* x0p, double yaw
         }
     }
     wp::sync();
-    for (int idx = lane; idx < 12 * H; idx += 32) {
-        const int j = idx / 12, rr = idx - 12 * j, a = rr / 3, y = rr - 3 * a;
+    for (int v = lane; v < w.nv; v += 32) {
+        const int p = v / 3, y = v - 3 * p, j = w.fk[p] >> 2, a = w.fk[p] & 3;
         const double* E0 = w.P0 + 12 * j;
         const double* E1 = w.P1 + 12 * j;
         double t0 = cs.inv_mass * E0[9 + y], t1 = cs.inv_mass * E1[3 + y];
@@ -288,7 +292,7 @@ MPCQ_DEV void setup_model(const Consts& cs, Work<T>& w, const T* x0p, double yaw
             t0 += w.GW[18 * a + 3 * k + y] * E0[6 + k];
             t1 += w.GW[18 * a + 9 + 3 * k + y] * E1[k];
         }
-        w.g[idx] = 2.0 * (dt * t0 + dt2 * t1);
+        w.g[3 * w.fo[p] + y] = 2.0 * (dt * t0 + dt2 * t1);
     }
     wp::sync();
 }
@@ -302,16 +306,26 @@ MPCQ_DEV void hess_apply(const Consts& cs, Work<T>& w) {
     const int H = cs.horizon;
     for (int idx = lane; idx < 9 * H; idx += 32) {
         const int i = idx / 9, k = idx - 9 * i;
-        const double* ui = w.u + 12 * i;
         double y = 0;
         if (k < 6) {
             const double* gw = w.GW + (k < 3 ? 3 * k : 9 + 3 * (k - 3));
             MPCQ_UNROLL
-            for (int a = 0; a < 4; ++a) y += gw[18 * a] * ui[3 * a] + gw[18 * a + 1] * ui[3 * a + 1] + gw[18 * a + 2] * ui[3 * a + 2];
+            for (int a = 0; a < 4; ++a) {
+                const int s = w.cidx[4 * i + a];
+                if (s != 255) {
+                    const double* ua = w.u + 3 * s;
+                    y += gw[18 * a] * ua[0] + gw[18 * a + 1] * ua[1] + gw[18 * a + 2] * ua[2];
+                }
+            }
             y *= k < 3 ? cs.q[6 + k] : cs.q[k - 3];
         } else {
             const int x = k - 6;
-            y = cs.inv_mass * (ui[x] + ui[3 + x] + ui[6 + x] + ui[9 + x]);
+            MPCQ_UNROLL
+            for (int a = 0; a < 4; ++a) {
+                const int s = w.cidx[4 * i + a];
+                if (s != 255) y += w.u[3 * s + x];
+            }
+            y *= cs.inv_mass;
         }
         w.P0[idx] = y;
     }
@@ -322,7 +336,7 @@ MPCQ_DEV void hess_apply(const Consts& cs, Work<T>& w) {
         const int src = c < 3 ? c : c < 6 ? 3 + c : c < 9 ? c - 3 : c - 3;     // y0r | fs | y1r | fs
         double acc = 0;
         for (int i = 0; i < H; ++i) {
-            const double wgt = useN ? (double)(H - (i > j ? i : j)) : w.Sd[i * H + j];
+            const double wgt = useN ? (double)(H - (i > j ? i : j)) : (double)w.St[i * H + j];
             acc += wgt * w.P0[9 * i + src];
         }
         if (c >= 3 && c < 6) acc *= cs.q[9 + (c - 3)];
@@ -331,13 +345,14 @@ MPCQ_DEV void hess_apply(const Consts& cs, Work<T>& w) {
     }
     wp::sync();
     const double dt2 = cs.dt * cs.dt, dt4 = dt2 * dt2;
-    for (int idx = lane; idx < 12 * H; idx += 32) {
-        const int j = idx / 12, r = idx - 12 * j, a = r / 3, y = r - 3 * a;
+    for (int v = lane; v < w.nv; v += 32) {
+        const int p = v / 3, y = v - 3 * p, j = w.fk[p] >> 2, a = w.fk[p] & 3;
+        const int o = 3 * w.fo[p] + y;
         const double* Y = w.P1 + 12 * j;
         const double* gw = w.GW + 18 * a + y;
         const double t0 = cs.inv_mass * Y[3 + y] + gw[0] * Y[0] + gw[3] * Y[1] + gw[6] * Y[2];
         const double t1 = cs.inv_mass * Y[9 + y] + gw[9] * Y[6] + gw[12] * Y[7] + gw[15] * Y[8];
-        w.gam[idx] = w.g[idx] + 2.0 * (cs.r[r] * w.u[idx] + dt2 * t0 + dt4 * t1);
+        w.gam[o] = w.g[o] + 2.0 * (cs.r[3 * a + y] * w.u[o] + dt2 * t0 + dt4 * t1);
     }
     wp::sync();
 }
@@ -350,7 +365,7 @@ MPCQ_DEV bool build_slots(const Consts& cs, Work<T>& w) {
     const int lane = wp::lane();
     const T mu = (T)cs.mu;
     bool nonzero_c = false;
-    for (int idx = lane; idx < 12 * cs.horizon; idx += 32) w.u[idx] = 0.0;
+    for (int idx = lane; idx < w.nv; idx += 32) w.u[idx] = 0.0;
     wp::sync();
     for (int p = lane; p < w.n / 3 + 1; p += 32) {
         T z[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
@@ -362,7 +377,7 @@ MPCQ_DEV bool build_slots(const Consts& cs, Work<T>& w) {
                 if (sz == 0) { z[6] = sx * mu; z[7] = sy * mu; z[8] = 1; }
                 else {
                     const double fm = w.fmax[p];
-                    double* up = w.u + 3 * w.fk[p];
+                    double* up = w.u + 3 * w.fo[p];
                     up[0] = sx * cs.mu * fm; up[1] = sy * cs.mu * fm; up[2] = fm;
                     nonzero_c = true;
                 }
@@ -635,7 +650,7 @@ MPCQ_DEV double reduced_gradient(Work<T>& w) {
         const int p = v / 3;
         double r = 0;
         if (p < w.ns) {
-            const double* gp = w.gam + 3 * w.fk[p];
+            const double* gp = w.gam + 3 * w.fo[p];
             const T* z = w.zt + 3 * v;
             r = -((double)z[0] * gp[0] + (double)z[1] * gp[1] + (double)z[2] * gp[2]);
         }
@@ -655,7 +670,7 @@ MPCQ_DEV void apply_step(const Consts& cs, Work<T>& w) {
     for (int p = lane; p < w.ns; p += 32) {
         const int sx = w.face[3 * p], sy = w.face[3 * p + 1], sz = w.face[3 * p + 2];
         if (sz < 0) continue;
-        double* up = w.u + 3 * w.fk[p];
+        double* up = w.u + 3 * w.fo[p];
         const double w0 = (double)w.vec[3 * p], w1 = (double)w.vec[3 * p + 1], w2 = (double)w.vec[3 * p + 2];
         if (sz == 0) {
             up[2] += w2;
@@ -676,7 +691,7 @@ MPCQ_DEV double refine(const Consts& cs, Work<T>& w, double tol_abs, bool u_is_z
     double rmax = 0, prev = 0;
     for (int it = 0;; ++it) {
         if (u_is_zero) {
-            for (int idx = lane; idx < 12 * cs.horizon; idx += 32) w.gam[idx] = w.g[idx];
+            for (int idx = lane; idx < w.nv; idx += 32) w.gam[idx] = w.g[idx];
             wp::sync();
             u_is_zero = false;
         } else {
@@ -701,8 +716,8 @@ MPCQ_DEV FaceCheck pdas_update(const Consts& cs, Work<T>& w, bool write) {
     const double mu = cs.mu;
     int npv = 0, ndv = 0;
     for (int p = lane; p < w.ns; p += 32) {
-        const double* f = w.u + 3 * w.fk[p];
-        const double* ga = w.gam + 3 * w.fk[p];
+        const double* f = w.u + 3 * w.fo[p];
+        const double* ga = w.gam + 3 * w.fo[p];
         const double fm = w.fmax[p];
         int sx = w.face[3 * p], sy = w.face[3 * p + 1], sz = w.face[3 * p + 2];
         const double gs = 1.0 + dmax(dabs(ga[0]), dmax(dabs(ga[1]), dabs(ga[2])));
@@ -759,7 +774,7 @@ MPCQ_DEV int reorder_feet(Work<T>& w) {
     const int lane = wp::lane();
     const int ns = w.ns;
     unsigned balc[NFS];
-    int fc[NFS], ff[NFS], fkv[NFS];
+    int fc[NFS], ff[NFS], fkv[NFS], fov[NFS];
     double fm[NFS];
     int n_changed = 0, first_changed = ns;
     MPCQ_UNROLL
@@ -769,6 +784,7 @@ MPCQ_DEV int reorder_feet(Work<T>& w) {
         fc[t] = valid ? ((w.face[3 * p] & 0xff) | ((w.face[3 * p + 1] & 0xff) << 8) | ((w.face[3 * p + 2] & 0xff) << 16)) : 0;
         ff[t] = valid ? ((w.facef[3 * p] & 0xff) | ((w.facef[3 * p + 1] & 0xff) << 8) | ((w.facef[3 * p + 2] & 0xff) << 16)) : 0;
         fkv[t] = valid ? w.fk[p] : 0;
+        fov[t] = valid ? w.fo[p] : 0;
         fm[t] = valid ? w.fmax[p] : 0.0;
         balc[t] = wp::ballot(valid && fc[t] != ff[t]);
         if (balc[t] != 0u && first_changed == ns) {
@@ -790,6 +806,7 @@ MPCQ_DEV int reorder_feet(Work<T>& w) {
             const bool changed = (balc[t] >> lane) & 1u;
             const int q = changed ? n_unchanged + cb : p - cb;
             w.fk[q] = (uint8_t)fkv[t];
+            w.fo[q] = (uint8_t)fov[t];
             w.fmax[q] = fm[t];
             w.face[3 * q] = (int8_t)(fc[t] & 0xff); w.face[3 * q + 1] = (int8_t)((fc[t] >> 8) & 0xff); w.face[3 * q + 2] = (int8_t)((fc[t] >> 16) & 0xff);
             w.facef[3 * q] = (int8_t)(fc[t] & 0xff); w.facef[3 * q + 1] = (int8_t)((fc[t] >> 8) & 0xff); w.facef[3 * q + 2] = (int8_t)((fc[t] >> 16) & 0xff);
@@ -804,6 +821,9 @@ MPCQ_DEV int reorder_feet(Work<T>& w) {
 template <class T, int NSLOT, int NFS>
 MPCQ_DEV bool face_solve(const Consts& cs, Work<T>& w, double tol_abs, double& rmax) {
     const int k_start = reorder_feet<T, NFS>(w);
+#if defined(MPCQ_HOST_EMU) && defined(MPCQ_TRACE)
+    if (wp::lane() == 0) printf("   face_solve: k_start %d of n %d\n", k_start, w.n);
+#endif
     const bool cnz = build_slots(cs, w);
     const bool ok = k_start < w.n ? chol_factor<T, NSLOT>(cs, w, k_start) : true;
     rmax = refine<T, NSLOT>(cs, w, tol_abs, !cnz);
@@ -818,11 +838,11 @@ template <class T>
 MPCQ_DEV void clamp_into(const Consts& cs, Work<T>& w, const double* src, double* dst, int8_t* fdst) {
     const int lane = wp::lane();
     const double mu = cs.mu;
-    for (int idx = lane; idx < 12 * cs.horizon; idx += 32) dst[idx] = 0.0;
+    for (int idx = lane; idx < w.nv; idx += 32) dst[idx] = 0.0;
     wp::sync();
     for (int p = lane; p < w.ns; p += 32) {
-        const double* f = src + 3 * w.fk[p];
-        double* o = dst + 3 * w.fk[p];
+        const double* f = src + 3 * w.fo[p];
+        double* o = dst + 3 * w.fo[p];
         const double fm = w.fmax[p];
         const double tp = cs.tol_p * (1.0 + dmax(dabs(f[0]), dmax(dabs(f[1]), dabs(f[2]))));
         int sx = 0, sy = 0, sz = 0;
@@ -846,7 +866,7 @@ MPCQ_DEV void clamp_into(const Consts& cs, Work<T>& w, const double* src, double
 template <class T>
 MPCQ_DEV double objective(const Consts& cs, Work<T>& w) {
     double s = 0.0;
-    for (int idx = wp::lane(); idx < 12 * cs.horizon; idx += 32) s += w.u[idx] * (w.gam[idx] + w.g[idx]);
+    for (int idx = wp::lane(); idx < w.nv; idx += 32) s += w.u[idx] * (w.gam[idx] + w.g[idx]);
     return 0.5 * wp::reduce_sum(s);
 }
 
@@ -878,8 +898,8 @@ MPCQ_DEV void ratio_test(const Consts& cs, Work<T>& w, double& alpha, int& tag) 
     for (int p = lane; p < w.ns; p += 32) {
         const int sx = w.face[3 * p], sy = w.face[3 * p + 1], sz = w.face[3 * p + 2];
         if (sz < 0) continue;
-        const double* f0 = w.ucur + 3 * w.fk[p];
-        const double* f1 = w.u + 3 * w.fk[p];
+        const double* f0 = w.ucur + 3 * w.fo[p];
+        const double* f1 = w.u + 3 * w.fo[p];
         double s0[6], s1[6];
         row_slacks(f0, mu, w.fmax[p], s0);
         row_slacks(f1, mu, w.fmax[p], s1);
@@ -908,8 +928,8 @@ MPCQ_DEV void block_all_at_zero(const Consts& cs, Work<T>& w) {
     for (int p = lane; p < w.ns; p += 32) {
         int sx = w.face[3 * p], sy = w.face[3 * p + 1], sz = w.face[3 * p + 2];
         if (sz < 0) continue;
-        double* f0 = w.ucur + 3 * w.fk[p];
-        const double* f1 = w.u + 3 * w.fk[p];
+        double* f0 = w.ucur + 3 * w.fo[p];
+        const double* f1 = w.u + 3 * w.fo[p];
         double s0[6], s1[6];
         row_slacks(f0, mu, w.fmax[p], s0);
         row_slacks(f1, mu, w.fmax[p], s1);
@@ -944,14 +964,14 @@ MPCQ_DEV void block_all_at_zero(const Consts& cs, Work<T>& w) {
 template <class T>
 MPCQ_DEV void blocked_step(const Consts& cs, Work<T>& w, double alpha, int tag) {
     const int lane = wp::lane();
-    for (int idx = lane; idx < 12 * cs.horizon; idx += 32) w.ucur[idx] += alpha * (w.u[idx] - w.ucur[idx]);
+    for (int idx = lane; idx < w.nv; idx += 32) w.ucur[idx] += alpha * (w.u[idx] - w.ucur[idx]);
     wp::sync();
     if (lane == 0) {
         const int p = tag >> 3, r = tag & 7;
         int sx = w.face[3 * p], sy = w.face[3 * p + 1], sz = w.face[3 * p + 2];
         const bool apex = (r == 4) || (r == 0 && sx == 1) || (r == 1 && sx == -1) || (r == 2 && sy == 1) || (r == 3 && sy == -1);
         if (r == 0) sx = -1; else if (r == 1) sx = 1; else if (r == 2) sy = -1; else if (r == 3) sy = 1; else if (r == 5) sz = 1;
-        double* f = w.ucur + 3 * w.fk[p];
+        double* f = w.ucur + 3 * w.fo[p];
         if (apex || !(f[2] > 0.0)) { sz = -1; f[0] = f[1] = f[2] = 0.0; }
         else {                                              // put the point exactly on the new face
             if (sz == 1) f[2] = w.fmax[p];
@@ -967,12 +987,13 @@ MPCQ_DEV void blocked_step(const Consts& cs, Work<T>& w, double alpha, int tag) 
 // the whole path for environment b.  NCAP = slot capacity of this size class.
 template <class T, int NCAP>
 MPCQ_DEV void solve_env(const Consts& cs, const IO<T>& io, int b, char* smem, T* l_global, int ns_lo, int ns_hi) {
+    const int nmax = (3 * (ns_hi < NCAP / 3 ? ns_hi : NCAP / 3) + 3) & ~3;     // largest system of this size class
     constexpr int NSLOT = NCAP / 32;
     constexpr int NFS = (NCAP / 3 + 31) / 32;
     const int lane = wp::lane();
     const int H = cs.horizon;
     Work<T> w;
-    carve(w, smem, l_global, H, NCAP);
+    carve(w, smem, l_global, H, NCAP, false, nmax);
     // ---- K3a: stance list from the contact table (ub_fz = gait * fz_max > 0)
     const float* gait = io.gait + (size_t)b * 4 * H;
     int ns = 0;
@@ -982,25 +1003,26 @@ MPCQ_DEV void solve_env(const Consts& cs, const IO<T>& io, int b, char* smem, T*
         const bool st = fm > 0.0;
         const unsigned bal = wp::ballot(st);
         const int pos = ns + wp::popc(bal & ((1u << lane) - 1u));
-        if (st && pos < NCAP / 3) { w.fk[pos] = (uint8_t)k; w.fmax[pos] = fm; w.face[3 * pos] = 0; w.face[3 * pos + 1] = 0; w.face[3 * pos + 2] = 0;
+        if (k < 4 * H) w.cidx[k] = (uint8_t)((st && pos < NCAP / 3) ? pos : 255);
+        if (st && pos < NCAP / 3) { w.fk[pos] = (uint8_t)k; w.fo[pos] = (uint8_t)pos; w.fmax[pos] = fm; w.face[3 * pos] = 0; w.face[3 * pos + 1] = 0; w.face[3 * pos + 2] = 0;
                                       w.facef[3 * pos] = 99; w.facef[3 * pos + 1] = 99; w.facef[3 * pos + 2] = 99; }
         ns += wp::popc(bal);
     }
     if (ns < ns_lo || ns > ns_hi) return;                       // another size class owns this env
     w.ns = ns;
+    w.nv = 3 * ns;
     w.n = (3 * ns + 3) & ~3;
     wp::sync();
     int status = 0, nfac = 0, nas = 0;
     double rmax = 0.0, pviol = 0.0;
     if (ns == 0) {
         status = ST_NO_STANCE | ST_VERIFIED;
-        for (int idx = lane; idx < 12 * H; idx += 32) w.u[idx] = 0.0;
         wp::sync();
     } else {
         const double yaw = io.yaw ? (double)io.yaw[b] : (double)io.x0[(size_t)b * 13 + 2];
         setup_model(cs, w, io.x0 + (size_t)b * 13, yaw, io.r_feet + (size_t)b * 12, io.x_ref + (size_t)b * 13 * H);
         double gsc = 0.0;
-        for (int idx = lane; idx < 12 * H; idx += 32) gsc = dmax(gsc, dabs(w.g[idx]));
+        for (int idx = lane; idx < w.nv; idx += 32) gsc = dmax(gsc, dabs(w.g[idx]));
         gsc = 1.0 + wp::reduce_max(gsc);
         const double tol_loose = cs.tol_r_loose * gsc, tol_tight = cs.tol_r_tight * gsc;
         bool numeric_ok = (gsc == gsc) && (gsc < 1e300);
@@ -1039,7 +1061,7 @@ MPCQ_DEV void solve_env(const Consts& cs, const IO<T>& io, int b, char* smem, T*
                 if (lane == 0) printf("  AS it %d: alpha %.3e tag %d phi_cur %.10e rmax %.2e\n", nas, alpha, tag, phi_cur, rmax);
 #endif
                 if (tag == 0x7fffffff) {                    // (a)
-                    for (int idx = lane; idx < 12 * H; idx += 32) w.ucur[idx] = w.u[idx];
+                    for (int idx = lane; idx < w.nv; idx += 32) w.ucur[idx] = w.u[idx];
                     phi_cur = objective(cs, w);
                     const FaceCheck fc = pdas_update(cs, w, true);
 #if defined(MPCQ_HOST_EMU) && defined(MPCQ_TRACE)
@@ -1054,7 +1076,7 @@ MPCQ_DEV void solve_env(const Consts& cs, const IO<T>& io, int b, char* smem, T*
                 if (lane == 0) printf("     trial phi %.10e -> %s\n", phi_t, phi_t < phi_cur - 1e-12 * dabs(phi_cur) ? "accept" : "ratio step");
 #endif
                 if (phi_t < phi_cur - 1e-12 * dabs(phi_cur)) {   // (b)
-                    for (int idx = lane; idx < 12 * H; idx += 32) w.ucur[idx] = w.utrial[idx];
+                    for (int idx = lane; idx < w.nv; idx += 32) w.ucur[idx] = w.utrial[idx];
                     for (int idx = lane; idx < 3 * w.ns; idx += 32) w.face[idx] = w.face2[idx];
                     wp::sync();
                     phi_cur = phi_t;
@@ -1066,7 +1088,7 @@ MPCQ_DEV void solve_env(const Consts& cs, const IO<T>& io, int b, char* smem, T*
                 }
             }
             if (!done) {                                   // return the feasible iterate
-                for (int idx = lane; idx < 12 * H; idx += 32) w.u[idx] = w.ucur[idx];
+                for (int idx = lane; idx < w.nv; idx += 32) w.u[idx] = w.ucur[idx];
                 wp::sync();
                 hess_apply(cs, w);
             }
@@ -1076,7 +1098,9 @@ MPCQ_DEV void solve_env(const Consts& cs, const IO<T>& io, int b, char* smem, T*
     // ---- outputs: forces, activity (on primal slack, like the oracle's kkt_report), residuals
     const double mu = cs.mu;
     for (int k = lane; k < 4 * H; k += 32) {
-        const double* f = w.u + 3 * k;
+        const int sidx = w.cidx[k];
+        double f[3] = {0.0, 0.0, 0.0};
+        if (sidx != 255) { f[0] = w.u[3 * sidx]; f[1] = w.u[3 * sidx + 1]; f[2] = w.u[3 * sidx + 2]; }
         const double fm = dmax((double)gait[k] * cs.fz_max, 0.0);
         const double sc = 1.0 + dmax(dabs(f[0]), dmax(dabs(f[1]), dabs(f[2])));
         double s[6];
@@ -1088,11 +1112,16 @@ MPCQ_DEV void solve_env(const Consts& cs, const IO<T>& io, int b, char* smem, T*
             pviol = dmax(pviol, -s[r]);
         }
         if (io.active) io.active[(size_t)b * 4 * H + k] = (uint8_t)bits;
+        if (io.u_full) {
+            T* uo = io.u_full + (size_t)b * 12 * H + 3 * k;
+            uo[0] = (T)f[0]; uo[1] = (T)f[1]; uo[2] = (T)f[2];
+        }
+        if (k < 4) {
+            T* fo = io.f_out + (size_t)b * 12 + 3 * k;
+            fo[0] = (T)f[0]; fo[1] = (T)f[1]; fo[2] = (T)f[2];
+        }
     }
     pviol = wp::reduce_max(pviol);
-    if (io.u_full)
-        for (int idx = lane; idx < 12 * H; idx += 32) io.u_full[(size_t)b * 12 * H + idx] = (T)w.u[idx];
-    if (lane < 12) io.f_out[(size_t)b * 12 + lane] = (T)w.u[lane];
     if (lane == 0) {
         if (io.iters) { io.iters[2 * b] = nfac; io.iters[2 * b + 1] = nas; }
         if (io.resid) { io.resid[2 * b] = rmax; io.resid[2 * b + 1] = dmax(pviol, 0.0); }

@@ -12,7 +12,8 @@ namespace mpcq {
 
 // size classes by number of stance foot-steps (slot capacity = 3 * stance, rounded to 32 rows/lane)
 struct SizeClass { int ncap, ns_lo, ns_hi; };
-static const SizeClass kClasses[4] = {{64, 0, 21}, {128, 22, 42}, {192, 43, 64}, {384, 65, 128}};
+static const SizeClass kClasses[4] = {{64, 0, 20}, {128, 21, 42}, {192, 43, 64}, {384, 65, 128}};
+inline int class_nmax(const SizeClass& c) { return (3 * c.ns_hi + 3) & ~3; }   // rows of the largest system in the class
 
 inline int num_classes(int horizon) {
     int n = 1;
