@@ -19,6 +19,7 @@ using mpcq::Consts;
 using mpcq::IO;
 
 constexpr size_t kMaxSmem = 227 * 1024;
+constexpr int kHostStreams = 4;             // chunks / streams of mpcq_solve_host
 constexpr int kGlobalCtas = 148 * 2;       // resident CTAs of a class whose factor lives in global memory
 
 template <class T, int NCAP, bool LGLOBAL>
@@ -87,7 +88,7 @@ struct mpcq_handle {
     char* pin = nullptr;
     char* dev = nullptr;
     size_t stage_cap = 0;
-    cudaStream_t stream = nullptr;
+    cudaStream_t streams[4] = {nullptr, nullptr, nullptr, nullptr};
     // measurement hooks
     bool profiling = false;
     cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -260,11 +261,12 @@ int mpcq_create(const mpcq_config* cfg, mpcq_handle** out) {
     cudaError_t e = cfg->dtype == MPCQ_F64 ? configure<double>(h) : configure<float>(h);
     if (e == cudaErrorInvalidValue && !h->smem[0]) { g_create_err = "horizon needs more shared memory than one SM has"; delete h; return MPCQ_ERR_UNSUPPORTED; }
     if (!cuda_ok(nullptr, e, "configure kernels")) { if (h->gws) cudaFree(h->gws); delete h; return MPCQ_ERR_CUDA; }
-    if (!cuda_ok(nullptr, cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking), "cudaStreamCreate")) {
-        if (h->gws) cudaFree(h->gws);
-        delete h;
-        return MPCQ_ERR_CUDA;
-    }
+    for (int i = 0; i < kHostStreams; ++i)
+        if (!cuda_ok(nullptr, cudaStreamCreateWithFlags(&h->streams[i], cudaStreamNonBlocking), "cudaStreamCreate")) {
+            if (h->gws) cudaFree(h->gws);
+            delete h;
+            return MPCQ_ERR_CUDA;
+        }
     *out = h;
     return MPCQ_OK;
 }
@@ -272,7 +274,8 @@ int mpcq_create(const mpcq_config* cfg, mpcq_handle** out) {
 void mpcq_destroy(mpcq_handle* h) {
     if (!h) return;
     DeviceGuard guard(h->cfg.device);
-    if (h->stream) { cudaStreamSynchronize(h->stream); cudaStreamDestroy(h->stream); }
+    for (int i = 0; i < kHostStreams; ++i)
+        if (h->streams[i]) { cudaStreamSynchronize(h->streams[i]); cudaStreamDestroy(h->streams[i]); }
     for (int i = 0; i < 8; ++i)
         if (h->ev[i]) cudaEventDestroy(h->ev[i]);
     if (h->gws) cudaFree(h->gws);
@@ -327,14 +330,18 @@ int mpcq_solve_host(mpcq_handle* h, int32_t B, const void* x0, const void* yaw, 
     if (B == 0) return MPCQ_OK;
     DeviceGuard guard(h->cfg.device);
     const size_t rs = h->real_size, H = (size_t)h->cs.horizon, b = (size_t)B;
-    // staging layout: inputs first (one H2D copy), outputs after (one D2H copy)
+    // per-environment byte widths of the 5 inputs and 6 outputs
+    const size_t width[11] = {13 * rs, yaw ? rs : 0, 12 * rs, 4 * H * 4, 13 * H * rs,
+                              12 * rs, u_full ? 12 * H * rs : 0, iters ? (size_t)8 : 0, resid ? (size_t)16 : 0,
+                              status ? (size_t)4 : 0, active ? 4 * H : 0};
+    const void* src[5] = {x0, yaw, r_feet, gait, x_ref};
+    void* dst[6] = {f_out, u_full, iters, resid, status, active};
     size_t off[12], cur = 0;
-    const size_t sizes[12] = {b * 13 * rs, yaw ? b * rs : 0, b * 12 * rs, b * 4 * H * 4, b * 13 * H * rs,
-                              b * 12 * rs, u_full ? b * 12 * H * rs : 0, iters ? b * 8 : 0, resid ? b * 16 : 0,
-                              status ? b * 4 : 0, active ? b * 4 * H : 0, 0};
-    for (int i = 0; i < 12; ++i) { off[i] = cur; cur += (sizes[i] + 255) / 256 * 256; }
-    const size_t in_bytes = off[5], total = cur;
+    for (int i = 0; i < 11; ++i) { off[i] = cur; cur += (b * width[i] + 255) / 256 * 256; }
+    off[11] = cur;
+    const size_t total = cur;
     if (total > h->stage_cap) {
+        for (int i = 0; i < kHostStreams; ++i) cudaStreamSynchronize(h->streams[i]);
         if (h->dev) cudaFree(h->dev);
         if (h->pin) cudaFreeHost(h->pin);
         h->dev = h->pin = nullptr;
@@ -343,23 +350,55 @@ int mpcq_solve_host(mpcq_handle* h, int32_t B, const void* x0, const void* yaw, 
         if (!cuda_ok(h, cudaMallocHost(&h->pin, total), "cudaMallocHost staging")) return MPCQ_ERR_CUDA;
         h->stage_cap = total;
     }
-    const void* src[5] = {x0, yaw, r_feet, gait, x_ref};
-    for (int i = 0; i < 5; ++i)
-        if (sizes[i]) memcpy(h->pin + off[i], src[i], sizes[i]);
-    cudaStream_t st = h->stream;
-    if (!cuda_ok(h, cudaMemcpyAsync(h->dev, h->pin, in_bytes, cudaMemcpyHostToDevice, st), "H2D")) return MPCQ_ERR_CUDA;
+    // caller buffers that are already page-locked are used for DMA directly; pageable ones go through the pinned staging
+    bool pinned[11];
+    for (int i = 0; i < 11; ++i) {
+        const void* p = i < 5 ? src[i] : dst[i - 5];
+        pinned[i] = false;
+        if (p && width[i]) {
+            cudaPointerAttributes at;
+            if (cudaPointerGetAttributes(&at, p) == cudaSuccess) pinned[i] = at.type == cudaMemoryTypeHost;
+            else cudaGetLastError();
+        }
+    }
+    // the batch is cut into chunks, each on its own stream: H2D(c+1) overlaps solve(c) overlaps D2H(c-1), and the
+    // kernels of neighbouring chunks fill each other's tails.  A class whose factor lives in the shared global
+    // workspace cannot run twice concurrently, so such handles use one chunk.
+    bool any_global = false;
+    for (int ci = 0; ci < h->ncls; ++ci) any_global = any_global || h->lglobal[ci];
+    const int nchunk = any_global ? 1 : (B >= 2048 ? kHostStreams : (B >= 512 ? 2 : 1));
     char* d = h->dev;
-    int rc = mpcq_solve(h, B, d + off[0], yaw ? d + off[1] : nullptr, d + off[2], reinterpret_cast<float*>(d + off[3]), d + off[4],
-                        d + off[5], u_full ? d + off[6] : nullptr, iters ? reinterpret_cast<int32_t*>(d + off[7]) : nullptr,
-                        resid ? reinterpret_cast<double*>(d + off[8]) : nullptr,
-                        status ? reinterpret_cast<int32_t*>(d + off[9]) : nullptr,
-                        active ? reinterpret_cast<uint8_t*>(d + off[10]) : nullptr, st);
-    if (rc != MPCQ_OK) return rc;
-    if (!cuda_ok(h, cudaMemcpyAsync(h->pin + in_bytes, d + in_bytes, total - in_bytes, cudaMemcpyDeviceToHost, st), "D2H")) return MPCQ_ERR_CUDA;
-    if (!cuda_ok(h, cudaStreamSynchronize(st), "mpcq_solve_host sync")) return MPCQ_ERR_CUDA;
-    void* dst[6] = {f_out, u_full, iters, resid, status, active};
-    for (int i = 0; i < 6; ++i)
-        if (sizes[5 + i]) memcpy(dst[i], h->pin + off[5 + i], sizes[5 + i]);
+    int launches = 0;
+    for (int c = 0; c < nchunk; ++c) {
+        const size_t lo = b * c / nchunk, hi = b * (c + 1) / nchunk, nb = hi - lo;
+        if (nb == 0) continue;
+        cudaStream_t st = h->streams[c % kHostStreams];
+        for (int i = 0; i < 5; ++i) {
+            if (!width[i]) continue;
+            const char* from = static_cast<const char*>(src[i]) + lo * width[i];
+            if (!pinned[i]) {
+                memcpy(h->pin + off[i] + lo * width[i], from, nb * width[i]);
+                from = h->pin + off[i] + lo * width[i];
+            }
+            if (!cuda_ok(h, cudaMemcpyAsync(d + off[i] + lo * width[i], from, nb * width[i], cudaMemcpyHostToDevice, st), "H2D")) return MPCQ_ERR_CUDA;
+        }
+        auto dp = [&](int i) -> char* { return width[i] ? d + off[i] + lo * width[i] : nullptr; };
+        const int rc = mpcq_solve(h, (int32_t)nb, dp(0), dp(1), dp(2), reinterpret_cast<float*>(dp(3)), dp(4), dp(5), dp(6),
+                                  reinterpret_cast<int32_t*>(dp(7)), reinterpret_cast<double*>(dp(8)),
+                                  reinterpret_cast<int32_t*>(dp(9)), reinterpret_cast<uint8_t*>(dp(10)), st);
+        if (rc != MPCQ_OK) return rc;
+        launches += h->last_launches;
+        for (int i = 5; i < 11; ++i) {
+            if (!width[i]) continue;
+            char* to = pinned[i] ? static_cast<char*>(dst[i - 5]) + lo * width[i] : h->pin + off[i] + lo * width[i];
+            if (!cuda_ok(h, cudaMemcpyAsync(to, d + off[i] + lo * width[i], nb * width[i], cudaMemcpyDeviceToHost, st), "D2H")) return MPCQ_ERR_CUDA;
+        }
+    }
+    for (int c = 0; c < nchunk && c < kHostStreams; ++c)
+        if (!cuda_ok(h, cudaStreamSynchronize(h->streams[c]), "mpcq_solve_host sync")) return MPCQ_ERR_CUDA;
+    for (int i = 5; i < 11; ++i)
+        if (width[i] && !pinned[i]) memcpy(dst[i - 5], h->pin + off[i], b * width[i]);
+    h->last_launches = launches;
     return MPCQ_OK;
 }
 

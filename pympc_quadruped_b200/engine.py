@@ -103,8 +103,10 @@ class MpcqEngine:
         self._err(rc, "mpcq_solve")
         return out
 
-    def solve_host(self, x0, r_feet, gait, x_ref, yaw=None, want=("status",)):
-        """numpy in / numpy out through `mpcq_solve_host` (H2D + solve + D2H inside the call)."""
+    def solve_host(self, x0, r_feet, gait, x_ref, yaw=None, want=("status",), out=None):
+        """numpy in / numpy out through `mpcq_solve_host` (H2D + solve + D2H inside the call).
+        Page-locked arrays (e.g. `torch.empty(..., pin_memory=True).numpy()`) are used for DMA directly;
+        `out` may hold preallocated result arrays (keys forces/u/iters/resid/status/active)."""
         rt = np.float64 if self.dtype == torch.float64 else np.float32
         B, H = x0.shape[0], self.horizon
         x0 = np.ascontiguousarray(x0, dtype=rt).reshape(B, 13)
@@ -112,17 +114,19 @@ class MpcqEngine:
         gait = np.ascontiguousarray(gait, dtype=np.float32).reshape(B, 4 * H)
         x_ref = np.ascontiguousarray(x_ref, dtype=rt).reshape(B, 13 * H)
         yaw = None if yaw is None else np.ascontiguousarray(yaw, dtype=rt).reshape(B)
-        res = dict(forces=np.empty((B, 12), rt))
-        if "u" in want:
-            res["u"] = np.empty((B, 12 * H), rt)
-        if "iters" in want:
-            res["iters"] = np.empty((B, 2), np.int32)
-        if "resid" in want:
-            res["resid"] = np.empty((B, 2), np.float64)
-        if "status" in want:
-            res["status"] = np.empty(B, np.int32)
-        if "active" in want:
-            res["active"] = np.empty((B, 4 * H), np.uint8)
+        spec = dict(forces=((B, 12), rt), u=((B, 12 * H), rt), iters=((B, 2), np.int32), resid=((B, 2), np.float64),
+                    status=((B,), np.int32), active=((B, 4 * H), np.uint8))
+        res = {}
+        for key, (shape, dt) in spec.items():
+            if key != "forces" and key not in want:
+                continue
+            if out is not None and key in out:
+                a = out[key]
+                if a.shape != shape or a.dtype != dt or not a.flags["C_CONTIGUOUS"]:
+                    raise ValueError(f"out[{key!r}] must be a C-contiguous {dt} array of shape {shape}")
+                res[key] = a
+            else:
+                res[key] = np.empty(shape, dt)
         p = lambda a: None if a is None else a.ctypes.data_as(C.c_void_p)
         rc = self.lib.mpcq_solve_host(self._h, B, p(x0), p(yaw), p(r_feet), p(gait), p(x_ref), p(res["forces"]),
                                       p(res.get("u")), p(res.get("iters")), p(res.get("resid")), p(res.get("status")),

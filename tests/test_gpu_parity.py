@@ -169,6 +169,29 @@ def test_host_entry_point_equals_device_entry_point():
     assert np.array_equal(host["iters"], res.iters.cpu().numpy())
 
 
+def test_host_entry_point_chunked_pinned_and_pageable():
+    """B large enough for the 4-chunk / 4-stream pipeline of mpcq_solve_host; pinned buffers are used for DMA
+    directly, pageable ones are staged - all three routes must agree bit for bit."""
+    B = 2500
+    batch = make_batch(A1Config, 10, B, "mixed", (Gait.TROTTING10, Gait.STANDING), 32, solve=False)
+    eng = _engine(batch, A1Config, torch.float32)
+    x0, feet, gait, xref, yaw = _to_dev(batch, torch.float32)
+    res = eng.solve(x0, feet, gait, xref, yaw=yaw)
+    host = eng.solve_host(batch["x0"], batch["feet"], batch["gait"], batch["xref"], yaw=batch["yaw"], want=("u", "status", "iters"))
+    pin = lambda a, dt: torch.empty(a.shape, dtype=dt, pin_memory=True).copy_(torch.as_tensor(a).to(dt)).numpy()
+    out = {"forces": torch.empty((B, 12), dtype=torch.float32, pin_memory=True).numpy(),
+           "u": torch.empty((B, 120), dtype=torch.float32, pin_memory=True).numpy()}
+    pinned = eng.solve_host(pin(batch["x0"], torch.float32), pin(batch["feet"], torch.float32), pin(batch["gait"], torch.float32),
+                            pin(batch["xref"], torch.float32), yaw=pin(batch["yaw"], torch.float32), want=("u", "status"), out=out)
+    assert pinned["forces"] is out["forces"]
+    for r in (host, pinned):
+        assert np.array_equal(r["forces"], res.forces.cpu().numpy())
+        assert np.array_equal(r["u"], res.u.cpu().numpy())
+        assert np.array_equal(r["status"], res.status.cpu().numpy())
+    assert np.array_equal(host["iters"], res.iters.cpu().numpy())
+    assert eng.last_launch_count == 2 * 4                       # 2 size classes x 4 chunks
+
+
 def test_edge_cases_empty_batch_all_swing_and_errors():
     from pympc_quadruped_b200 import with_horizon
     from pympc_quadruped_b200.engine import MpcqEngine
