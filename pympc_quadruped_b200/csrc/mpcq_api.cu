@@ -22,15 +22,18 @@ constexpr size_t kMaxSmem = 227 * 1024;
 constexpr int kHostStreams = 4;             // chunks / streams of mpcq_solve_host
 constexpr int kGlobalCtas = 148 * 2;       // resident CTAs of a class whose factor lives in global memory
 
+// warps of the team that owns one environment, per slot capacity (must match mpcq::kClasses)
+template <int NCAP> struct TeamWarps { static constexpr int value = NCAP <= 64 ? MPCQ_NW0 : (NCAP <= 128 ? MPCQ_NW1 : (NCAP <= 192 ? MPCQ_NW2 : MPCQ_NW3)); };
+
 template <class T, int NCAP, bool LGLOBAL>
-__global__ void __launch_bounds__(32)
+__global__ void __launch_bounds__(32 * TeamWarps<NCAP>::value, (NCAP <= 64 && MPCQ_NW0 > 1) ? 12 : 1)   // small class with 2-warp teams: 12 teams (24 warps) per SM
 mpcq_solve_kernel(const __grid_constant__ Consts cs, const __grid_constant__ IO<T> io, T* gws, size_t gws_stride,
                   int ns_lo, int ns_hi) {
     extern __shared__ __align__(32) char smem[];
     T* lg = LGLOBAL ? gws + (size_t)blockIdx.x * gws_stride : nullptr;
     for (int b = blockIdx.x; b < io.B; b += gridDim.x) {
-        mpcq::solve_env<T, NCAP>(cs, io, b, smem, lg, ns_lo, ns_hi);
-        __syncwarp();
+        mpcq::solve_env<T, NCAP, TeamWarps<NCAP>::value>(cs, io, b, smem, lg, ns_lo, ns_hi);
+        __syncthreads();
     }
 }
 
@@ -48,6 +51,7 @@ mpcq_build_qp_kernel(const __grid_constant__ Consts cs, const __grid_constant__ 
     w.ns = 4 * H;
     w.nv = 12 * H;
     w.n = 12 * H;
+    w.t.tid = lane; w.t.nt = 32; w.t.wid = 0;
     __syncwarp();
     const double yaw = io.yaw ? (double)io.yaw[b] : (double)io.x0[(size_t)b * 13 + 2];
     mpcq::setup_model(cs, w, io.x0 + (size_t)b * 13, yaw, io.r_feet + (size_t)b * 12, io.x_ref + (size_t)b * 13 * H);
@@ -124,7 +128,7 @@ cudaError_t launch_class(mpcq_handle* h, const IO<T>& io, int ci, cudaStream_t s
     auto kern = mpcq_solve_kernel<T, NCAP, LG>;
     const mpcq::SizeClass& sc = mpcq::kClasses[ci];
     const int grid = LG ? (io.B < kGlobalCtas ? io.B : kGlobalCtas) : io.B;
-    kern<<<grid, 32, h->smem[ci], st>>>(h->cs, io, static_cast<T*>(h->gws), h->gws_stride, sc.ns_lo, sc.ns_hi);
+    kern<<<grid, 32 * TeamWarps<NCAP>::value, h->smem[ci], st>>>(h->cs, io, static_cast<T*>(h->gws), h->gws_stride, sc.ns_lo, sc.ns_hi);
     return cudaGetLastError();
 }
 

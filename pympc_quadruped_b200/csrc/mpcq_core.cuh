@@ -81,12 +81,13 @@ template <class T> struct Work {
     int8_t* face2;         // trial faces of the fallback
     int8_t* facef;         // faces the current factor was built for
     int n, ns, H, nv;      // nv = 3 * ns: live length of the compact vectors
+    team::Ctx t;             // the team of warps that owns this environment
 };
 
 template <class T>
 MPCQ_HD constexpr size_t work_bytes(int H, int ncap, bool l_in_smem, bool with_md = false, int nmax = 0) {
-    size_t nd = (with_md ? 288 : 0) + 72 + 2 * 12 * (size_t)H + 5 * (size_t)ncap + ncap / 3 + 1;
-    size_t nt = (l_in_smem ? l_elems(nmax > 0 ? nmax : ncap) : 0) + 3 * (ncap / 4) * 4 + ncap + 128 + 3 * ncap + 288 + (size_t)H * H;
+    size_t nd = (with_md ? 288 : 0) + 72 + 2 * 12 * (size_t)H + 5 * (size_t)ncap + ncap / 3 + 1 + 12;
+    size_t nt = (l_in_smem ? l_elems(nmax > 0 ? nmax : ncap) : 0) + 3 * (ncap / 4) * 4 + ncap + 256 + 3 * ncap + 288 + (size_t)H * H;
     size_t nb = (ncap / 3 + 1) * 11 + 4 * (size_t)H + 16 + 4 * (size_t)ncap;
     return align_up(nd * 8, 16) + align_up(nt * sizeof(T), 16) + align_up(nb, 16);
 }
@@ -104,7 +105,9 @@ MPCQ_DEV void carve(Work<T>& w, char* base, T* l_global, int H, int ncap, bool w
     w.ucur = d; d += ncap;
     w.utrial = d; d += ncap;
     w.fmax = d; d += ncap / 3 + 1;
-    size_t nd = (with_md ? 288 : 0) + 72 + 2 * 12 * (size_t)H + 5 * (size_t)ncap + ncap / 3 + 1;
+    w.t.red = d; d += 8;
+    w.t.redi = reinterpret_cast<int*>(d); d += 4;
+    size_t nd = (with_md ? 288 : 0) + 72 + 2 * 12 * (size_t)H + 5 * (size_t)ncap + ncap / 3 + 1 + 12;
     T* t = reinterpret_cast<T*>(base + align_up(nd * 8, 16));
     size_t used = 0;
     if (l_global) {
@@ -115,7 +118,7 @@ MPCQ_DEV void carve(Work<T>& w, char* base, T* l_global, int H, int ncap, bool w
     }
     w.dblk = t; t += 3 * (ncap / 4) * 4; used += 3 * (ncap / 4) * 4;
     w.vec = t; t += ncap; used += ncap;
-    w.cw = t; t += 128; used += 128;
+    w.cw = t; t += 256; used += 256;
     w.zt = t; t += 3 * ncap; used += 3 * ncap;
     w.Mf = t; t += 288; used += 288;
     w.St = t; t += H * H; used += (size_t)H * H;
@@ -172,7 +175,7 @@ MPCQ_DEV double dabs(double a) { return a < 0 ? -a : a; }
 // K1 + K2 (per-env part): model matrices M00, M11, horizon table S and the linear term g.
 template <class T>
 MPCQ_DEV void setup_model(const Consts& cs, Work<T>& w, const T* x0p, double yaw, const T* feetp, const T* xrefp) {
-    const int lane = wp::lane();
+    const int lane = w.t.tid;
     const int H = cs.horizon;
     // --- Rz (float32-rounded like the reference), world inertia, its inverse: every lane, redundantly
     const double c = (double)(float)cos(yaw), s = (double)(float)sin(yaw);
@@ -233,17 +236,17 @@ MPCQ_DEV void setup_model(const Consts& cs, Work<T>& w, const T* x0p, double yaw
             }
     }
     // --- horizon table S
-    for (int idx = lane; idx < H * H; idx += 32) {
+    for (int idx = lane; idx < H * H; idx += w.t.nt) {
         const int i = idx / H, j = idx - i * H;
         const int m = i > j ? i : j;
         const double a = m - i + 0.5, b = m - j + 0.5, Ln = H - m;
         const double sv = Ln * a * b + (a + b) * Ln * (Ln - 1) * 0.5 + (Ln - 1) * Ln * (2 * Ln - 1) / 6.0;
         w.St[idx] = (T)sv;                                  // multiples of 1/4 below 2^17: exact in float
     }
-    wp::sync();
+    team::sync(w.t);
     // --- M00 = B0'QB0, M11 = B1'QB1
     const double dt = cs.dt, dt2 = dt * dt, dt4 = dt2 * dt2, im2 = cs.inv_mass * cs.inv_mass;
-    for (int idx = lane; idx < 144; idx += 32) {
+    for (int idx = lane; idx < 144; idx += w.t.nt) {
         const int r = idx / 12, cc2 = idx - r * 12;
         const int a = r / 3, x = r - 3 * a, b = cc2 / 3, y = cc2 - 3 * b;
         double m0 = 0, m1 = 0;
@@ -281,8 +284,8 @@ MPCQ_DEV void setup_model(const Consts& cs, Work<T>& w, const T* x0p, double yaw
             w.P1[12 * j + cidx] = E1;
         }
     }
-    wp::sync();
-    for (int v = lane; v < w.nv; v += 32) {
+    team::sync(w.t);
+    for (int v = lane; v < w.nv; v += w.t.nt) {
         const int p = v / 3, y = v - 3 * p, j = w.fk[p] >> 2, a = w.fk[p] & 3;
         const double* E0 = w.P0 + 12 * j;
         const double* E1 = w.P1 + 12 * j;
@@ -294,7 +297,7 @@ MPCQ_DEV void setup_model(const Consts& cs, Work<T>& w, const T* x0p, double yaw
         }
         w.g[3 * w.fo[p] + y] = 2.0 * (dt * t0 + dt2 * t1);
     }
-    wp::sync();
+    team::sync(w.t);
 }
 
 // gam = H u + g in fp64 through the factored structure H = 2 (N (x) B0'QB0 + S (x) B1'QB1 + R):
@@ -302,9 +305,9 @@ MPCQ_DEV void setup_model(const Consts& cs, Work<T>& w, const T* x0p, double yaw
 //   3. project back with G', W'.   u, gam in full [H][12] layout; P0 / P1 are scratch.
 template <class T>
 MPCQ_DEV void hess_apply(const Consts& cs, Work<T>& w) {
-    const int lane = wp::lane();
+    const int lane = w.t.tid;
     const int H = cs.horizon;
-    for (int idx = lane; idx < 9 * H; idx += 32) {
+    for (int idx = lane; idx < 9 * H; idx += w.t.nt) {
         const int i = idx / 9, k = idx - 9 * i;
         double y = 0;
         if (k < 6) {
@@ -329,8 +332,8 @@ MPCQ_DEV void hess_apply(const Consts& cs, Work<T>& w) {
         }
         w.P0[idx] = y;
     }
-    wp::sync();
-    for (int idx = lane; idx < 12 * H; idx += 32) {
+    team::sync(w.t);
+    for (int idx = lane; idx < 12 * H; idx += w.t.nt) {
         const int j = idx / 12, c = idx - 12 * j;
         const bool useN = c < 6;
         const int src = c < 3 ? c : c < 6 ? 3 + c : c < 9 ? c - 3 : c - 3;     // y0r | fs | y1r | fs
@@ -343,9 +346,9 @@ MPCQ_DEV void hess_apply(const Consts& cs, Work<T>& w) {
         if (c >= 9) acc *= cs.q[3 + (c - 9)];
         w.P1[idx] = acc;
     }
-    wp::sync();
+    team::sync(w.t);
     const double dt2 = cs.dt * cs.dt, dt4 = dt2 * dt2;
-    for (int v = lane; v < w.nv; v += 32) {
+    for (int v = lane; v < w.nv; v += w.t.nt) {
         const int p = v / 3, y = v - 3 * p, j = w.fk[p] >> 2, a = w.fk[p] & 3;
         const int o = 3 * w.fo[p] + y;
         const double* Y = w.P1 + 12 * j;
@@ -354,7 +357,7 @@ MPCQ_DEV void hess_apply(const Consts& cs, Work<T>& w) {
         const double t1 = cs.inv_mass * Y[9 + y] + gw[9] * Y[6] + gw[12] * Y[7] + gw[15] * Y[8];
         w.gam[o] = w.g[o] + 2.0 * (cs.r[3 * a + y] * w.u[o] + dt2 * t0 + dt4 * t1);
     }
-    wp::sync();
+    team::sync(w.t);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -362,12 +365,12 @@ MPCQ_DEV void hess_apply(const Consts& cs, Work<T>& w) {
 // slot v = 3p + comp of stance foot-step p; dead slots (z = 0) become identity rows.
 template <class T>
 MPCQ_DEV bool build_slots(const Consts& cs, Work<T>& w) {
-    const int lane = wp::lane();
+    const int lane = w.t.tid;
     const T mu = (T)cs.mu;
     bool nonzero_c = false;
-    for (int idx = lane; idx < w.nv; idx += 32) w.u[idx] = 0.0;
-    wp::sync();
-    for (int p = lane; p < w.n / 3 + 1; p += 32) {
+    for (int idx = lane; idx < w.nv; idx += w.t.nt) w.u[idx] = 0.0;
+    team::sync(w.t);
+    for (int p = lane; p < w.n / 3 + 1; p += w.t.nt) {
         T z[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
         if (p < w.ns) {
             const int sx = w.face[3 * p], sy = w.face[3 * p + 1], sz = w.face[3 * p + 2];
@@ -394,72 +397,80 @@ MPCQ_DEV bool build_slots(const Consts& cs, Work<T>& w) {
                 w.sinf[3 * p + c] = (k >> 2) | ((k & 3) << 8) | (p << 16) | (dead ? (1 << 30) : 0);
             }
     }
-    wp::sync();
-    return wp::any(nonzero_c);
+    team::sync(w.t);
+    return team::any(w.t, nonzero_c);
 }
 
 // ---------------------------------------------------------------------------------------------
 // K2 + K4a: assemble K = Z'HZ column panel by column panel (never materialised) and factor it.
-// Left-looking, 4-column panels; lane owns rows lane, lane+32, ... ; returns false on a bad pivot.
-// The inner sweeps are unpredicated: rows above the panel / beyond n compute garbage that is never stored.
-template <class T, int NSLOT>
+// Left-looking, 4-column panels, executed by the whole team (NW warps).  Rows are dealt to threads in blocks of
+// 4, round-robin over the warps:   row = 4 * (NW * (8 * slot + lane / 4) + warp) + lane % 4,
+// so that every warp keeps a share of the rows that are still active as the panel index grows (for NW = 1 this
+// is row = lane + 32 * slot).  Returns false on a bad pivot.  The inner sweeps are unpredicated: rows above the
+// panel / beyond n compute garbage that is never stored.
+template <class T, int NCAP, int NW>
 MPCQ_DEV bool chol_factor(const Consts& cs, Work<T>& w, int k_start) {
-    const int lane = wp::lane();
+    constexpr int NSLOT = NCAP / (32 * NW);
+    constexpr int RSTEP = 32 * NW;                 // rows between two slots of a thread
+    const int lane = wp::lane(), wid = w.t.wid;
     const int n = w.n, H = cs.horizon;
     T* L = w.L;
     bool ok = true;
-    // row data of this lane, fixed for the whole factorisation
+    const int row0 = 4 * (NW * (lane >> 2) + wid) + (lane & 3);
+    // row data of this thread, fixed for the whole factorisation
     T zr[NSLOT][3];
     int ri[NSLOT];
     MPCQ_UNROLL
     for (int m = 0; m < NSLOT; ++m) {
-        const int v = lane + 32 * m;
+        const int v = row0 + RSTEP * m;
         const bool in = v < n;
         ri[m] = in ? w.sinf[v] : (1 << 30);
         zr[m][0] = in ? w.zt[3 * v] : (T)0;
         zr[m][1] = in ? w.zt[3 * v + 1] : (T)0;
         zr[m][2] = in ? w.zt[3 * v + 2] : (T)0;
     }
-    const T* colg = L;            // base of the current group of 4 previous columns (used incrementally below)
+    // cw[c][mat][leg][x] = sum_y M_mat[3 leg + x][3 b_c + y] z_c[y] for the 4 panel columns: one (c,mat,leg) per lane of
+    // warp 0, double-buffered so the next panel's table can be written while other warps still read this one
+    auto write_cw = [&](int k0, T* dstbuf) {
+        const int c = lane >> 3, mat = (lane >> 2) & 1, leg = lane & 3;
+        const int info = w.sinf[k0 + c];
+        const int b = (info >> 8) & 3;
+        const T* z = w.zt + 3 * (k0 + c);
+        const T z0 = z[0], z1 = z[1], z2 = z[2];
+        const T* mrow = w.Mf + mat * 144 + (3 * leg) * 12 + 3 * b;
+        T* dst = dstbuf + 4 * lane;
+        dst[0] = mrow[0] * z0 + mrow[1] * z1 + mrow[2] * z2;
+        dst[1] = mrow[12] * z0 + mrow[13] * z1 + mrow[14] * z2;
+        dst[2] = mrow[24] * z0 + mrow[25] * z1 + mrow[26] * z2;
+        dst[3] = 0;
+    };
+    if (wid == 0) write_cw(0, w.cw);
+    team::sync(w.t);
     // Rows < k_start keep their factor (leading block unchanged since the previous factorisation, see
     // reorder_feet): for panels k0 < k_start only the rows >= k_start are recomputed (L21 = K21 L11^-T, using the
     // stored diagonal blocks); from k_start on it is the plain left-looking factorisation.
     for (int k0 = 0; k0 < n; k0 += 4) {
         const bool keep_diag = k0 < k_start;
         const int row_lo = keep_diag ? k_start : k0;
-        // ---- panel columns: info + cw[c][mat][leg][x] = sum_y M_mat[3 leg + x][3 b_c + y] z_c[y]; one (c,mat,leg) per lane
+        const T* cw = w.cw + 128 * ((k0 >> 2) & 1);
         int ci[4];
         MPCQ_UNROLL
         for (int c = 0; c < 4; ++c) ci[c] = w.sinf[k0 + c];
-        {
-            const int c = lane >> 3, mat = (lane >> 2) & 1, leg = lane & 3;
-            const int info = w.sinf[k0 + c];
-            const int b = (info >> 8) & 3;
-            const T* z = w.zt + 3 * (k0 + c);
-            const T z0 = z[0], z1 = z[1], z2 = z[2];
-            const T* mrow = w.Mf + mat * 144 + (3 * leg) * 12 + 3 * b;
-            T* dst = w.cw + 4 * lane;
-            dst[0] = mrow[0] * z0 + mrow[1] * z1 + mrow[2] * z2;
-            dst[1] = mrow[12] * z0 + mrow[13] * z1 + mrow[14] * z2;
-            dst[2] = mrow[24] * z0 + mrow[25] * z1 + mrow[26] * z2;
-            dst[3] = 0;
-        }
-        wp::sync();
         // ---- initial entries of the panel
         T acc[NSLOT][4];
-        const int m0 = row_lo >> 5;
+        const int m0 = row_lo / RSTEP;
         MPCQ_UNROLL
         for (int m = 0; m < NSLOT; ++m) {
             if (m < m0) continue;
             const int iv = ri[m] & 0xff, av = (ri[m] >> 8) & 3;
             const bool dead = (ri[m] >> 30) != 0;
-            const int v = lane + 32 * m;
+            const int v = row0 + RSTEP * m;
             MPCQ_UNROLL
             for (int c = 0; c < 4; ++c) {
                 const int jw = ci[c] & 0xff;
                 T q0, q1, q2, q3, s0, s1, s2, s3;
-                load4(w.cw + 4 * (8 * c + av), q0, q1, q2, q3);
-                load4(w.cw + 4 * (8 * c + 4 + av), s0, s1, s2, s3);
+                load4(cw + 4 * (8 * c + av), q0, q1, q2, q3);
+                load4(cw + 4 * (8 * c + 4 + av), s0, s1, s2, s3);
                 const T t0 = zr[m][0] * q0 + zr[m][1] * q1 + zr[m][2] * q2;
                 const T t1 = zr[m][0] * s0 + zr[m][1] * s1 + zr[m][2] * s2;
                 const int mx = iv > jw ? iv : jw;
@@ -474,6 +485,7 @@ MPCQ_DEV bool chol_factor(const Consts& cs, Work<T>& w, int k_start) {
             }
         }
         // ---- left-looking update with all previous columns
+        const T* colg;
         {
             const T* col = L;
             int stride = n;
@@ -485,7 +497,7 @@ MPCQ_DEV bool chol_factor(const Consts& cs, Work<T>& w, int k_start) {
                     MPCQ_UNROLL
                     for (int m = 0; m < NSLOT; ++m) {
                         if (m < m0) continue;
-                        const T lr = col[lane + 32 * m];
+                        const T lr = col[row0 + RSTEP * m];
                         acc[m][0] -= lr * p0; acc[m][1] -= lr * p1; acc[m][2] -= lr * p2; acc[m][3] -= lr * p3;
                     }
                     col += stride;
@@ -495,45 +507,49 @@ MPCQ_DEV bool chol_factor(const Consts& cs, Work<T>& w, int k_start) {
             }
             colg = col;                                       // == L + colbase(k0, n)
         }
-        // ---- 4x4 diagonal block: kept, or fetched from its owner lanes and factored redundantly by every lane
-        T l10, l20, l21, l30, l31, l32, i0, i1, i2, i3;
-        if (keep_diag) {
-            T pad0, pad1;
+        // ---- 4x4 diagonal block: kept, or factored by the warp that owns its rows and published through dblk
+        if (!keep_diag) {
+            const int kb = k0 >> 2, q = kb / NW;
+            if (wid == kb - q * NW) {
+                const int ld = 4 * (q & 7), md = q >> 3;
+                T a0 = acc[0][0], a1 = acc[0][1], a2 = acc[0][2], a3 = acc[0][3];
+                MPCQ_UNROLL
+                for (int m = 1; m < NSLOT; ++m)
+                    if (m == md) { a0 = acc[m][0]; a1 = acc[m][1]; a2 = acc[m][2]; a3 = acc[m][3]; }
+                const T d00 = wp::shfl(a0, ld);
+                const T d10 = wp::shfl(a0, ld + 1), d11 = wp::shfl(a1, ld + 1);
+                const T d20 = wp::shfl(a0, ld + 2), d21 = wp::shfl(a1, ld + 2), d22 = wp::shfl(a2, ld + 2);
+                const T d30 = wp::shfl(a0, ld + 3), d31 = wp::shfl(a1, ld + 3), d32 = wp::shfl(a2, ld + 3), d33 = wp::shfl(a3, ld + 3);
+                T piv = d00;
+                ok = ok && (piv > (T)0);
+                const T i0 = wp::rsqrt_(piv > (T)0 ? piv : (T)1);
+                const T l10 = d10 * i0, l20 = d20 * i0, l30 = d30 * i0;
+                piv = d11 - l10 * l10;
+                ok = ok && (piv > (T)0);
+                const T i1 = wp::rsqrt_(piv > (T)0 ? piv : (T)1);
+                const T l21 = (d21 - l20 * l10) * i1, l31 = (d31 - l30 * l10) * i1;
+                piv = d22 - l20 * l20 - l21 * l21;
+                ok = ok && (piv > (T)0);
+                const T i2 = wp::rsqrt_(piv > (T)0 ? piv : (T)1);
+                const T l32 = (d32 - l30 * l20 - l31 * l21) * i2;
+                piv = d33 - l30 * l30 - l31 * l31 - l32 * l32;
+                ok = ok && (piv > (T)0);
+                const T i3 = wp::rsqrt_(piv > (T)0 ? piv : (T)1);
+                if (lane == 0) {
+                    T* db = w.dblk + 3 * k0;          // 12 values per block of 4 columns
+                    db[0] = l10; db[1] = l20; db[2] = l21; db[3] = l30;
+                    db[4] = l31; db[5] = l32; db[6] = i0; db[7] = i1;
+                    db[8] = i2; db[9] = i3; db[10] = 0; db[11] = 0;
+                }
+            }
+            team::sync(w.t);                                    // dblk visible to the team
+        }
+        T l10, l20, l21, l30, l31, l32, i0, i1, i2, i3, pad0, pad1;
+        {
             const T* db = w.dblk + 3 * k0;
             load4(db, l10, l20, l21, l30);
             load4(db + 4, l31, l32, i0, i1);
             load4(db + 8, i2, i3, pad0, pad1);
-        } else {
-            const int ld = k0 & 31, md = k0 >> 5;
-            T a0 = acc[0][0], a1 = acc[0][1], a2 = acc[0][2], a3 = acc[0][3];
-            MPCQ_UNROLL
-            for (int m = 1; m < NSLOT; ++m)
-                if (m == md) { a0 = acc[m][0]; a1 = acc[m][1]; a2 = acc[m][2]; a3 = acc[m][3]; }
-            const T d00 = wp::shfl(a0, ld);
-            const T d10 = wp::shfl(a0, ld + 1), d11 = wp::shfl(a1, ld + 1);
-            const T d20 = wp::shfl(a0, ld + 2), d21 = wp::shfl(a1, ld + 2), d22 = wp::shfl(a2, ld + 2);
-            const T d30 = wp::shfl(a0, ld + 3), d31 = wp::shfl(a1, ld + 3), d32 = wp::shfl(a2, ld + 3), d33 = wp::shfl(a3, ld + 3);
-            T piv = d00;
-            ok = ok && (piv > (T)0);
-            i0 = wp::rsqrt_(piv > (T)0 ? piv : (T)1);
-            l10 = d10 * i0; l20 = d20 * i0; l30 = d30 * i0;
-            piv = d11 - l10 * l10;
-            ok = ok && (piv > (T)0);
-            i1 = wp::rsqrt_(piv > (T)0 ? piv : (T)1);
-            l21 = (d21 - l20 * l10) * i1; l31 = (d31 - l30 * l10) * i1;
-            piv = d22 - l20 * l20 - l21 * l21;
-            ok = ok && (piv > (T)0);
-            i2 = wp::rsqrt_(piv > (T)0 ? piv : (T)1);
-            l32 = (d32 - l30 * l20 - l31 * l21) * i2;
-            piv = d33 - l30 * l30 - l31 * l31 - l32 * l32;
-            ok = ok && (piv > (T)0);
-            i3 = wp::rsqrt_(piv > (T)0 ? piv : (T)1);
-            if (lane == 0) {
-                T* db = w.dblk + 3 * k0;          // 12 values per block of 4 columns
-                db[0] = l10; db[1] = l20; db[2] = l21; db[3] = l30;
-                db[4] = l31; db[5] = l32; db[6] = i0; db[7] = i1;
-                db[8] = i2; db[9] = i3; db[10] = 0; db[11] = 0;
-            }
         }
         // ---- panel rows: x = acc * inv(Ld)'
         {
@@ -541,7 +557,7 @@ MPCQ_DEV bool chol_factor(const Consts& cs, Work<T>& w, int k_start) {
             T* c0 = const_cast<T*>(colg);
             MPCQ_UNROLL
             for (int m = 0; m < NSLOT; ++m) {
-                const int v = lane + 32 * m;
+                const int v = row0 + RSTEP * m;
                 if (m >= m0 && v >= row_lo && v < n) {
                     const T x0 = acc[m][0] * i0;
                     const T x1 = (acc[m][1] - x0 * l10) * i1;
@@ -555,9 +571,10 @@ MPCQ_DEV bool chol_factor(const Consts& cs, Work<T>& w, int k_start) {
                 }
             }
         }
-        wp::sync();
+        if (wid == 0 && k0 + 4 < n) write_cw(k0 + 4, w.cw + 128 * (((k0 >> 2) + 1) & 1));
+        team::sync(w.t);                                        // panel columns + next cw visible
     }
-    return wp::all(ok);
+    return team::any(w.t, !ok) == false;
 }
 
 // K4b: solve L L' x = vec in place (vec in shared memory, precision T)
@@ -644,9 +661,9 @@ MPCQ_DEV void tri_solve(Work<T>& w) {
 // reduced gradient r = -Z' gam into vec (precision T); returns |r|_inf (fp64)
 template <class T>
 MPCQ_DEV double reduced_gradient(Work<T>& w) {
-    const int lane = wp::lane();
+    const int lane = w.t.tid;
     double rmax = 0;
-    for (int v = lane; v < w.n; v += 32) {
+    for (int v = lane; v < w.n; v += w.t.nt) {
         const int p = v / 3;
         double r = 0;
         if (p < w.ns) {
@@ -657,8 +674,8 @@ MPCQ_DEV double reduced_gradient(Work<T>& w) {
         w.vec[v] = (T)r;
         rmax = dmax(rmax, dabs(r));
     }
-    rmax = wp::reduce_max(rmax);
-    wp::sync();
+    rmax = team::reduce_max(w.t, rmax);
+    team::sync(w.t);
     return rmax;
 }
 
@@ -666,8 +683,8 @@ MPCQ_DEV double reduced_gradient(Work<T>& w) {
 // to double precision whatever T is
 template <class T>
 MPCQ_DEV void apply_step(const Consts& cs, Work<T>& w) {
-    const int lane = wp::lane();
-    for (int p = lane; p < w.ns; p += 32) {
+    const int lane = w.t.tid;
+    for (int p = lane; p < w.ns; p += w.t.nt) {
         const int sx = w.face[3 * p], sy = w.face[3 * p + 1], sz = w.face[3 * p + 2];
         if (sz < 0) continue;
         double* up = w.u + 3 * w.fo[p];
@@ -681,18 +698,18 @@ MPCQ_DEV void apply_step(const Consts& cs, Work<T>& w) {
             if (sy == 0) up[1] += w1;
         }
     }
-    wp::sync();
+    team::sync(w.t);
 }
 
 // refine u on the current factorisation until the reduced gradient is below tol; leaves gam = Hu+g
 template <class T, int NSLOT>
 MPCQ_DEV double refine(const Consts& cs, Work<T>& w, double tol_abs, bool u_is_zero) {
-    const int lane = wp::lane();
+    const int lane = w.t.tid;
     double rmax = 0, prev = 0;
     for (int it = 0;; ++it) {
         if (u_is_zero) {
-            for (int idx = lane; idx < w.nv; idx += 32) w.gam[idx] = w.g[idx];
-            wp::sync();
+            for (int idx = lane; idx < w.nv; idx += w.t.nt) w.gam[idx] = w.g[idx];
+            team::sync(w.t);
             u_is_zero = false;
         } else {
             hess_apply(cs, w);
@@ -700,7 +717,8 @@ MPCQ_DEV double refine(const Consts& cs, Work<T>& w, double tol_abs, bool u_is_z
         rmax = reduced_gradient(w);
         if (rmax <= tol_abs || it >= cs.refine_max || (it > 1 && rmax > 0.5 * prev)) break;   // done / cap / stagnating
         prev = rmax;
-        tri_solve<T, NSLOT>(w);
+        if (w.t.wid == 0) tri_solve<T, NSLOT>(w);               // the serial chain of the solve runs on one warp
+        team::sync(w.t);
         apply_step(cs, w);
     }
     return rmax;
@@ -712,10 +730,10 @@ struct FaceCheck { int n_primal, n_dual; };
 
 template <class T>
 MPCQ_DEV FaceCheck pdas_update(const Consts& cs, Work<T>& w, bool write) {
-    const int lane = wp::lane();
+    const int lane = w.t.tid;
     const double mu = cs.mu;
     int npv = 0, ndv = 0;
-    for (int p = lane; p < w.ns; p += 32) {
+    for (int p = lane; p < w.ns; p += w.t.nt) {
         const double* f = w.u + 3 * w.fo[p];
         const double* ga = w.gam + 3 * w.fo[p];
         const double fm = w.fmax[p];
@@ -759,9 +777,9 @@ MPCQ_DEV FaceCheck pdas_update(const Consts& cs, Work<T>& w, bool write) {
         if (write) { w.face[3 * p] = (int8_t)sx; w.face[3 * p + 1] = (int8_t)sy; w.face[3 * p + 2] = (int8_t)sz; }
     }
     FaceCheck fc;
-    fc.n_primal = wp::reduce_sum(npv);
-    fc.n_dual = wp::reduce_sum(ndv);
-    wp::sync();
+    fc.n_primal = team::reduce_sum(w.t, npv);
+    fc.n_dual = team::reduce_sum(w.t, ndv);
+    team::sync(w.t);
     return fc;
 }
 
@@ -794,6 +812,9 @@ MPCQ_DEV int reorder_feet(Work<T>& w) {
         }
         n_changed += wp::popc(balc[t]);
     }
+#if defined(MPCQ_HOST_EMU) && defined(MPCQ_TRACE)
+    if (lane == 0) { printf("   changed steps:"); for (int t = 0; t < NFS; ++t) for (int bb = 0; bb < 32; ++bb) if ((balc[t] >> bb) & 1u) printf(" %d", w.fk[32 * t + bb] >> 2); printf("\n"); }
+#endif
     if (n_changed == 0) return w.n;
     const int n_unchanged = ns - n_changed;
     wp::sync();
@@ -818,15 +839,18 @@ MPCQ_DEV int reorder_feet(Work<T>& w) {
 }
 
 // one factor-and-solve on the current faces: u = argmin on the faces (to tol), gam = Hu+g
-template <class T, int NSLOT, int NFS>
+template <class T, int NCAP, int NW>
 MPCQ_DEV bool face_solve(const Consts& cs, Work<T>& w, double tol_abs, double& rmax) {
-    const int k_start = reorder_feet<T, NFS>(w);
+    constexpr int NFS = (NCAP / 3 + 31) / 32;
+    int k_start = 0;
+    if (w.t.wid == 0) k_start = reorder_feet<T, NFS>(w);        // one warp permutes the stance list ...
+    k_start = team::bcast(w.t, k_start);                           // ... and the team learns the restart column
 #if defined(MPCQ_HOST_EMU) && defined(MPCQ_TRACE)
-    if (wp::lane() == 0) printf("   face_solve: k_start %d of n %d\n", k_start, w.n);
+    if (w.t.tid == 0) printf("   face_solve: k_start %d of n %d\n", k_start, w.n);
 #endif
     const bool cnz = build_slots(cs, w);
-    const bool ok = k_start < w.n ? chol_factor<T, NSLOT>(cs, w, k_start) : true;
-    rmax = refine<T, NSLOT>(cs, w, tol_abs, !cnz);
+    const bool ok = k_start < w.n ? chol_factor<T, NCAP, NW>(cs, w, k_start) : true;
+    rmax = refine<T, NCAP / 32>(cs, w, tol_abs, !cnz);
     return ok;
 }
 
@@ -836,11 +860,11 @@ MPCQ_DEV bool face_solve(const Consts& cs, Work<T>& w, double tol_abs, double& r
 // a row is taken active when the point sits on it (or beyond it) within the primal tolerance.
 template <class T>
 MPCQ_DEV void clamp_into(const Consts& cs, Work<T>& w, const double* src, double* dst, int8_t* fdst) {
-    const int lane = wp::lane();
+    const int lane = w.t.tid;
     const double mu = cs.mu;
-    for (int idx = lane; idx < w.nv; idx += 32) dst[idx] = 0.0;
-    wp::sync();
-    for (int p = lane; p < w.ns; p += 32) {
+    for (int idx = lane; idx < w.nv; idx += w.t.nt) dst[idx] = 0.0;
+    team::sync(w.t);
+    for (int p = lane; p < w.ns; p += w.t.nt) {
         const double* f = src + 3 * w.fo[p];
         double* o = dst + 3 * w.fo[p];
         const double fm = w.fmax[p];
@@ -859,15 +883,15 @@ MPCQ_DEV void clamp_into(const Consts& cs, Work<T>& w, const double* src, double
         }
         fdst[3 * p] = (int8_t)sx; fdst[3 * p + 1] = (int8_t)sy; fdst[3 * p + 2] = (int8_t)sz;
     }
-    wp::sync();
+    team::sync(w.t);
 }
 
 // phi(v) = 1/2 v'Hv + g'v = 1/2 v'(gam + g) for the vector v currently in w.u with w.gam = Hv + g
 template <class T>
 MPCQ_DEV double objective(const Consts& cs, Work<T>& w) {
     double s = 0.0;
-    for (int idx = wp::lane(); idx < w.nv; idx += 32) s += w.u[idx] * (w.gam[idx] + w.g[idx]);
-    return 0.5 * wp::reduce_sum(s);
+    for (int idx = w.t.tid; idx < w.nv; idx += w.t.nt) s += w.u[idx] * (w.gam[idx] + w.g[idx]);
+    return 0.5 * team::reduce_sum(w.t, s);
 }
 
 // objective of an arbitrary vector (temporarily viewed as w.u); clobbers w.gam
@@ -891,11 +915,11 @@ MPCQ_DEV void row_slacks(const double* f, double mu, double fm, double (&s)[6]) 
 // inactive row satisfied, and the (foot, row) that blocks (tag = 8*p + row, 0x7fffffff if none)
 template <class T>
 MPCQ_DEV void ratio_test(const Consts& cs, Work<T>& w, double& alpha, int& tag) {
-    const int lane = wp::lane();
+    const int lane = w.t.tid;
     const double mu = cs.mu;
     alpha = 1.0;
     tag = 0x7fffffff;
-    for (int p = lane; p < w.ns; p += 32) {
+    for (int p = lane; p < w.ns; p += w.t.nt) {
         const int sx = w.face[3 * p], sy = w.face[3 * p + 1], sz = w.face[3 * p + 2];
         if (sz < 0) continue;
         const double* f0 = w.ucur + 3 * w.fo[p];
@@ -915,7 +939,7 @@ MPCQ_DEV void ratio_test(const Consts& cs, Work<T>& w, double& alpha, int& tag) 
             }
         }
     }
-    wp::reduce_argmin(alpha, tag);
+    team::reduce_argmin(w.t, alpha, tag);
     if (tag == 0x7fffffff) alpha = 1.0;
 }
 
@@ -923,9 +947,9 @@ MPCQ_DEV void ratio_test(const Consts& cs, Work<T>& w, double& alpha, int& tag) 
 // them part of their faces at once (instead of one factorisation per row).
 template <class T>
 MPCQ_DEV void block_all_at_zero(const Consts& cs, Work<T>& w) {
-    const int lane = wp::lane();
+    const int lane = w.t.tid;
     const double mu = cs.mu;
-    for (int p = lane; p < w.ns; p += 32) {
+    for (int p = lane; p < w.ns; p += w.t.nt) {
         int sx = w.face[3 * p], sy = w.face[3 * p + 1], sz = w.face[3 * p + 2];
         if (sz < 0) continue;
         double* f0 = w.ucur + 3 * w.fo[p];
@@ -957,15 +981,15 @@ MPCQ_DEV void block_all_at_zero(const Consts& cs, Work<T>& w) {
         }
         w.face[3 * p] = (int8_t)sx; w.face[3 * p + 1] = (int8_t)sy; w.face[3 * p + 2] = (int8_t)sz;
     }
-    wp::sync();
+    team::sync(w.t);
 }
 
 // move ucur by alpha towards u and make the blocking row part of its foot's face
 template <class T>
 MPCQ_DEV void blocked_step(const Consts& cs, Work<T>& w, double alpha, int tag) {
-    const int lane = wp::lane();
-    for (int idx = lane; idx < w.nv; idx += 32) w.ucur[idx] += alpha * (w.u[idx] - w.ucur[idx]);
-    wp::sync();
+    const int lane = w.t.tid;
+    for (int idx = lane; idx < w.nv; idx += w.t.nt) w.ucur[idx] += alpha * (w.u[idx] - w.ucur[idx]);
+    team::sync(w.t);
     if (lane == 0) {
         const int p = tag >> 3, r = tag & 7;
         int sx = w.face[3 * p], sy = w.face[3 * p + 1], sz = w.face[3 * p + 2];
@@ -980,56 +1004,69 @@ MPCQ_DEV void blocked_step(const Consts& cs, Work<T>& w, double alpha, int tag) 
         }
         w.face[3 * p] = (int8_t)sx; w.face[3 * p + 1] = (int8_t)sy; w.face[3 * p + 2] = (int8_t)sz;
     }
-    wp::sync();
+    team::sync(w.t);
 }
 
 // ---------------------------------------------------------------------------------------------
 // the whole path for environment b.  NCAP = slot capacity of this size class.
-template <class T, int NCAP>
+template <class T, int NCAP, int NW>
 MPCQ_DEV void solve_env(const Consts& cs, const IO<T>& io, int b, char* smem, T* l_global, int ns_lo, int ns_hi) {
     const int nmax = (3 * (ns_hi < NCAP / 3 ? ns_hi : NCAP / 3) + 3) & ~3;     // largest system of this size class
-    constexpr int NSLOT = NCAP / 32;
-    constexpr int NFS = (NCAP / 3 + 31) / 32;
-    const int lane = wp::lane();
     const int H = cs.horizon;
     Work<T> w;
     carve(w, smem, l_global, H, NCAP, false, nmax);
-    // ---- K3a: stance list from the contact table (ub_fz = gait * fz_max > 0)
+    w.t.tid = NW == 1 ? wp::lane() : wp::team_tid();
+    w.t.nt = 32 * NW;
+    w.t.wid = NW == 1 ? 0 : (w.t.tid >> 5);
+    const int lane = w.t.tid;                                   // thread index within the team
+    constexpr int NSLOT = NCAP / 32;                            // rows per lane when ONE warp sweeps (triangular solves)
+    // ---- K3a: stance list from the contact table (ub_fz = gait * fz_max > 0); every warp builds it redundantly
+    // (identical values, so the concurrent writes are benign) and therefore knows ns without a broadcast
     const float* gait = io.gait + (size_t)b * 4 * H;
     int ns = 0;
-    for (int k0 = 0; k0 < 4 * H; k0 += 32) {
-        const int k = k0 + lane;
-        const double fm = k < 4 * H ? (double)gait[k] * cs.fz_max : 0.0;
-        const bool st = fm > 0.0;
-        const unsigned bal = wp::ballot(st);
-        const int pos = ns + wp::popc(bal & ((1u << lane) - 1u));
-        if (k < 4 * H) w.cidx[k] = (uint8_t)((st && pos < NCAP / 3) ? pos : 255);
-        if (st && pos < NCAP / 3) { w.fk[pos] = (uint8_t)k; w.fo[pos] = (uint8_t)pos; w.fmax[pos] = fm; w.face[3 * pos] = 0; w.face[3 * pos + 1] = 0; w.face[3 * pos + 2] = 0;
-                                      w.facef[3 * pos] = 99; w.facef[3 * pos + 1] = 99; w.facef[3 * pos + 2] = 99; }
-        ns += wp::popc(bal);
+    {
+        const int wl = wp::lane();
+        // The list is built LAST horizon step first: face changes concentrate on the early steps (measured), so the
+        // volatile foot-steps end up at the back of the factor and re-factorisations restart late (reorder_feet).
+        for (int k0 = 0; k0 < 4 * H; k0 += 32) {
+            const int k = 4 * H - 1 - (k0 + wl);
+            const double fm = k >= 0 ? (double)gait[k] * cs.fz_max : 0.0;
+            const bool st = fm > 0.0;
+            const unsigned bal = wp::ballot(st);
+            const int pos = ns + wp::popc(bal & ((1u << wl) - 1u));
+            if (w.t.wid == 0) {
+                if (k >= 0) w.cidx[k] = (uint8_t)((st && pos < NCAP / 3) ? pos : 255);
+                if (st && pos < NCAP / 3) {
+                    w.fk[pos] = (uint8_t)k; w.fo[pos] = (uint8_t)pos; w.fmax[pos] = fm;
+                    w.face[3 * pos] = 0; w.face[3 * pos + 1] = 0; w.face[3 * pos + 2] = 0;
+                    w.facef[3 * pos] = 99; w.facef[3 * pos + 1] = 99; w.facef[3 * pos + 2] = 99;
+                }
+            }
+            ns += wp::popc(bal);
+        }
     }
     if (ns < ns_lo || ns > ns_hi) return;                       // another size class owns this env
     w.ns = ns;
     w.nv = 3 * ns;
     w.n = (3 * ns + 3) & ~3;
-    wp::sync();
+    team::sync(w.t);
     int status = 0, nfac = 0, nas = 0;
     double rmax = 0.0, pviol = 0.0;
     if (ns == 0) {
         status = ST_NO_STANCE | ST_VERIFIED;
-        wp::sync();
+        team::sync(w.t);
     } else {
         const double yaw = io.yaw ? (double)io.yaw[b] : (double)io.x0[(size_t)b * 13 + 2];
         setup_model(cs, w, io.x0 + (size_t)b * 13, yaw, io.r_feet + (size_t)b * 12, io.x_ref + (size_t)b * 13 * H);
         double gsc = 0.0;
-        for (int idx = lane; idx < w.nv; idx += 32) gsc = dmax(gsc, dabs(w.g[idx]));
-        gsc = 1.0 + wp::reduce_max(gsc);
+        for (int idx = lane; idx < w.nv; idx += w.t.nt) gsc = dmax(gsc, dabs(w.g[idx]));
+        gsc = 1.0 + team::reduce_max(w.t, gsc);
         const double tol_loose = cs.tol_r_loose * gsc, tol_tight = cs.tol_r_tight * gsc;
         bool numeric_ok = (gsc == gsc) && (gsc < 1e300);
         bool done = false;
         // ---- primal-dual active-set rounds
         for (int round = 0; round <= cs.pdas_cap && numeric_ok && !done; ++round) {
-            numeric_ok = face_solve<T, NSLOT, NFS>(cs, w, tol_loose, rmax) && numeric_ok;
+            numeric_ok = face_solve<T, NCAP, NW>(cs, w, tol_loose, rmax) && numeric_ok;
             ++nfac;
             FaceCheck fc = pdas_update(cs, w, false);
             if (fc.n_primal == 0 && fc.n_dual == 0) {
@@ -1051,7 +1088,7 @@ MPCQ_DEV void solve_env(const Consts& cs, const IO<T>& io, int b, char* smem, T*
             clamp_into(cs, w, w.u, w.ucur, w.face);
             double phi_cur = objective_of(cs, w, w.ucur);
             for (nas = 1; nas <= cs.as_cap; ++nas) {
-                numeric_ok = face_solve<T, NSLOT, NFS>(cs, w, tol_tight, rmax) && numeric_ok;
+                numeric_ok = face_solve<T, NCAP, NW>(cs, w, tol_tight, rmax) && numeric_ok;
                 ++nfac;
                 if (!numeric_ok) break;
                 double alpha;
@@ -1061,7 +1098,7 @@ MPCQ_DEV void solve_env(const Consts& cs, const IO<T>& io, int b, char* smem, T*
                 if (lane == 0) printf("  AS it %d: alpha %.3e tag %d phi_cur %.10e rmax %.2e\n", nas, alpha, tag, phi_cur, rmax);
 #endif
                 if (tag == 0x7fffffff) {                    // (a)
-                    for (int idx = lane; idx < w.nv; idx += 32) w.ucur[idx] = w.u[idx];
+                    for (int idx = lane; idx < w.nv; idx += w.t.nt) w.ucur[idx] = w.u[idx];
                     phi_cur = objective(cs, w);
                     const FaceCheck fc = pdas_update(cs, w, true);
 #if defined(MPCQ_HOST_EMU) && defined(MPCQ_TRACE)
@@ -1076,9 +1113,9 @@ MPCQ_DEV void solve_env(const Consts& cs, const IO<T>& io, int b, char* smem, T*
                 if (lane == 0) printf("     trial phi %.10e -> %s\n", phi_t, phi_t < phi_cur - 1e-12 * dabs(phi_cur) ? "accept" : "ratio step");
 #endif
                 if (phi_t < phi_cur - 1e-12 * dabs(phi_cur)) {   // (b)
-                    for (int idx = lane; idx < w.nv; idx += 32) w.ucur[idx] = w.utrial[idx];
-                    for (int idx = lane; idx < 3 * w.ns; idx += 32) w.face[idx] = w.face2[idx];
-                    wp::sync();
+                    for (int idx = lane; idx < w.nv; idx += w.t.nt) w.ucur[idx] = w.utrial[idx];
+                    for (int idx = lane; idx < 3 * w.ns; idx += w.t.nt) w.face[idx] = w.face2[idx];
+                    team::sync(w.t);
                     phi_cur = phi_t;
                 } else if (alpha <= 1e-13) {                // (c0) degenerate: no move possible, fix every such row
                     block_all_at_zero(cs, w);
@@ -1088,8 +1125,8 @@ MPCQ_DEV void solve_env(const Consts& cs, const IO<T>& io, int b, char* smem, T*
                 }
             }
             if (!done) {                                   // return the feasible iterate
-                for (int idx = lane; idx < w.nv; idx += 32) w.u[idx] = w.ucur[idx];
-                wp::sync();
+                for (int idx = lane; idx < w.nv; idx += w.t.nt) w.u[idx] = w.ucur[idx];
+                team::sync(w.t);
                 hess_apply(cs, w);
             }
         }
@@ -1097,7 +1134,7 @@ MPCQ_DEV void solve_env(const Consts& cs, const IO<T>& io, int b, char* smem, T*
     }
     // ---- outputs: forces, activity (on primal slack, like the oracle's kkt_report), residuals
     const double mu = cs.mu;
-    for (int k = lane; k < 4 * H; k += 32) {
+    for (int k = lane; k < 4 * H; k += w.t.nt) {
         const int sidx = w.cidx[k];
         double f[3] = {0.0, 0.0, 0.0};
         if (sidx != 255) { f[0] = w.u[3 * sidx]; f[1] = w.u[3 * sidx + 1]; f[2] = w.u[3 * sidx + 2]; }
@@ -1121,7 +1158,7 @@ MPCQ_DEV void solve_env(const Consts& cs, const IO<T>& io, int b, char* smem, T*
             fo[0] = (T)f[0]; fo[1] = (T)f[1]; fo[2] = (T)f[2];
         }
     }
-    pviol = wp::reduce_max(pviol);
+    pviol = team::reduce_max(w.t, pviol);
     if (lane == 0) {
         if (io.iters) { io.iters[2 * b] = nfac; io.iters[2 * b + 1] = nas; }
         if (io.resid) { io.resid[2 * b] = rmax; io.resid[2 * b + 1] = dmax(pviol, 0.0); }

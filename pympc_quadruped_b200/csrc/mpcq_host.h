@@ -11,8 +11,23 @@
 namespace mpcq {
 
 // size classes by number of stance foot-steps (slot capacity = 3 * stance, rounded to 32 rows/lane)
-struct SizeClass { int ncap, ns_lo, ns_hi; };
-static const SizeClass kClasses[4] = {{64, 0, 20}, {128, 21, 42}, {192, 43, 64}, {384, 65, 128}};
+struct SizeClass { int ncap, ns_lo, ns_hi, nw; };      // nw = warps of the team that owns one environment
+// team sizes are compile-time constants of the kernels (tunable with -DMPCQ_NWx=... for experiments).
+// Measured on B200 (profiles/r01_team_size_sweep.txt): one warp is best for n <= 60 (the CTA barriers and the lower
+// FMA density cost more than the extra warps hide), 2-3 warps give 1.3-1.5x for n = 120 / 180, larger teams lose.
+#ifndef MPCQ_NW0
+#define MPCQ_NW0 1
+#endif
+#ifndef MPCQ_NW1
+#define MPCQ_NW1 2
+#endif
+#ifndef MPCQ_NW2
+#define MPCQ_NW2 3
+#endif
+#ifndef MPCQ_NW3
+#define MPCQ_NW3 2
+#endif
+static const SizeClass kClasses[4] = {{64, 0, 20, MPCQ_NW0}, {128, 21, 42, MPCQ_NW1}, {192, 43, 64, MPCQ_NW2}, {384, 65, 128, MPCQ_NW3}};
 inline int class_nmax(const SizeClass& c) { return (3 * c.ns_hi + 3) & ~3; }   // rows of the largest system in the class
 
 inline int num_classes(int horizon) {

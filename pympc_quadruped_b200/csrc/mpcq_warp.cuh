@@ -17,8 +17,10 @@
 #define MPCQ_HD inline
 #define MPCQ_UNROLL
 namespace mpcq_emu {
-int lane_id();
-uint64_t exchange(uint64_t v, int src);   // every lane publishes v, returns the value of lane `src`
+int lane_id();                            // lane within the warp
+int thread_id();                          // thread within the team (CTA)
+uint64_t exchange(uint64_t v, int src);   // every lane of the warp publishes v, returns the value of lane `src`
+void team_barrier();                      // all threads of the team
 }
 #else
 #include <cuda_runtime.h>
@@ -72,6 +74,14 @@ MPCQ_DEV double rsqrt_(double x) {
 }
 #endif
 
+#ifdef MPCQ_HOST_EMU
+MPCQ_DEV int team_tid() { return mpcq_emu::thread_id(); }
+MPCQ_DEV void team_sync() { mpcq_emu::team_barrier(); }
+#else
+MPCQ_DEV int team_tid() { return threadIdx.x; }
+MPCQ_DEV void team_sync() { __syncthreads(); }
+#endif
+
 MPCQ_DEV bool any(bool p) { return ballot(p) != 0u; }
 MPCQ_DEV bool all(bool p) { return ballot(p) == FULL; }
 
@@ -100,3 +110,78 @@ MPCQ_DEV void reduce_argmin(double& v, int& tag) {
 }
 
 }  // namespace wp
+
+// A team = the warps (one CTA of nt threads) that own one environment.  With one warp the team collectives are the
+// warp collectives; with more they go through a few words of shared memory and the CTA barrier.
+namespace team {
+
+struct Ctx {
+    int tid, nt, wid;      // thread in team, team size, warp in team
+    double* red;           // [8] scratch
+    int* redi;             // [8] scratch
+};
+
+MPCQ_DEV void sync(const Ctx& c) {
+    if (c.nt == 32) wp::sync(); else wp::team_sync();
+}
+
+MPCQ_DEV double reduce_max(const Ctx& c, double v) {
+    v = wp::reduce_max(v);
+    if (c.nt == 32) return v;
+    if (wp::lane() == 0) c.red[c.wid] = v;
+    wp::team_sync();
+    double r = c.red[0];
+    for (int i = 1; i < (c.nt >> 5); ++i) r = c.red[i] > r ? c.red[i] : r;
+    wp::team_sync();
+    return r;
+}
+
+MPCQ_DEV double reduce_sum(const Ctx& c, double v) {
+    v = wp::reduce_sum(v);
+    if (c.nt == 32) return v;
+    if (wp::lane() == 0) c.red[c.wid] = v;
+    wp::team_sync();
+    double r = c.red[0];
+    for (int i = 1; i < (c.nt >> 5); ++i) r += c.red[i];
+    wp::team_sync();
+    return r;
+}
+
+MPCQ_DEV int reduce_sum(const Ctx& c, int v) {
+    v = wp::reduce_sum(v);
+    if (c.nt == 32) return v;
+    if (wp::lane() == 0) c.redi[c.wid] = v;
+    wp::team_sync();
+    int r = c.redi[0];
+    for (int i = 1; i < (c.nt >> 5); ++i) r += c.redi[i];
+    wp::team_sync();
+    return r;
+}
+
+MPCQ_DEV void reduce_argmin(const Ctx& c, double& v, int& tag) {
+    wp::reduce_argmin(v, tag);
+    if (c.nt == 32) return;
+    if (wp::lane() == 0) { c.red[c.wid] = v; c.redi[c.wid] = tag; }
+    wp::team_sync();
+    double rv = c.red[0];
+    int rt = c.redi[0];
+    for (int i = 1; i < (c.nt >> 5); ++i)
+        if (c.red[i] < rv || (c.red[i] == rv && c.redi[i] < rt)) { rv = c.red[i]; rt = c.redi[i]; }
+    wp::team_sync();
+    v = rv;
+    tag = rt;
+}
+
+MPCQ_DEV bool any(const Ctx& c, bool p) { return reduce_sum(c, p ? 1 : 0) != 0; }
+
+// value held by warp 0 -> every thread (also a barrier: what warp 0 wrote before is visible after)
+MPCQ_DEV int bcast(const Ctx& c, int v) {
+    if (c.nt == 32) { wp::sync(); return v; }
+    if (c.tid == 0) c.redi[7] = v;
+    wp::team_sync();
+    const int r = c.redi[7];
+    wp::team_sync();
+    return r;
+}
+
+}  // namespace team

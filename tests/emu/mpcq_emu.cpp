@@ -3,8 +3,8 @@
 // (libmpcq.so) never contains or loads this file: it has no CPU path.  Built by tests/emu/build.py
 // into tests/emu/_build/libmpcq_emu.so and used only by `-m "not gpu"` tests.
 //
-// The 32 lanes of a warp run as coroutines (ucontext) on one thread, switched round-robin at
-// every warp collective; values are exchanged through a double-buffered slot array.
+// The threads of a team (1-6 warps) run as coroutines (ucontext) on one thread, switched round-robin at
+// every collective; values are exchanged through a double-buffered slot array.
 #define MPCQ_HOST_EMU 1
 #include <stdint.h>
 #include <stdlib.h>
@@ -15,20 +15,24 @@
 #include "../../pympc_quadruped_b200/csrc/mpcq_host.h"
 
 namespace mpcq_emu {
-static ucontext_t main_ctx, ctx[32];
-static int cur = 0;
-static uint64_t slots[2][32];
-static long gen[32];
-static bool finished[32];
+// A team of NT threads (NT / 32 warps) runs as coroutines on one host thread, switched round-robin at every
+// collective.  Warp collectives exchange values among the 32 threads of one warp; the team barrier spans all.
+constexpr int MAXT = 256;
+static ucontext_t main_ctx, ctx[MAXT];
+static int cur = 0, NT = 32;
+static uint64_t slots[2][MAXT];
+static long gen[MAXT], bgen[MAXT];
+static bool finished[MAXT];
 static void (*lane_fn)(void*) = nullptr;
 static void* lane_arg = nullptr;
 
-int lane_id() { return cur; }
+int lane_id() { return cur & 31; }
+int thread_id() { return cur; }
 
 static void yield_next() {
     int old = cur;
-    for (int step = 1; step <= 32; ++step) {
-        int nxt = (old + step) & 31;
+    for (int step = 1; step <= NT; ++step) {
+        int nxt = (old + step) % NT;
         if (!finished[nxt]) {
             if (nxt == old) return;
             cur = nxt;
@@ -36,23 +40,35 @@ static void yield_next() {
             return;
         }
     }
-    // everyone finished
     cur = old;
     swapcontext(&ctx[old], &main_ctx);
 }
 
 uint64_t exchange(uint64_t v, int src) {
     const long g = gen[cur];
+    const int base = cur & ~31;
     slots[g & 1][cur] = v;
     gen[cur] = g + 1;
     for (;;) {
         bool all = true;
-        for (int l = 0; l < 32; ++l)
+        for (int l = base; l < base + 32; ++l)
             if (!finished[l] && gen[l] <= g) { all = false; break; }
         if (all) break;
         yield_next();
     }
-    return slots[g & 1][src];
+    return slots[g & 1][base + src];
+}
+
+void team_barrier() {
+    const long g = bgen[cur];
+    bgen[cur] = g + 1;
+    for (;;) {
+        bool all = true;
+        for (int l = 0; l < NT; ++l)
+            if (!finished[l] && bgen[l] <= g) { all = false; break; }
+        if (all) break;
+        yield_next();
+    }
 }
 
 static void trampoline() {
@@ -61,15 +77,17 @@ static void trampoline() {
     for (;;) yield_next();
 }
 
-void run_warp(void (*fn)(void*), void* arg) {
+void run_team(int nthreads, void (*fn)(void*), void* arg) {
     static std::vector<char> stacks;
     const size_t STK = 512 * 1024;
-    if (stacks.empty()) stacks.resize(32 * STK);
+    if (stacks.empty()) stacks.resize(MAXT * STK);
+    NT = nthreads;
     lane_fn = fn;
     lane_arg = arg;
-    for (int l = 0; l < 32; ++l) {
+    for (int l = 0; l < NT; ++l) {
         finished[l] = false;
         gen[l] = 0;
+        bgen[l] = 0;
         getcontext(&ctx[l]);
         ctx[l].uc_stack.ss_sp = stacks.data() + l * STK;
         ctx[l].uc_stack.ss_size = STK;
@@ -95,10 +113,10 @@ template <class T> void lane_entry(void* p) {
     Job<T>* j = static_cast<Job<T>*>(p);
     const mpcq::SizeClass& sc = mpcq::kClasses[j->ncap];
     switch (j->ncap) {
-        case 0: mpcq::solve_env<T, 64>(j->cs, j->io, j->b, j->smem, j->lglobal, sc.ns_lo, sc.ns_hi); break;
-        case 1: mpcq::solve_env<T, 128>(j->cs, j->io, j->b, j->smem, j->lglobal, sc.ns_lo, sc.ns_hi); break;
-        case 2: mpcq::solve_env<T, 192>(j->cs, j->io, j->b, j->smem, j->lglobal, sc.ns_lo, sc.ns_hi); break;
-        default: mpcq::solve_env<T, 384>(j->cs, j->io, j->b, j->smem, j->lglobal, sc.ns_lo, sc.ns_hi); break;
+        case 0: mpcq::solve_env<T, 64, MPCQ_NW0>(j->cs, j->io, j->b, j->smem, j->lglobal, sc.ns_lo, sc.ns_hi); break;
+        case 1: mpcq::solve_env<T, 128, MPCQ_NW1>(j->cs, j->io, j->b, j->smem, j->lglobal, sc.ns_lo, sc.ns_hi); break;
+        case 2: mpcq::solve_env<T, 192, MPCQ_NW2>(j->cs, j->io, j->b, j->smem, j->lglobal, sc.ns_lo, sc.ns_hi); break;
+        default: mpcq::solve_env<T, 384, MPCQ_NW3>(j->cs, j->io, j->b, j->smem, j->lglobal, sc.ns_lo, sc.ns_hi); break;
     }
 }
 
@@ -120,7 +138,7 @@ int run(const mpcq_config* cfg, int B, const T* x0, const T* yaw, const T* feet,
             j.smem = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(smem.data()) + 31) & ~uintptr_t(31));
             j.lglobal = nullptr;
             j.ncap = ci;
-            mpcq_emu::run_warp(lane_entry<T>, &j);
+            mpcq_emu::run_team(32 * mpcq::kClasses[ci].nw, lane_entry<T>, &j);
         }
     }
     return 0;
