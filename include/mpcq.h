@@ -70,7 +70,7 @@ typedef struct mpcq_config {
     /* solver knobs (0 = default) */
     int32_t max_pdas_rounds;        /* primal-dual active-set rounds before the fallback; default 8 */
     int32_t max_as_iter;            /* fallback active-set iterations; default 12*horizon + 30 */
-    int32_t max_refine;             /* residual-refinement solves per factorisation; default 8 */
+    int32_t max_refine;             /* preconditioned-CG refinement steps per factorisation; default 20 */
     int32_t reserved1;
     double tol_primal;              /* relative feasibility tolerance of the face tests; default 1e-7 (f32) / 1e-9 (f64) */
     double tol_dual;                /* relative multiplier-sign tolerance; default 1e-7 (f32) / 1e-9 (f64) */

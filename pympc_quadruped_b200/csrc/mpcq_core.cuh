@@ -42,6 +42,7 @@ struct Consts {
     double tol_p, tol_d;   // relative primal / dual tolerances of the face tests
     double tol_r_loose, tol_r_tight;   // reduced-gradient tolerances (relative to 1 + |g|_inf)
     double tol_active;     // slack tolerance of the reported constraint activity
+    double tol_r_abs;      // absolute cap of the tight reduced-gradient tolerance: 2 min(R) * (force accuracy in N)
 };
 
 template <class T> struct IO {
@@ -68,7 +69,7 @@ MPCQ_HD constexpr int l_elems(int n) { return n * n / 2 + 2 * n + 32; }   // +32
 
 template <class T> struct Work {
     // fp64
-    double *Md, *GW, *g, *u, *gam, *P0, *P1, *ucur, *utrial, *fmax;
+    double *Md, *GW, *g, *u, *gam, *P0, *P1, *ucur, *utrial, *hd, *fmax;
     // precision T
     T *L, *dblk, *vec, *cw, *zt, *Mf, *St;
     int32_t* sinf;         // per slot: step | leg << 8 | foot << 16 | dead << 30
@@ -86,7 +87,7 @@ template <class T> struct Work {
 
 template <class T>
 MPCQ_HD constexpr size_t work_bytes(int H, int ncap, bool l_in_smem, bool with_md = false, int nmax = 0) {
-    size_t nd = (with_md ? 288 : 0) + 72 + 2 * 12 * (size_t)H + 5 * (size_t)ncap + ncap / 3 + 1 + 12;
+    size_t nd = (with_md ? 288 : 0) + 72 + 2 * 12 * (size_t)H + 6 * (size_t)ncap + ncap / 3 + 1 + 12;
     size_t nt = (l_in_smem ? l_elems(nmax > 0 ? nmax : ncap) : 0) + 3 * (ncap / 4) * 4 + ncap + 256 + 3 * ncap + 288 + (size_t)H * H;
     size_t nb = (ncap / 3 + 1) * 11 + 4 * (size_t)H + 16 + 4 * (size_t)ncap;
     return align_up(nd * 8, 16) + align_up(nt * sizeof(T), 16) + align_up(nb, 16);
@@ -104,10 +105,11 @@ MPCQ_DEV void carve(Work<T>& w, char* base, T* l_global, int H, int ncap, bool w
     w.P1 = d; d += 12 * H;
     w.ucur = d; d += ncap;
     w.utrial = d; d += ncap;
+    w.hd = d; d += ncap;
     w.fmax = d; d += ncap / 3 + 1;
     w.t.red = d; d += 8;
     w.t.redi = reinterpret_cast<int*>(d); d += 4;
-    size_t nd = (with_md ? 288 : 0) + 72 + 2 * 12 * (size_t)H + 5 * (size_t)ncap + ncap / 3 + 1 + 12;
+    size_t nd = (with_md ? 288 : 0) + 72 + 2 * 12 * (size_t)H + 6 * (size_t)ncap + ncap / 3 + 1 + 12;
     T* t = reinterpret_cast<T*>(base + align_up(nd * 8, 16));
     size_t used = 0;
     if (l_global) {
@@ -304,7 +306,7 @@ MPCQ_DEV void setup_model(const Consts& cs, Work<T>& w, const T* x0p, double yaw
 //   1. y_i = (G u_i, W u_i, sum_legs u_i / m)  per step      2. mix over steps with N and S
 //   3. project back with G', W'.   u, gam in full [H][12] layout; P0 / P1 are scratch.
 template <class T>
-MPCQ_DEV void hess_apply(const Consts& cs, Work<T>& w) {
+MPCQ_DEV void hess_apply(const Consts& cs, Work<T>& w, const double* uin, double* out, bool add_g) {
     const int lane = w.t.tid;
     const int H = cs.horizon;
     for (int idx = lane; idx < 9 * H; idx += w.t.nt) {
@@ -316,7 +318,7 @@ MPCQ_DEV void hess_apply(const Consts& cs, Work<T>& w) {
             for (int a = 0; a < 4; ++a) {
                 const int s = w.cidx[4 * i + a];
                 if (s != 255) {
-                    const double* ua = w.u + 3 * s;
+                    const double* ua = uin + 3 * s;
                     y += gw[18 * a] * ua[0] + gw[18 * a + 1] * ua[1] + gw[18 * a + 2] * ua[2];
                 }
             }
@@ -326,7 +328,7 @@ MPCQ_DEV void hess_apply(const Consts& cs, Work<T>& w) {
             MPCQ_UNROLL
             for (int a = 0; a < 4; ++a) {
                 const int s = w.cidx[4 * i + a];
-                if (s != 255) y += w.u[3 * s + x];
+                if (s != 255) y += uin[3 * s + x];
             }
             y *= cs.inv_mass;
         }
@@ -355,10 +357,13 @@ MPCQ_DEV void hess_apply(const Consts& cs, Work<T>& w) {
         const double* gw = w.GW + 18 * a + y;
         const double t0 = cs.inv_mass * Y[3 + y] + gw[0] * Y[0] + gw[3] * Y[1] + gw[6] * Y[2];
         const double t1 = cs.inv_mass * Y[9 + y] + gw[9] * Y[6] + gw[12] * Y[7] + gw[15] * Y[8];
-        w.gam[o] = w.g[o] + 2.0 * (cs.r[3 * a + y] * w.u[o] + dt2 * t0 + dt4 * t1);
+        out[o] = (add_g ? w.g[o] : 0.0) + 2.0 * (cs.r[3 * a + y] * uin[o] + dt2 * t0 + dt4 * t1);
     }
     team::sync(w.t);
 }
+
+template <class T>
+MPCQ_DEV void hess_apply(const Consts& cs, Work<T>& w) { hess_apply(cs, w, w.u, w.gam, true); }
 
 // ---------------------------------------------------------------------------------------------
 // K3: faces -> slot vectors z (precision T) and the face constants c written into u.
@@ -658,19 +663,24 @@ MPCQ_DEV void tri_solve(Work<T>& w) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// -z_v' gam_p for slot v = 3p + c with z rebuilt from the face code in fp64 (the float z of the factor carries a
+// float-rounded mu: good enough for a preconditioner, not for the stationarity test)
+MPCQ_DEV double slot_residual(int sx, int sy, int sz, int c, const double* gp, double mu) {
+    if (sz < 0) return 0.0;
+    if (c == 0) return sx == 0 ? -gp[0] : 0.0;
+    if (c == 1) return sy == 0 ? -gp[1] : 0.0;
+    return sz == 0 ? -(sx * mu * gp[0] + sy * mu * gp[1] + gp[2]) : 0.0;
+}
+
 // reduced gradient r = -Z' gam into vec (precision T); returns |r|_inf (fp64)
 template <class T>
-MPCQ_DEV double reduced_gradient(Work<T>& w) {
+MPCQ_DEV double reduced_gradient(const Consts& cs, Work<T>& w) {
     const int lane = w.t.tid;
     double rmax = 0;
     for (int v = lane; v < w.n; v += w.t.nt) {
         const int p = v / 3;
         double r = 0;
-        if (p < w.ns) {
-            const double* gp = w.gam + 3 * w.fo[p];
-            const T* z = w.zt + 3 * v;
-            r = -((double)z[0] * gp[0] + (double)z[1] * gp[1] + (double)z[2] * gp[2]);
-        }
+        if (p < w.ns) r = slot_residual(w.face[3 * p], w.face[3 * p + 1], w.face[3 * p + 2], v - 3 * p, w.gam + 3 * w.fo[p], cs.mu);
         w.vec[v] = (T)r;
         rmax = dmax(rmax, dabs(r));
     }
@@ -701,26 +711,92 @@ MPCQ_DEV void apply_step(const Consts& cs, Work<T>& w) {
     team::sync(w.t);
 }
 
-// refine u on the current factorisation until the reduced gradient is below tol; leaves gam = Hu+g
+// Improve u on the current faces until the reduced gradient is below tol; leaves gam = Hu+g.
+// Conjugate gradients on the reduced system Z'HZ w = -Z'(Hu+g), preconditioned by the (precision-T) Cholesky
+// factor, with every residual and the operator in fp64.  With an accurate factor this is one step of
+// iterative refinement per iteration; with a factor that is only a rough inverse (fp32, n = 180, cond 1e6)
+// plain refinement stagnates while CG still converges in a few steps.  The search direction lives in the
+// full space (d = Z p, kept in utrial), so no reduced-space fp64 vectors are needed.
 template <class T, int NSLOT>
-MPCQ_DEV double refine(const Consts& cs, Work<T>& w, double tol_abs, bool u_is_zero) {
+MPCQ_DEV double refine(const Consts& cs, Work<T>& w, double tol_abs, bool u_is_zero, bool use_cg) {
     const int lane = w.t.tid;
-    double rmax = 0, prev = 0;
-    for (int it = 0;; ++it) {
-        if (u_is_zero) {
-            for (int idx = lane; idx < w.nv; idx += w.t.nt) w.gam[idx] = w.g[idx];
-            team::sync(w.t);
-            u_is_zero = false;
-        } else {
-            hess_apply(cs, w);
-        }
-        rmax = reduced_gradient(w);
-        if (rmax <= tol_abs || it >= cs.refine_max || (it > 1 && rmax > 0.5 * prev)) break;   // done / cap / stagnating
-        prev = rmax;
-        if (w.t.wid == 0) tri_solve<T, NSLOT>(w);               // the serial chain of the solve runs on one warp
+    if (u_is_zero) {
+        for (int idx = lane; idx < w.nv; idx += w.t.nt) w.gam[idx] = w.g[idx];
         team::sync(w.t);
-        apply_step(cs, w);
+    } else {
+        hess_apply(cs, w);
     }
+    double rmax = reduced_gradient(cs, w);                            // r = -Z' gam -> vec
+    // Plain refinement (u += Z M^-1 r) first: with an accurate factor it gains 2-3 digits per step and is the cheapest.
+    // Intermediate active-set rounds (use_cg = false) stop there - they only need the faces right.
+    {
+        double prev = 0.0;
+        const int cap = use_cg ? cs.refine_max : 3;
+        int it = 0;
+        for (; rmax > tol_abs && it < cap; ++it) {
+            if (it > 0 && rmax > 0.2 * prev) break;              // converging too slowly: hand over to CG
+            prev = rmax;
+            if (w.t.wid == 0) tri_solve<T, NSLOT>(w);
+            team::sync(w.t);
+            apply_step(cs, w);
+            hess_apply(cs, w);
+            rmax = reduced_gradient(cs, w);
+        }
+        if (!use_cg || rmax <= tol_abs) return rmax;
+    }
+    double rz = 0.0;
+    double* d = w.utrial;
+    for (int it = 0; rmax > tol_abs && it < cs.refine_max; ++it) {
+        if (w.t.wid == 0) tri_solve<T, NSLOT>(w);               // z = M^-1 r; the serial chain runs on one warp
+        team::sync(w.t);
+        // rz = r'z (r recomputed from gam in fp64), beta, d = Z z + beta d
+        double part = 0.0;
+        for (int v = lane; v < w.n; v += w.t.nt) {
+            const int p = v / 3;
+            if (p < w.ns)
+                part += slot_residual(w.face[3 * p], w.face[3 * p + 1], w.face[3 * p + 2], v - 3 * p, w.gam + 3 * w.fo[p], cs.mu) *
+                        (double)w.vec[v];
+        }
+        const double rz_new = team::reduce_sum(w.t, part);
+        const double beta = it == 0 ? 0.0 : rz_new / rz;
+        rz = rz_new;
+        if (!(rz > 0.0)) break;                                  // converged to rounding (or a broken factor)
+        for (int p = lane; p < w.ns; p += w.t.nt) {
+            const int sx = w.face[3 * p], sy = w.face[3 * p + 1], sz = w.face[3 * p + 2];
+            double* dp = d + 3 * w.fo[p];
+            double z0 = 0.0, z1 = 0.0, z2 = 0.0;
+            if (sz >= 0) {
+                const double w0 = (double)w.vec[3 * p], w1 = (double)w.vec[3 * p + 1], w2 = (double)w.vec[3 * p + 2];
+                if (sz == 0) { z2 = w2; z0 = sx != 0 ? sx * cs.mu * w2 : w0; z1 = sy != 0 ? sy * cs.mu * w2 : w1; }
+                else { z0 = sx == 0 ? w0 : 0.0; z1 = sy == 0 ? w1 : 0.0; }
+            }
+            if (it == 0) { dp[0] = z0; dp[1] = z1; dp[2] = z2; }
+            else { dp[0] = z0 + beta * dp[0]; dp[1] = z1 + beta * dp[1]; dp[2] = z2 + beta * dp[2]; }
+        }
+        team::sync(w.t);
+        hess_apply(cs, w, d, w.hd, false);                       // hd = H d
+        part = 0.0;
+        for (int idx = lane; idx < w.nv; idx += w.t.nt) part += d[idx] * w.hd[idx];
+        const double dHd = team::reduce_sum(w.t, part);
+        if (!(dHd > 0.0)) break;
+        const double alpha = rz / dHd;
+        for (int idx = lane; idx < w.nv; idx += w.t.nt) {
+            w.u[idx] += alpha * d[idx];
+            w.gam[idx] += alpha * w.hd[idx];
+        }
+        team::sync(w.t);
+        rmax = reduced_gradient(cs, w);
+    }
+    // the face equalities hold to rounding after the updates; make them exact again (changes u by ~1 ulp)
+    for (int p = lane; p < w.ns; p += w.t.nt) {
+        const int sx = w.face[3 * p], sy = w.face[3 * p + 1], sz = w.face[3 * p + 2];
+        double* up = w.u + 3 * w.fo[p];
+        if (sz < 0) { up[0] = up[1] = up[2] = 0.0; continue; }
+        if (sz > 0) up[2] = w.fmax[p];
+        if (sx != 0) up[0] = sx * cs.mu * up[2];
+        if (sy != 0) up[1] = sy * cs.mu * up[2];
+    }
+    team::sync(w.t);
     return rmax;
 }
 
@@ -840,7 +916,7 @@ MPCQ_DEV int reorder_feet(Work<T>& w) {
 
 // one factor-and-solve on the current faces: u = argmin on the faces (to tol), gam = Hu+g
 template <class T, int NCAP, int NW>
-MPCQ_DEV bool face_solve(const Consts& cs, Work<T>& w, double tol_abs, double& rmax) {
+MPCQ_DEV bool face_solve(const Consts& cs, Work<T>& w, double tol_abs, double& rmax, bool use_cg) {
     constexpr int NFS = (NCAP / 3 + 31) / 32;
     int k_start = 0;
     if (w.t.wid == 0) k_start = reorder_feet<T, NFS>(w);        // one warp permutes the stance list ...
@@ -850,7 +926,7 @@ MPCQ_DEV bool face_solve(const Consts& cs, Work<T>& w, double tol_abs, double& r
 #endif
     const bool cnz = build_slots(cs, w);
     const bool ok = k_start < w.n ? chol_factor<T, NCAP, NW>(cs, w, k_start) : true;
-    rmax = refine<T, NCAP / 32>(cs, w, tol_abs, !cnz);
+    rmax = refine<T, NCAP / 32>(cs, w, tol_abs, !cnz, use_cg);
     return ok;
 }
 
@@ -894,15 +970,13 @@ MPCQ_DEV double objective(const Consts& cs, Work<T>& w) {
     return 0.5 * team::reduce_sum(w.t, s);
 }
 
-// objective of an arbitrary vector (temporarily viewed as w.u); clobbers w.gam
+// objective of an arbitrary vector v: 1/2 v'(Hv + g + g); uses hd as scratch
 template <class T>
-MPCQ_DEV double objective_of(const Consts& cs, Work<T>& w, double* v) {
-    double* keep = w.u;
-    w.u = v;
-    hess_apply(cs, w);
-    const double phi = objective(cs, w);
-    w.u = keep;
-    return phi;
+MPCQ_DEV double objective_of(const Consts& cs, Work<T>& w, const double* v) {
+    hess_apply(cs, w, v, w.hd, true);
+    double s = 0.0;
+    for (int idx = w.t.tid; idx < w.nv; idx += w.t.nt) s += v[idx] * (w.hd[idx] + w.g[idx]);
+    return 0.5 * team::reduce_sum(w.t, s);
 }
 
 MPCQ_DEV void row_slacks(const double* f, double mu, double fm, double (&s)[6]) {
@@ -1061,16 +1135,18 @@ MPCQ_DEV void solve_env(const Consts& cs, const IO<T>& io, int b, char* smem, T*
         double gsc = 0.0;
         for (int idx = lane; idx < w.nv; idx += w.t.nt) gsc = dmax(gsc, dabs(w.g[idx]));
         gsc = 1.0 + team::reduce_max(w.t, gsc);
-        const double tol_loose = cs.tol_r_loose * gsc, tol_tight = cs.tol_r_tight * gsc;
+        // the weakest curvature of H is 2 min(R): a reduced gradient r can hide a force error of r / (2 min R)
+        const double tol_tight = dmin(cs.tol_r_tight * gsc, cs.tol_r_abs);
+        const double tol_loose = dmax(cs.tol_r_loose * gsc, tol_tight);
         bool numeric_ok = (gsc == gsc) && (gsc < 1e300);
         bool done = false;
         // ---- primal-dual active-set rounds
         for (int round = 0; round <= cs.pdas_cap && numeric_ok && !done; ++round) {
-            numeric_ok = face_solve<T, NCAP, NW>(cs, w, tol_loose, rmax) && numeric_ok;
+            numeric_ok = face_solve<T, NCAP, NW>(cs, w, tol_loose, rmax, false) && numeric_ok;
             ++nfac;
             FaceCheck fc = pdas_update(cs, w, false);
             if (fc.n_primal == 0 && fc.n_dual == 0) {
-                rmax = refine<T, NSLOT>(cs, w, tol_tight, false);   // tighten on the same factor, re-test
+                rmax = refine<T, NSLOT>(cs, w, tol_tight, false, true);   // tighten on the same factor (CG), re-test
                 fc = pdas_update(cs, w, false);
                 if (fc.n_primal == 0 && fc.n_dual == 0) { done = true; break; }
             }
@@ -1088,7 +1164,7 @@ MPCQ_DEV void solve_env(const Consts& cs, const IO<T>& io, int b, char* smem, T*
             clamp_into(cs, w, w.u, w.ucur, w.face);
             double phi_cur = objective_of(cs, w, w.ucur);
             for (nas = 1; nas <= cs.as_cap; ++nas) {
-                numeric_ok = face_solve<T, NCAP, NW>(cs, w, tol_tight, rmax) && numeric_ok;
+                numeric_ok = face_solve<T, NCAP, NW>(cs, w, tol_tight, rmax, true) && numeric_ok;
                 ++nfac;
                 if (!numeric_ok) break;
                 double alpha;

@@ -48,7 +48,7 @@ inline bool consts_from_config(const mpcq_config& c, Consts& k, std::string& err
     k.horizon = c.horizon;
     k.pdas_cap = c.max_pdas_rounds > 0 ? c.max_pdas_rounds : 8;
     k.as_cap = c.max_as_iter > 0 ? c.max_as_iter : 12 * c.horizon + 30;
-    k.refine_max = c.max_refine > 0 ? c.max_refine : 8;
+    k.refine_max = c.max_refine > 0 ? c.max_refine : 20;
     k.dt = c.dt; k.mu = c.mu; k.fz_max = c.fz_max;
     k.inv_mass = (double)(float)(1.0 / c.mass);            // Bc[9:12] = I/m is stored in float32 (mpc.py:190)
     for (int i = 0; i < 9; ++i) k.inertia[i] = c.inertia[i];
@@ -60,6 +60,9 @@ inline bool consts_from_config(const mpcq_config& c, Consts& k, std::string& err
     k.tol_r_loose = c.tol_residual_loose > 0 ? c.tol_residual_loose : (f64 ? 1e-9 : 1e-6);
     if (k.tol_r_loose < k.tol_r_tight) k.tol_r_loose = k.tol_r_tight;
     k.tol_active = c.tol_active > 0 ? c.tol_active : 1e-6;
+    double rmin = c.r_diag[0];
+    for (int i = 1; i < 12; ++i) rmin = c.r_diag[i] < rmin ? c.r_diag[i] : rmin;
+    k.tol_r_abs = 2.0 * rmin * (f64 ? 2e-6 : 2e-4);            // forces to 2e-4 N (f32 mode) / 2e-6 N (f64 mode) in the weakest direction
     double det = c.inertia[0] * (c.inertia[4] * c.inertia[8] - c.inertia[5] * c.inertia[7]) -
                  c.inertia[1] * (c.inertia[3] * c.inertia[8] - c.inertia[5] * c.inertia[6]) +
                  c.inertia[2] * (c.inertia[3] * c.inertia[7] - c.inertia[4] * c.inertia[6]);
