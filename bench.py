@@ -183,12 +183,17 @@ def run_ours(a):
     eng = ctrl.engine
     ctrl.update_robot_state(BatchedRobotData(st["quat_base"], st["pos_base"], st["ang_vel_base"], st["lin_vel_base"],
                                              st["pos_base_feet"], st["R_base"]))
+    # desired xy = current xy: preset the integrators so that this (non-first) tick lands there, then let the
+    # fused kernel (mpcq_assemble) do state assembly + command integration + reference trajectory on the device
+    vcmd = torch.as_tensor(st["vel_cmd_body"], device=dev)
+    vel = torch.einsum("bij,bj->bi", torch.as_tensor(st["R_base"], device=dev), vcmd)
+    pos32 = torch.as_tensor(st["pos_base"], device=dev).float().double()
+    ctrl._xy_des.copy_(pos32[:, 0:2] - ctrl.dt_control * vel[:, 0:2])
     ctrl.is_first_run = False
-    ctrl.xpos_base_desired = ctrl.current_state[:, 3].double()
-    ctrl.ypos_base_desired = ctrl.current_state[:, 4].double()
-    ctrl.yaw_desired = ctrl.yaw.clone()
-    vel = torch.einsum("bij,bj->bi", ctrl.R_base, torch.as_tensor(st["vel_cmd_body"], device=dev))
-    xref = ctrl.generate_reference_trajectory(vel, torch.as_tensor(st["yaw_rate_cmd"], device=dev))
+    eng.assemble(ctrl._quat, ctrl._pos, ctrl._omega, ctrl._vel, vcmd.contiguous(),
+                 torch.as_tensor(st["yaw_rate_cmd"], device=dev).contiguous(), ctrl._xy_des, ctrl.yaw_desired, ctrl._rp_init,
+                 False, True, ctrl.current_state, ctrl.yaw, ctrl.ref_traj, R_base=ctrl._R_given)
+    xref = ctrl.ref_traj
     x0 = ctrl.current_state.to(tdt).reshape(S, B, 13).contiguous()
     yaw = ctrl.yaw.to(tdt).reshape(S, B).contiguous()
     feet = ctrl.pos_base_feet.to(tdt).reshape(S, B, 12).contiguous()
@@ -282,6 +287,28 @@ def run_ours(a):
     e2e_value = world * B * a.steps / float(te.item())
     assert np.array_equal(r["forces"], hout["forces"])
 
+    # ---- the batched controller API on device tensors: update_robot_state + update_mpc_if_needed (fused assembly kernel +
+    # solve), i.e. the call sequence of scripts/isaacgym_a1.py:141-143 for the whole batch
+    c2 = BatchedModelPredictiveController(with_horizon(H), robot, B, device=dev, dtype=tdt)
+    dv = lambda key, k: torch.as_tensor(st[key][k * B:(k + 1) * B], device=dev)
+    rds = [BatchedRobotData(dv("quat_base", k), dv("pos_base", k), dv("ang_vel_base", k), dv("lin_vel_base", k),
+                            dv("pos_base_feet", k), dv("R_base", k)) for k in range(min(S, 8))]
+    cmds = [(dv("vel_cmd_body", k), dv("yaw_rate_cmd", k)) for k in range(min(S, 8))]
+    def ctrl_step(s):
+        k = s % len(rds)
+        c2.update_robot_state(rds[k])
+        return c2.update_mpc_if_needed(0, cmds[k][0], cmds[k][1], gait[k])
+    for s in range(a.warmup):
+        ctrl_step(s)
+    barrier()
+    c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    c0.record()
+    for s in range(a.steps):
+        ctrl_step(a.warmup + s)
+    c1.record()
+    barrier()
+    ctrl_ms = c0.elapsed_time(c1) / a.steps
+
     # ---- roofline of the dominant kernel
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(peaks_path):
@@ -313,6 +340,9 @@ def run_ours(a):
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "api": "mpcq_solve_host (C ABI, pinned host buffers in and out, 4 chunks pipelined on 4 streams)",
                     "ms_per_step": 1e3 * float(te.item()) / a.steps, "launches_per_step": e2e_launches},
+            "controller_api": {"value": world * B / (ctrl_ms * 1e-3), "unit": UNIT, "ms_per_step": ctrl_ms,
+                               "api": "BatchedModelPredictiveController.update_robot_state + update_mpc_if_needed on device tensors "
+                                      "(mpcq_assemble + mpcq_solve: 3 kernel launches)"},
             "gpu_launches": launches_per_step * a.steps,
             "kernel_ms": {"per_class_mean": [float(v) for v in kmean], "dominant_class": dom,
                           "share_of_step": float(kmean[dom] / (total_ms / a.steps))},

@@ -77,6 +77,8 @@ typedef struct mpcq_config {
     double tol_residual;            /* reduced-gradient tolerance relative to 1+|g|_inf; default 1e-9 (f32) / 1e-12 (f64) */
     double tol_active;              /* slack tolerance of the reported activity; default 1e-6 */
     double tol_residual_loose;      /* reduced-gradient tolerance of intermediate active-set rounds; default 1e-6 (f32) / 1e-9 (f64) */
+    double dt_control;              /* LinearMpcConfig.dt_control (used by mpcq_assemble only) */
+    double com_height_des;          /* RobotConfig.base_height_des (used by mpcq_assemble only) */
 } mpcq_config;
 
 typedef struct mpcq_handle mpcq_handle;
@@ -112,6 +114,25 @@ int mpcq_solve(mpcq_handle* h, int32_t B,
                const void* x0, const void* yaw, const void* r_feet, const float* gait, const void* x_ref,
                void* f_out, void* u_full, int32_t* iters, double* resid, int32_t* status, uint8_t* active,
                void* stream);
+
+/*
+ * replaces, for B robots and in ONE elementwise kernel, everything the reference does between the simulator
+ * state and _solve_mpc: ModelPredictiveController.update_robot_state (mpc.py:55-79, quat -> ZYX angles,
+ * kinematics.py:40-49), the preamble of update_mpc_if_needed (:83-93, command rotation and the dt_control
+ * integrators) and generate_reference_trajectory (:110-170, clamp, roll/pitch compensation, X_ref fill), with the
+ * reference's float32 storage / float64 scalar arithmetic.  All inputs and the controller state are float64
+ * device arrays (RobotData holds float64):
+ *   quat [B,4] (w,x,y,z), pos [B,3], omega [B,3] (world), vel [B,3] (world), R_base [B,9] or NULL (from quat),
+ *   v_des_body [B,3], yaw_rate_des [B]
+ *   in/out state: xy_des [B,2], yaw_des [B], rp_init [B,2] (roll_init, pitch_init)
+ *   first_run != 0: desired pose initialised as mpc.py:84-88;  do_mpc != 0: this tick recomputes X_ref (mpc.py:95-96)
+ * outputs (`real`): x0 [B,13] and yaw [B] always, x_ref [B,13H] when do_mpc != 0 - exactly the arrays mpcq_solve takes.
+ */
+int mpcq_assemble(mpcq_handle* h, int32_t B,
+                  const double* quat, const double* pos, const double* omega, const double* vel, const double* R_base,
+                  const double* v_des_body, const double* yaw_rate_des,
+                  double* xy_des, double* yaw_des, double* rp_init, int32_t first_run, int32_t do_mpc,
+                  void* x0, void* yaw, void* x_ref, void* stream);
 
 /*
  * Same call with HOST buffers (what a CPU-side simulator loop such as scripts/isaacgym_a1.py:119-164

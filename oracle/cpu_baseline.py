@@ -43,7 +43,9 @@ def solve_chunk(args):
         m.is_first_run = False
         m.xpos_base_desired = float(m.current_state[3])
         m.ypos_base_desired = float(m.current_state[4])
-        m.yaw_desired = m.yaw
+        # a regular (non-first) control tick whose integrated desired xy equals the current xy;
+        # yaw_desired follows mpc.py:92
+        m.yaw_desired = m.yaw + m.dt_control * float(st["yaw_rate_cmd"][b])
         xr = m.reference_trajectory(rd.R_base @ st["vel_cmd_body"][b], float(st["yaw_rate_cmd"][b]))
         H, g, C, lb, ub = m.build_qp(xr, tabs[b])
         t1 = time.perf_counter()

@@ -28,6 +28,7 @@ class MpcqConfig(C.Structure):
         ("reserved1", C.c_int32),
         ("tol_primal", C.c_double), ("tol_dual", C.c_double), ("tol_residual", C.c_double),
         ("tol_active", C.c_double), ("tol_residual_loose", C.c_double),
+        ("dt_control", C.c_double), ("com_height_des", C.c_double),
     ]
 
 
@@ -42,6 +43,8 @@ def make_config(consts: dict, dtype: int = MPCQ_F32, device: int = 0, **knobs) -
     cfg.fz_max = float(consts["fz_max"])
     cfg.mass = float(consts["mass"])
     cfg.gravity = float(consts["gravity"])
+    cfg.dt_control = float(consts.get("dt_control", 0.001))
+    cfg.com_height_des = float(consts.get("com_height_des", 0.0))
     cfg.inertia[:] = [float(v) for v in np.asarray(consts["inertia"], dtype=np.float32).reshape(9)]
     cfg.q_diag[:] = [float(v) for v in consts["q_diag"]]
     cfg.r_diag[:] = [float(v) for v in consts["r_diag"]]
@@ -69,6 +72,8 @@ def bind(lib: C.CDLL) -> C.CDLL:
     lib.mpcq_solve_host.restype = C.c_int
     lib.mpcq_build_qp.argtypes = [C.c_void_p, C.c_int32] + [C.c_void_p] * 5 + [C.c_void_p] * 3 + [C.c_void_p]
     lib.mpcq_build_qp.restype = C.c_int
+    lib.mpcq_assemble.argtypes = [C.c_void_p, C.c_int32] + [C.c_void_p] * 10 + [C.c_int32, C.c_int32] + [C.c_void_p] * 4
+    lib.mpcq_assemble.restype = C.c_int
     lib.mpcq_last_launch_count.argtypes = [C.c_void_p]
     lib.mpcq_last_launch_count.restype = C.c_int
     lib.mpcq_set_profiling.argtypes = [C.c_void_p, C.c_int32]
@@ -79,7 +84,7 @@ def bind(lib: C.CDLL) -> C.CDLL:
 
 
 EXPORTS = ("mpcq_version", "mpcq_create", "mpcq_destroy", "mpcq_last_error", "mpcq_solve",
-           "mpcq_solve_host", "mpcq_build_qp", "mpcq_last_launch_count", "mpcq_set_profiling",
+           "mpcq_solve_host", "mpcq_build_qp", "mpcq_assemble", "mpcq_last_launch_count", "mpcq_set_profiling",
            "mpcq_last_kernel_ms")
 
 _lib = None

@@ -57,7 +57,7 @@ def quat_to_zyx(q: torch.Tensor) -> torch.Tensor:
 
 class BatchedModelPredictiveController:
     def __init__(self, mpc_config, robot_config, num_envs: int, device="cuda:0", dtype=torch.float32, engine=None,
-                 **solver_knobs):
+                 fused=None, **solver_knobs):
         """`engine` is for dependency injection in tests (an object with MpcqEngine.solve's signature);
         by default the CUDA engine is created and a missing GPU / library raises."""
         c = extract_mpc_constants(mpc_config, robot_config)
@@ -80,16 +80,23 @@ class BatchedModelPredictiveController:
         f64 = dict(dtype=torch.float64, device=dev)
         self.is_initialized = False
         self.is_first_run = True
-        self.current_state = torch.zeros((B, 13), dtype=torch.float32, device=dev)
-        self.yaw = torch.zeros(B, **f64)
-        self.roll_init = torch.zeros(B, **f64)
-        self.pitch_init = torch.zeros(B, **f64)
-        self.xpos_base_desired = torch.zeros(B, **f64)
-        self.ypos_base_desired = torch.zeros(B, **f64)
+        # the fused device path (mpcq_assemble) is used whenever the engine offers it; the torch statement of the same
+        # arithmetic below serves engines without it (the test double) and as the readable specification
+        self._fused = hasattr(self.engine, "assemble") if fused is None else bool(fused)
+        self.current_state = torch.zeros((B, 13), dtype=dtype if self._fused else torch.float32, device=dev)
+        self.yaw = torch.zeros(B, dtype=dtype if self._fused else torch.float64, device=dev)
+        self._xy_des = torch.zeros((B, 2), **f64)
+        self._rp_init = torch.zeros((B, 2), **f64)             # roll_init, pitch_init
         self.yaw_desired = torch.zeros(B, **f64)
         self.contact_forces = torch.zeros((B, 12), dtype=dtype, device=dev)
-        self.ref_traj = torch.zeros((B, 13 * self.horizon), dtype=torch.float32, device=dev)
+        self.ref_traj = torch.zeros((B, 13 * self.horizon), dtype=dtype if self._fused else torch.float32, device=dev)
         self.last_result = None
+
+    # reference attribute names (mpc.py:85-92,143-150) as views of the packed state
+    xpos_base_desired = property(lambda self: self._xy_des[:, 0], lambda self, v: self._xy_des[:, 0].copy_(torch.as_tensor(v)))
+    ypos_base_desired = property(lambda self: self._xy_des[:, 1], lambda self, v: self._xy_des[:, 1].copy_(torch.as_tensor(v)))
+    roll_init = property(lambda self: self._rp_init[:, 0], lambda self, v: self._rp_init[:, 0].copy_(torch.as_tensor(v)))
+    pitch_init = property(lambda self: self._rp_init[:, 1], lambda self, v: self._rp_init[:, 1].copy_(torch.as_tensor(v)))
 
     # ---------------------------------------------------------------------------------------
     def _t(self, a, shape):
@@ -100,17 +107,22 @@ class BatchedModelPredictiveController:
     def update_robot_state(self, robot_data) -> None:
         """mpc.py:55-79: current_state = [rpy, pos, omega, vel, -g] rounded to float32; yaw kept in float64."""
         B = self.num_envs
-        quat = self._t(robot_data.quat_base, (B, 4))
-        rpy = quat_to_zyx(quat)
-        st = torch.cat([rpy, self._t(robot_data.pos_base, (B, 3)), self._t(robot_data.ang_vel_base, (B, 3)),
-                        self._t(robot_data.lin_vel_base, (B, 3)),
+        self._quat = self._t(robot_data.quat_base, (B, 4)).contiguous()
+        self._pos = self._t(robot_data.pos_base, (B, 3)).contiguous()
+        self._omega = self._t(robot_data.ang_vel_base, (B, 3)).contiguous()
+        self._vel = self._t(robot_data.lin_vel_base, (B, 3)).contiguous()
+        self.pos_base_feet = self._t(robot_data.pos_base_feet, (B, 12))
+        R = getattr(robot_data, "R_base", None)
+        self._R_given = None if R is None else self._t(R, (B, 3, 3)).contiguous()
+        self.is_initialized = True
+        if self._fused:
+            return                                              # assembled on the device inside update_mpc_if_needed
+        rpy = quat_to_zyx(self._quat)
+        st = torch.cat([rpy, self._pos, self._omega, self._vel,
                         torch.full((B, 1), -self.gravity, dtype=torch.float64, device=self.device)], dim=1)
         self.current_state = st.to(torch.float32)
         self.yaw = rpy[:, 2].clone()
-        self.pos_base_feet = self._t(robot_data.pos_base_feet, (B, 12))
-        R = getattr(robot_data, "R_base", None)
-        self.R_base = quat_to_matrix(quat) if R is None else self._t(R, (B, 3, 3))
-        self.is_initialized = True
+        self.R_base = quat_to_matrix(self._quat) if self._R_given is None else self._R_given
 
     def update_mpc_if_needed(self, iter_counter: int, base_vel_base_des, yaw_turn_rate_des, gait_table,
                              solver: str = "drake", debug: bool = False, iter_debug=None):
@@ -123,42 +135,50 @@ class BatchedModelPredictiveController:
         B = self.num_envs
         v_body = self._t(base_vel_base_des, (-1, 3)).expand(B, 3)
         yaw_rate = self._t(yaw_turn_rate_des, (-1,)).expand(B)
+        do_mpc = iter_counter % self.iterations_between_mpc == 0
+        if self._fused:
+            self.engine.assemble(self._quat, self._pos, self._omega, self._vel, v_body.contiguous(), yaw_rate.contiguous(),
+                                 self._xy_des, self.yaw_desired, self._rp_init, self.is_first_run, do_mpc,
+                                 self.current_state, self.yaw, self.ref_traj, R_base=self._R_given)
+            self.is_first_run = False
+            if do_mpc:
+                self.contact_forces = self._solve_mpc(self.ref_traj, gait_table)
+            return self.contact_forces
         vel_des = torch.einsum("bij,bj->bi", self.R_base, v_body)
         if self.is_first_run:
-            self.xpos_base_desired = torch.zeros_like(self.xpos_base_desired)
-            self.ypos_base_desired = torch.zeros_like(self.ypos_base_desired)
+            self._xy_des.zero_()
             self.yaw_desired = self.yaw.clone()
             self.is_first_run = False
         else:
-            self.xpos_base_desired = self.xpos_base_desired + self.dt_control * vel_des[:, 0]
-            self.ypos_base_desired = self.ypos_base_desired + self.dt_control * vel_des[:, 1]
+            self._xy_des[:, 0] += self.dt_control * vel_des[:, 0]
+            self._xy_des[:, 1] += self.dt_control * vel_des[:, 1]
             self.yaw_desired = self.yaw + self.dt_control * yaw_rate
-        if iter_counter % self.iterations_between_mpc == 0:
+        if do_mpc:
             self.ref_traj = self.generate_reference_trajectory(vel_des, yaw_rate)
             self.contact_forces = self._solve_mpc(self.ref_traj, gait_table)
         return self.contact_forces
 
     def generate_reference_trajectory(self, vel_des: torch.Tensor, yaw_rate: torch.Tensor) -> torch.Tensor:
         """mpc.py:110-170 with its float32 storage / float64 scalar arithmetic reproduced."""
-        x = self.current_state.to(torch.float64)            # float32 values
+        x = self.current_state.to(torch.float64)            # float32 values (torch path only)
         H, n, B = self.horizon, 13, self.num_envs
         lim = 0.1
-        xd, yd = self.xpos_base_desired, self.ypos_base_desired
+        xd, yd = self._xy_des[:, 0].clone(), self._xy_des[:, 1].clone()
         xd = torch.where(xd - x[:, 3] > lim, x[:, 3] + lim, xd)
         xd = torch.where(x[:, 3] - xd > lim, x[:, 3] - lim, xd)
         yd = torch.where(yd - x[:, 4] > lim, x[:, 4] + lim, yd)
         yd = torch.where(x[:, 4] - yd > lim, x[:, 4] - lim, yd)
-        self.xpos_base_desired, self.ypos_base_desired = xd, yd
+        self._xy_des[:, 0], self._xy_des[:, 1] = xd, yd
         safe = lambda v: torch.where(v == 0, torch.ones_like(v), v)
-        self.pitch_init = torch.where(x[:, 9].abs() > 0.2, self.pitch_init + self.dt * (0.0 - x[:, 1]) / safe(x[:, 9]),
-                                      self.pitch_init)
-        self.roll_init = torch.where(x[:, 10].abs() > 0.1, self.roll_init + self.dt * (0.0 - x[:, 0]) / safe(x[:, 10]),
-                                     self.roll_init)
-        self.roll_init = self.roll_init.clamp(-0.25, 0.25)
-        self.pitch_init = self.pitch_init.clamp(-0.25, 0.25)
+        pitch_init = torch.where(x[:, 9].abs() > 0.2, self._rp_init[:, 1] + self.dt * (0.0 - x[:, 1]) / safe(x[:, 9]),
+                                 self._rp_init[:, 1])
+        roll_init = torch.where(x[:, 10].abs() > 0.1, self._rp_init[:, 0] + self.dt * (0.0 - x[:, 0]) / safe(x[:, 10]),
+                                self._rp_init[:, 0])
+        self._rp_init[:, 0] = roll_init.clamp(-0.25, 0.25)
+        self._rp_init[:, 1] = pitch_init.clamp(-0.25, 0.25)
         X = torch.zeros((B, H, n), dtype=torch.float32, device=self.device)
-        X[:, :, 0] = (x[:, 10] * self.roll_init).to(torch.float32)[:, None]
-        X[:, :, 1] = (x[:, 9] * self.pitch_init).to(torch.float32)[:, None]
+        X[:, :, 0] = (x[:, 10] * self._rp_init[:, 0]).to(torch.float32)[:, None]
+        X[:, :, 1] = (x[:, 9] * self._rp_init[:, 1]).to(torch.float32)[:, None]
         X[:, :, 5] = self.com_height_des
         X[:, :, 8] = yaw_rate.to(torch.float32)[:, None]
         X[:, :, 9] = vel_des[:, 0].to(torch.float32)[:, None]

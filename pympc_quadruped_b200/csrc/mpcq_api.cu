@@ -75,6 +75,85 @@ mpcq_build_qp_kernel(const __grid_constant__ Consts cs, const __grid_constant__ 
     }
 }
 
+// state assembly + reference trajectory, one thread per environment (HBM-stream bound: ~34 doubles in, 13 + 13H reals out)
+struct AssembleArgs {
+    const double *quat, *pos, *omega, *vel, *R, *vdes, *yawrate;
+    double *xy_des, *yaw_des, *rp_init;
+    int first_run, do_mpc, B, H;
+    double dt_control, dt, com_height, gravity;
+};
+
+template <class T>
+__global__ void __launch_bounds__(128)
+mpcq_assemble_kernel(const __grid_constant__ AssembleArgs a, T* x0, T* yaw_out, T* x_ref) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= a.B) return;
+    const double qw = a.quat[4 * b], qx = a.quat[4 * b + 1], qy = a.quat[4 * b + 2], qz = a.quat[4 * b + 3];
+    // quat2ZYXangle (utils/kinematics.py:40-49), float64
+    const double roll = atan2(2 * (qw * qx + qy * qz), 1 - 2 * (qx * qx + qy * qy));
+    const double pitch = asin(2 * (qw * qy - qz * qx));
+    const double yaw = atan2(2 * (qw * qz + qx * qy), 1 - 2 * (qy * qy + qz * qz));
+    // current_state is a float32 array (mpc.py:57,70-76)
+    float st[13];
+    st[0] = (float)roll; st[1] = (float)pitch; st[2] = (float)yaw;
+    for (int i = 0; i < 3; ++i) {
+        st[3 + i] = (float)a.pos[3 * b + i];
+        st[6 + i] = (float)a.omega[3 * b + i];
+        st[9 + i] = (float)a.vel[3 * b + i];
+    }
+    st[12] = (float)(-a.gravity);
+    for (int i = 0; i < 13; ++i) x0[(size_t)b * 13 + i] = (T)st[i];
+    yaw_out[b] = (T)yaw;
+    // vel_base_des = R_base @ base_vel_base_des (mpc.py:83)
+    double R[9];
+    if (a.R) {
+        for (int i = 0; i < 9; ++i) R[i] = a.R[9 * b + i];
+    } else {                                                    // quat2matrix (utils/kinematics.py:51-71)
+        R[0] = qw * qw + qx * qx - qy * qy - qz * qz; R[1] = 2 * (qx * qy - qw * qz); R[2] = 2 * (qw * qy + qx * qz);
+        R[3] = 2 * (qw * qz + qx * qy); R[4] = qw * qw - qx * qx + qy * qy - qz * qz; R[5] = 2 * (qy * qz - qw * qx);
+        R[6] = 2 * (qx * qz - qw * qy); R[7] = 2 * (qw * qx + qy * qz); R[8] = qw * qw - qx * qx - qy * qy + qz * qz;
+    }
+    const double vb0 = a.vdes[3 * b], vb1 = a.vdes[3 * b + 1], vb2 = a.vdes[3 * b + 2];
+    const double vx = (R[0] * vb0 + R[1] * vb1) + R[2] * vb2, vy = (R[3] * vb0 + R[4] * vb1) + R[5] * vb2;
+    const double rate = a.yawrate[b];
+    double xd, yd, yawd;
+    if (a.first_run) { xd = 0.0; yd = 0.0; yawd = yaw; }       // mpc.py:84-88
+    else {                                                      // mpc.py:89-92
+        xd = a.xy_des[2 * b] + a.dt_control * vx;
+        yd = a.xy_des[2 * b + 1] + a.dt_control * vy;
+        yawd = yaw + a.dt_control * rate;
+    }
+    if (a.do_mpc) {                                             // generate_reference_trajectory, mpc.py:110-170
+        const double x3 = st[3], x4 = st[4];
+        const double lim = 0.1;
+        if (xd - x3 > lim) xd = x3 + lim;
+        if (x3 - xd > lim) xd = x3 - lim;
+        if (yd - x4 > lim) yd = x4 + lim;
+        if (x4 - yd > lim) yd = x4 - lim;
+        double roll_init = a.rp_init[2 * b], pitch_init = a.rp_init[2 * b + 1];
+        if (fabs((double)st[9]) > 0.2) pitch_init += a.dt * (0.0 - (double)st[1]) / (double)st[9];
+        if (fabs((double)st[10]) > 0.1) roll_init += a.dt * (0.0 - (double)st[0]) / (double)st[10];
+        roll_init = fmin(fmax(roll_init, -0.25), 0.25);
+        pitch_init = fmin(fmax(pitch_init, -0.25), 0.25);
+        a.rp_init[2 * b] = roll_init; a.rp_init[2 * b + 1] = pitch_init;
+        const float rc = (float)((double)st[10] * roll_init), pc = (float)((double)st[9] * pitch_init);
+        float ry = (float)yawd, rx = (float)xd, rY = (float)yd;
+        T* X = x_ref + (size_t)b * 13 * a.H;
+        for (int i = 0; i < a.H; ++i) {
+            if (i > 0) {                                        // float32 storage, float64 increments (mpc.py:163-166)
+                ry = (float)((double)ry + a.dt * rate);
+                rx = (float)((double)rx + a.dt * vx);
+                rY = (float)((double)rY + a.dt * vy);
+            }
+            T* r = X + 13 * i;
+            r[0] = (T)rc; r[1] = (T)pc; r[2] = (T)ry; r[3] = (T)rx; r[4] = (T)rY; r[5] = (T)(float)a.com_height;
+            r[6] = (T)0; r[7] = (T)0; r[8] = (T)(float)rate; r[9] = (T)(float)vx; r[10] = (T)(float)vy; r[11] = (T)0;
+            r[12] = (T)(float)(-a.gravity);
+        }
+    }
+    a.xy_des[2 * b] = xd; a.xy_des[2 * b + 1] = yd; a.yaw_des[b] = yawd;
+}
+
 }  // namespace
 
 struct mpcq_handle {
@@ -323,6 +402,27 @@ int mpcq_build_qp(mpcq_handle* h, int32_t B, const void* x0, const void* yaw, co
     }
     h->last_launches = 1;
     return cuda_ok(h, cudaGetLastError(), "mpcq_build_qp launch") ? MPCQ_OK : MPCQ_ERR_CUDA;
+}
+
+int mpcq_assemble(mpcq_handle* h, int32_t B, const double* quat, const double* pos, const double* omega, const double* vel,
+                  const double* R_base, const double* v_des_body, const double* yaw_rate_des, double* xy_des, double* yaw_des,
+                  double* rp_init, int32_t first_run, int32_t do_mpc, void* x0, void* yaw, void* x_ref, void* stream) {
+    if (!h) return MPCQ_ERR_INVALID;
+    if (B < 0 || (B > 0 && (!quat || !pos || !omega || !vel || !v_des_body || !yaw_rate_des || !xy_des || !yaw_des || !rp_init ||
+                            !x0 || !yaw || (do_mpc && !x_ref)))) { h->err = "null input/output pointer"; return MPCQ_ERR_INVALID; }
+    h->last_launches = 0;
+    if (B == 0) return MPCQ_OK;
+    DeviceGuard guard(h->cfg.device);
+    AssembleArgs a{quat, pos, omega, vel, R_base, v_des_body, yaw_rate_des, xy_des, yaw_des, rp_init, first_run, do_mpc, B,
+                   h->cs.horizon, h->cfg.dt_control, h->cfg.dt, h->cfg.com_height_des, h->cfg.gravity};
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int grid = (B + 127) / 128;
+    if (h->cfg.dtype == MPCQ_F64)
+        mpcq_assemble_kernel<double><<<grid, 128, 0, st>>>(a, static_cast<double*>(x0), static_cast<double*>(yaw), static_cast<double*>(x_ref));
+    else
+        mpcq_assemble_kernel<float><<<grid, 128, 0, st>>>(a, static_cast<float*>(x0), static_cast<float*>(yaw), static_cast<float*>(x_ref));
+    h->last_launches = 1;
+    return cuda_ok(h, cudaGetLastError(), "mpcq_assemble launch") ? MPCQ_OK : MPCQ_ERR_CUDA;
 }
 
 int mpcq_solve_host(mpcq_handle* h, int32_t B, const void* x0, const void* yaw, const void* r_feet, const float* gait,

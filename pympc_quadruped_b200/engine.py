@@ -157,6 +157,31 @@ class MpcqEngine:
     def last_launch_count(self) -> int:
         return int(self.lib.mpcq_last_launch_count(self._h))
 
+    def assemble(self, quat, pos, omega, vel, v_des_body, yaw_rate_des, xy_des, yaw_des, rp_init, first_run, do_mpc,
+                 x0, yaw, x_ref, R_base=None):
+        """Fused state assembly + command integration + reference trajectory (`mpcq_assemble`): float64 device
+        tensors in, controller state updated in place, (x0, yaw, x_ref) written in the engine's dtype."""
+        B, H = quat.shape[0], self.horizon
+        f64 = torch.float64
+        quat = self._check("quat", quat, (B, 4), f64)
+        pos = self._check("pos", pos, (B, 3), f64)
+        omega = self._check("omega", omega, (B, 3), f64)
+        vel = self._check("vel", vel, (B, 3), f64)
+        v_des_body = self._check("v_des_body", v_des_body, (B, 3), f64)
+        yaw_rate_des = self._check("yaw_rate_des", yaw_rate_des, (B,), f64)
+        if R_base is not None:
+            R_base = self._check("R_base", R_base.reshape(B, 9), (B, 9), f64)
+        for name, t, shape, dt in (("xy_des", xy_des, (B, 2), f64), ("yaw_des", yaw_des, (B,), f64), ("rp_init", rp_init, (B, 2), f64),
+                                   ("x0", x0, (B, 13), self.dtype), ("yaw", yaw, (B,), self.dtype),
+                                   ("x_ref", x_ref, (B, 13 * H), self.dtype)):
+            if self._check(name, t, shape, dt) is not t:
+                raise ValueError(f"{name} must be contiguous (it is written in place)")
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        rc = self.lib.mpcq_assemble(self._h, B, _ptr(quat), _ptr(pos), _ptr(omega), _ptr(vel), _ptr(R_base), _ptr(v_des_body),
+                                    _ptr(yaw_rate_des), _ptr(xy_des), _ptr(yaw_des), _ptr(rp_init), int(bool(first_run)),
+                                    int(bool(do_mpc)), _ptr(x0), _ptr(yaw), _ptr(x_ref), C.c_void_p(stream))
+        self._err(rc, "mpcq_assemble")
+
     def set_profiling(self, enable: bool) -> None:
         self._err(self.lib.mpcq_set_profiling(self._h, int(bool(enable))), "mpcq_set_profiling")
 

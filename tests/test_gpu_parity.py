@@ -214,6 +214,25 @@ def test_edge_cases_empty_batch_all_swing_and_errors():
         MpcqEngine(with_horizon(40), A1Config)
 
 
+def test_non_finite_inputs_are_flagged_not_propagated():
+    """A robot with NaN / inf state must come back flagged MPCQ_ST_NUMERIC (never VERIFIED) without disturbing its neighbours."""
+    batch = make_batch(A1Config, 10, 16, "mixed", (Gait.TROTTING10,), 71, solve=False)
+    eng = _engine(batch, A1Config, torch.float32)
+    x0, feet, gait, xref, yaw = _to_dev(batch, torch.float32)
+    good = eng.solve(x0, feet, gait, xref, yaw=yaw).u.clone()
+    x0b, feetb, xrefb = x0.clone(), feet.clone(), xref.clone()
+    x0b[3, 9] = float("nan")
+    feetb[7, 2] = float("inf")
+    xrefb[11, 5] = float("nan")
+    res = eng.solve(x0b, feetb, gait, xrefb, yaw=yaw)
+    st = res.status.cpu().numpy()
+    for b in (3, 7, 11):
+        assert st[b] & _capi.ST_NUMERIC and not (st[b] & _capi.ST_VERIFIED), (b, st[b])
+    keep = [b for b in range(16) if b not in (3, 7, 11)]
+    assert np.all(st[keep] & _capi.ST_VERIFIED)
+    assert torch.equal(res.u[keep], good[keep])
+
+
 def test_batch_permutation_and_split_invariance():
     """Environments are independent: any split / order of the batch gives bitwise-equal results
     (this is what makes the multi-GPU sharding exact)."""
@@ -227,3 +246,58 @@ def test_batch_permutation_and_split_invariance():
     lo = eng.solve(x0[:20], feet[:20], gait[:20], xref[:20], yaw=yaw[:20]).u.clone()
     hi = eng.solve(x0[20:], feet[20:], gait[20:], xref[20:], yaw=yaw[20:]).u
     assert torch.equal(torch.cat([lo, hi]), full)
+
+
+def test_fused_assembly_equals_torch_statement_and_reference_sequence():
+    """mpcq_assemble (state assembly + integrators + reference trajectory in one kernel) against the torch statement of the
+    same arithmetic on the device, over a multi-tick sequence with MPC decimation; and the B = 1 adapter against the
+    fixture recorded from the reference class."""
+    import os
+    from pympc_quadruped_b200 import with_horizon
+    from pympc_quadruped_b200.controller import BatchedModelPredictiveController, BatchedRobotData, ModelPredictiveController
+    from pympc_quadruped_b200.synth import synth_states, synth_gait_tables
+    B, H = 257, 10
+    cfg = with_horizon(H)
+    st = synth_states(B, A1Config, "mixed", seed=61)
+    for dtype in (torch.float32, torch.float64):
+        fused = BatchedModelPredictiveController(cfg, A1Config, B, dtype=dtype)
+        plain = BatchedModelPredictiveController(cfg, A1Config, B, dtype=dtype, fused=False)
+        assert fused._fused and not plain._fused
+        for tick in (0, 1, 2, 20, 21, 40):
+            s = 1.0 + 0.002 * tick
+            rd = BatchedRobotData(st["quat_base"], st["pos_base"] * s, st["ang_vel_base"], st["lin_vel_base"] * s, st["pos_base_feet"],
+                                  st["R_base"] if tick % 2 else None)
+            tabs = synth_gait_tables(B, H, (Gait.TROTTING10,), seed=tick)
+            ff, fp = None, None
+            for c in (fused, plain):
+                c.update_robot_state(rd)
+                f = c.update_mpc_if_needed(tick, st["vel_cmd_body"], st["yaw_rate_cmd"], tabs)
+                ff, fp = (f, fp) if c is fused else (ff, f)
+            assert torch.equal(fused.current_state.float(), plain.current_state.float())
+            assert torch.equal(fused.ref_traj.float(), plain.ref_traj.float()), tick
+            assert torch.allclose(fused._xy_des, plain._xy_des, rtol=0, atol=1e-15)
+            assert torch.allclose(fused.yaw_desired, plain.yaw_desired, rtol=0, atol=1e-15)
+            assert torch.allclose(fused._rp_init, plain._rp_init, rtol=0, atol=1e-15)
+            assert torch.equal(ff, fp)
+    # single-robot adapter on the real engine against the recorded reference sequence
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_h10.npz"))
+    k = "A1/seq/"
+    ctrl = ModelPredictiveController(cfg, A1Config, dtype=torch.float64)
+    gt = Gait.TROTTING10.with_horizon(10)
+
+    class RD:
+        pass
+    from oracle.mpc_oracle import quat_to_matrix
+    for tick in range(61):
+        b = (tick // 20) % 4
+        rd = RD()
+        rd.quat_base, rd.pos_base = z[k + "quat_base"][b], z[k + "pos_base"][b]
+        rd.ang_vel_base, rd.lin_vel_base = z[k + "ang_vel_base"][b], z[k + "lin_vel_base"][b]
+        rd.pos_base_feet = [z[k + "pos_base_feet"][b, i] for i in range(4)]
+        rd.R_base = quat_to_matrix(rd.quat_base)
+        gt.set_iteration(20, tick)
+        ctrl.update_robot_state(rd)
+        f = ctrl.update_mpc_if_needed(tick, z[k + "vel_cmd_body"][b], float(z[k + "yaw_rate_cmd"][b]), gt.get_gait_table())
+        ref = z[k + "forces__oracle_solver"][tick]
+        assert np.abs(f - ref).max() <= max(1e-3, 1e-4 * np.abs(ref).max()), tick
+        assert np.abs(ctrl.ref_traj - z[k + "ref_traj"][tick]).max() <= 1.2e-7 * max(1.0, np.abs(z[k + "ref_traj"][tick]).max())

@@ -30,7 +30,7 @@ def test_c_abi_library_exports_every_declared_symbol():
         assert hasattr(lib, name), name
     assert lib.mpcq_version() == 100
     # struct mirror has the C layout's size: 4 ints + 5 doubles + 34 doubles + 4 ints + 4 doubles
-    assert ctypes.sizeof(_capi.MpcqConfig) == 16 + 8 * 5 + 8 * 34 + 16 + 40
+    assert ctypes.sizeof(_capi.MpcqConfig) == 16 + 8 * 5 + 8 * 34 + 16 + 56
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="CPU-only check")
