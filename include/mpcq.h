@@ -14,8 +14,9 @@
  *     MPCQ_F64; the gait table is always float32 like the reference's (gait.py:87);
  *   - calls are asynchronous on `stream` (a cudaStream_t passed as void*) and never
  *     synchronise or throw: 0 = success, negative = error (text via mpcq_last_error);
- *   - all device workspace is allocated by mpcq_create; `*_host` calls additionally keep
- *     pinned staging buffers that grow to the largest batch seen;
+ *   - the factor workspace is allocated by mpcq_create; a launch-order buffer (5 bytes per environment) and the pinned /
+ *     device staging of the `*_host` calls grow to the largest batch seen (a growing call synchronises the device);
+ *   - one call in flight per handle: do not overlap two mpcq_solve calls of one handle on different streams;
  *   - a handle is bound to one device and is not thread-safe;
  *   - there is no CPU fallback: without a CUDA device mpcq_create fails.
  */
@@ -46,7 +47,7 @@ enum {
     MPCQ_ST_VERIFIED = 1,           /* KKT conditions (primal, dual, stationarity) hold in fp64 on the returned point */
     MPCQ_ST_FALLBACK = 2,           /* the primal active-set fallback ran (primal-dual rounds cycled) */
     MPCQ_ST_MAXITER = 4,            /* iteration cap reached: the point is feasible but not verified optimal */
-    MPCQ_ST_NUMERIC = 8,            /* non-finite input or a failed factorisation */
+    MPCQ_ST_NUMERIC = 8,            /* non-finite input, failed factorisation or unreachable residual: forces are returned as 0 */
     MPCQ_ST_NO_STANCE = 32          /* every foot-step is swing: u = 0 */
 };
 
@@ -71,7 +72,7 @@ typedef struct mpcq_config {
     int32_t max_pdas_rounds;        /* primal-dual active-set rounds before the fallback; default 8 */
     int32_t max_as_iter;            /* fallback active-set iterations; default 12*horizon + 30 */
     int32_t max_refine;             /* preconditioned-CG refinement steps per factorisation; default 20 */
-    int32_t reserved1;
+    int32_t schedule;               /* expected-work-first launch order (Q-weighted tracking error, hardest envs first); 0 = on (default), < 0 = natural order */
     double tol_primal;              /* relative feasibility tolerance of the face tests; default 1e-7 (f32) / 1e-9 (f64) */
     double tol_dual;                /* relative multiplier-sign tolerance; default 1e-7 (f32) / 1e-9 (f64) */
     double tol_residual;            /* reduced-gradient tolerance relative to 1+|g|_inf; default 1e-9 (f32) / 1e-12 (f64) */

@@ -25,7 +25,7 @@ class MpcqConfig(C.Structure):
         ("gravity", C.c_double),
         ("inertia", C.c_double * 9), ("q_diag", C.c_double * 13), ("r_diag", C.c_double * 12),
         ("max_pdas_rounds", C.c_int32), ("max_as_iter", C.c_int32), ("max_refine", C.c_int32),
-        ("reserved1", C.c_int32),
+        ("schedule", C.c_int32),
         ("tol_primal", C.c_double), ("tol_dual", C.c_double), ("tol_residual", C.c_double),
         ("tol_active", C.c_double), ("tol_residual_loose", C.c_double),
         ("dt_control", C.c_double), ("com_height_des", C.c_double),

@@ -57,6 +57,7 @@ template <class T> struct IO {
     double* resid;         // [B,2] or null
     int32_t* status;       // [B] or null
     uint8_t* active;       // [B,4H] or null
+    const int32_t* perm;   // [B] launch order (expected-work-first schedule) or null = natural order
     int B;
 };
 
@@ -169,7 +170,7 @@ template <class T, int NS> MPCQ_DEV T pick(const T (&a)[NS], int m) {
     return v;
 }
 
-MPCQ_DEV double dmax(double a, double b) { return a > b ? a : b; }
+MPCQ_DEV double dmax(double a, double b) { return (a > b || a != a) ? a : b; }      // NaN propagates
 MPCQ_DEV double dmin(double a, double b) { return a < b ? a : b; }
 MPCQ_DEV double dabs(double a) { return a < 0 ? -a : a; }
 
@@ -1126,7 +1127,24 @@ MPCQ_DEV void solve_env(const Consts& cs, const IO<T>& io, int b, char* smem, T*
     team::sync(w.t);
     int status = 0, nfac = 0, nas = 0;
     double rmax = 0.0, pviol = 0.0;
-    if (ns == 0) {
+    // ---- non-finite inputs are flagged before any arithmetic: u = 0, MPCQ_ST_NUMERIC
+    bool finite_in = true;
+    {
+        const T* x0p = io.x0 + (size_t)b * 13;
+        const T* ftp = io.r_feet + (size_t)b * 12;
+        const T* xrp = io.x_ref + (size_t)b * 13 * H;
+        for (int idx = lane; idx < 13 * H; idx += w.t.nt) { const double v = (double)xrp[idx]; finite_in = finite_in && (v - v == 0.0); }
+        if (lane < 13) { const double v = (double)x0p[lane]; finite_in = finite_in && (v - v == 0.0); }
+        if (lane < 12) { const double v = (double)ftp[lane]; finite_in = finite_in && (v - v == 0.0); }
+        for (int idx = lane; idx < 4 * H; idx += w.t.nt) { const double v = (double)gait[idx]; finite_in = finite_in && (v - v == 0.0); }
+        if (io.yaw && lane == 0) { const double v = (double)io.yaw[b]; finite_in = finite_in && (v - v == 0.0); }
+        finite_in = !team::any(w.t, !finite_in);
+    }
+    if (!finite_in) {
+        status = ST_NUMERIC;
+        for (int idx = lane; idx < w.nv; idx += w.t.nt) w.u[idx] = 0.0;
+        team::sync(w.t);
+    } else if (ns == 0) {
         status = ST_NO_STANCE | ST_VERIFIED;
         team::sync(w.t);
     } else {
@@ -1140,6 +1158,10 @@ MPCQ_DEV void solve_env(const Consts& cs, const IO<T>& io, int b, char* smem, T*
         const double tol_loose = dmax(cs.tol_r_loose * gsc, tol_tight);
         bool numeric_ok = (gsc == gsc) && (gsc < 1e300);
         bool done = false;
+        if (!numeric_ok) {                                     // nothing was solved: return zeros, flagged
+            for (int idx = lane; idx < w.nv; idx += w.t.nt) w.u[idx] = 0.0;
+            team::sync(w.t);
+        }
         // ---- primal-dual active-set rounds
         for (int round = 0; round <= cs.pdas_cap && numeric_ok && !done; ++round) {
             numeric_ok = face_solve<T, NCAP, NW>(cs, w, tol_loose, rmax, false) && numeric_ok;
@@ -1148,7 +1170,11 @@ MPCQ_DEV void solve_env(const Consts& cs, const IO<T>& io, int b, char* smem, T*
             if (fc.n_primal == 0 && fc.n_dual == 0) {
                 rmax = refine<T, NSLOT>(cs, w, tol_tight, false, true);   // tighten on the same factor (CG), re-test
                 fc = pdas_update(cs, w, false);
-                if (fc.n_primal == 0 && fc.n_dual == 0) { done = true; break; }
+                if (fc.n_primal == 0 && fc.n_dual == 0) {
+                    // verified only with the stationarity residual actually at tolerance (a NaN fails this test)
+                    if (rmax <= 10.0 * tol_tight) done = true; else numeric_ok = false;
+                    break;
+                }
             }
 #if defined(MPCQ_HOST_EMU) && defined(MPCQ_TRACE)
             if (lane == 0) printf(" PDAS round %d: primal %d dual %d rmax %.2e\n", round, fc.n_primal, fc.n_dual, rmax);
@@ -1176,6 +1202,7 @@ MPCQ_DEV void solve_env(const Consts& cs, const IO<T>& io, int b, char* smem, T*
                 if (tag == 0x7fffffff) {                    // (a)
                     for (int idx = lane; idx < w.nv; idx += w.t.nt) w.ucur[idx] = w.u[idx];
                     phi_cur = objective(cs, w);
+                    if (!(rmax <= 10.0 * tol_tight)) { numeric_ok = false; break; }   // the factor cannot deliver the residual
                     const FaceCheck fc = pdas_update(cs, w, true);
 #if defined(MPCQ_HOST_EMU) && defined(MPCQ_TRACE)
                     if (lane == 0) printf("     feasible minimiser: primal %d dual %d\n", fc.n_primal, fc.n_dual);
@@ -1207,6 +1234,10 @@ MPCQ_DEV void solve_env(const Consts& cs, const IO<T>& io, int b, char* smem, T*
             }
         }
         if (done) status |= ST_VERIFIED; else status |= numeric_ok ? ST_MAXITER : ST_NUMERIC;
+        if (!done && !numeric_ok) {                            // never hand out the debris of a numerical breakdown
+            for (int idx = lane; idx < w.nv; idx += w.t.nt) w.u[idx] = 0.0;
+            team::sync(w.t);
+        }
     }
     // ---- outputs: forces, activity (on primal slack, like the oracle's kkt_report), residuals
     const double mu = cs.mu;

@@ -85,28 +85,35 @@ MPCQ_DEV void team_sync() { __syncthreads(); }
 MPCQ_DEV bool any(bool p) { return ballot(p) != 0u; }
 MPCQ_DEV bool all(bool p) { return ballot(p) == FULL; }
 
+// Reductions must hand EVERY lane the same value - control flow is decided on them, and lanes that disagree would
+// diverge around later full-mask collectives (a hang on real hardware).  `o > v ? o : v` is not commutative when a NaN
+// is involved, so NaN is made to win explicitly, and the result is taken from lane 0 in the end.
 template <class V> MPCQ_DEV V reduce_max(V v) {
     MPCQ_UNROLL
     for (int m = 16; m > 0; m >>= 1) {
         V o = shfl_xor(v, m);
-        v = o > v ? o : v;
+        v = (o > v || o != o) ? o : v;                         // NaN propagates
     }
-    return v;
+    return shfl(v, 0);
 }
 template <class V> MPCQ_DEV V reduce_sum(V v) {
     MPCQ_UNROLL
     for (int m = 16; m > 0; m >>= 1) v += shfl_xor(v, m);
-    return v;
+    return shfl(v, 0);
 }
-// (value, payload) arg-min; ties resolved towards the smaller payload so the result is
-// independent of lane order
+// (value, payload) arg-min; ties resolved towards the smaller payload so the result is independent of lane order;
+// a NaN value counts as smaller than everything (it must be noticed, not skipped)
 MPCQ_DEV void reduce_argmin(double& v, int& tag) {
     MPCQ_UNROLL
     for (int m = 16; m > 0; m >>= 1) {
         double ov = shfl_xor(v, m);
         int ot = shfl_xor(tag, m);
-        if (ov < v || (ov == v && ot < tag)) { v = ov; tag = ot; }
+        const bool o_nan = ov != ov, v_nan = v != v;
+        const bool take = (o_nan && !v_nan) || (o_nan == v_nan && (ov < v || ((ov == v || o_nan) && ot < tag)));
+        if (take) { v = ov; tag = ot; }
     }
+    v = shfl(v, 0);
+    tag = shfl(tag, 0);
 }
 
 }  // namespace wp
@@ -131,7 +138,7 @@ MPCQ_DEV double reduce_max(const Ctx& c, double v) {
     if (wp::lane() == 0) c.red[c.wid] = v;
     wp::team_sync();
     double r = c.red[0];
-    for (int i = 1; i < (c.nt >> 5); ++i) r = c.red[i] > r ? c.red[i] : r;
+    for (int i = 1; i < (c.nt >> 5); ++i) r = (c.red[i] > r || c.red[i] != c.red[i]) ? c.red[i] : r;
     wp::team_sync();
     return r;
 }

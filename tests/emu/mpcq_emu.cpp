@@ -7,6 +7,7 @@
 // every collective; values are exchanged through a double-buffered slot array.
 #define MPCQ_HOST_EMU 1
 #include <stdint.h>
+#include <stdio.h>
 #include <stdlib.h>
 #include <ucontext.h>
 
@@ -96,6 +97,16 @@ void run_team(int nthreads, void (*fn)(void*), void* arg) {
     }
     cur = 0;
     swapcontext(&main_ctx, &ctx[0]);
+    // every lane of a warp must have gone through the same number of warp collectives, every thread of the team
+    // through the same number of barriers: anything else is divergence around a full-mask collective, which
+    // deadlocks on real hardware even if this emulation happens to get through it
+    for (int l = 0; l < NT; ++l) {
+        if (gen[l] != gen[l & ~31] || bgen[l] != bgen[0]) {
+            fprintf(stderr, "mpcq_emu: DIVERGENT COLLECTIVES: thread %d did %ld warp collectives / %ld barriers, thread %d did %ld / %ld\n",
+                    l, gen[l], bgen[l], l & ~31, gen[l & ~31], bgen[0]);
+            abort();
+        }
+    }
 }
 }  // namespace mpcq_emu
 
@@ -133,7 +144,7 @@ int run(const mpcq_config* cfg, int B, const T* x0, const T* yaw, const T* feet,
         for (int b = 0; b < B; ++b) {
             Job<T> j;
             j.cs = *cs;
-            j.io = mpcq::IO<T>{x0, yaw, feet, gait, xref, f_out, u_full, iters, resid, status, active, B};
+            j.io = mpcq::IO<T>{x0, yaw, feet, gait, xref, f_out, u_full, iters, resid, status, active, nullptr, B};
             j.b = b;
             j.smem = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(smem.data()) + 31) & ~uintptr_t(31));
             j.lglobal = nullptr;

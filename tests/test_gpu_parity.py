@@ -189,7 +189,7 @@ def test_host_entry_point_chunked_pinned_and_pageable():
         assert np.array_equal(r["u"], res.u.cpu().numpy())
         assert np.array_equal(r["status"], res.status.cpu().numpy())
     assert np.array_equal(host["iters"], res.iters.cpu().numpy())
-    assert eng.last_launch_count == 2 * 4                       # 2 size classes x 4 chunks
+    assert eng.last_launch_count == 3 * 4                       # (schedule + 2 size classes) x 4 chunks
 
 
 def test_edge_cases_empty_batch_all_swing_and_errors():
@@ -214,6 +214,19 @@ def test_edge_cases_empty_batch_all_swing_and_errors():
         MpcqEngine(with_horizon(40), A1Config)
 
 
+def test_schedule_does_not_change_results():
+    """The expected-work-first launch order only reorders CTAs: results are bitwise those of the natural order."""
+    batch = make_batch(A1Config, 10, 1500, "mixed", (Gait.TROTTING10, Gait.STANDING), 81, solve=False)
+    from pympc_quadruped_b200.engine import MpcqEngine
+    x0, feet, gait, xref, yaw = _to_dev(batch, torch.float32)
+    a = MpcqEngine(batch["cfg"], A1Config).solve(x0, feet, gait, xref, yaw=yaw)
+    eng = MpcqEngine(batch["cfg"], A1Config, schedule=-1)
+    b = eng.solve(x0, feet, gait, xref, yaw=yaw)
+    assert eng.last_launch_count == 2
+    for k in ("forces", "u", "iters", "status", "active"):
+        assert torch.equal(getattr(a, k), getattr(b, k)), k
+
+
 def test_non_finite_inputs_are_flagged_not_propagated():
     """A robot with NaN / inf state must come back flagged MPCQ_ST_NUMERIC (never VERIFIED) without disturbing its neighbours."""
     batch = make_batch(A1Config, 10, 16, "mixed", (Gait.TROTTING10,), 71, solve=False)
@@ -231,6 +244,24 @@ def test_non_finite_inputs_are_flagged_not_propagated():
     keep = [b for b in range(16) if b not in (3, 7, 11)]
     assert np.all(st[keep] & _capi.ST_VERIFIED)
     assert torch.equal(res.u[keep], good[keep])
+
+
+def test_internal_overflow_terminates_and_is_flagged():
+    """Finite but absurd inputs that overflow inside the kernel must terminate (bounded loops, uniform control flow)."""
+    batch = make_batch(A1Config, 10, 8, "mixed", (Gait.TROTTING10,), 72, solve=False)
+    for dtype in (torch.float32, torch.float64):
+        eng = _engine(batch, A1Config, dtype)
+        x0, feet, gait, xref, yaw = _to_dev(batch, dtype)
+        feet = feet.clone(); x0 = x0.clone()
+        feet[1, :] = 1e25
+        x0[2, 3:6] = 1e30
+        res = eng.solve(x0, feet, gait, xref, yaw=yaw)
+        st = res.status.cpu().numpy()
+        u = res.u.double().cpu().numpy()
+        for b in (1, 2):
+            assert not (st[b] & _capi.ST_VERIFIED) or np.all(np.isfinite(u[b]))
+        keep = [0, 3, 4, 5, 6, 7]
+        assert np.all(st[keep] & _capi.ST_VERIFIED)
 
 
 def test_batch_permutation_and_split_invariance():

@@ -89,3 +89,31 @@ def test_iteration_cap_is_reported(emu_lib):
     bad = ~(out["status"] & _capi.ST_VERIFIED).astype(bool)
     assert bad.any() and np.all(out["status"][bad] & _capi.ST_MAXITER)
     assert out["resid"][:, 1].max() <= 1e-9      # the returned point is still feasible
+
+
+def test_non_finite_inputs_exit_early_and_uniformly(emu_lib):
+    """NaN / inf inputs: flagged MPCQ_ST_NUMERIC, zero forces, and - checked by the emulator on every run - no lane
+    may diverge around a collective (on hardware that is a hang, which is how this case was found)."""
+    batch = make_batch(A1Config, 10, 6, "mixed", (Gait.TROTTING10,), 114, solve=False)
+    batch["x0"][1, 9] = np.nan
+    batch["feet"][2, 2] = np.inf
+    batch["xref"][4, 5] = np.nan
+    out = emu_solve(emu_lib, batch, A1Config, False)
+    for b in (1, 2, 4):
+        assert out["status"][b] == _capi.ST_NUMERIC and np.all(out["u"][b] == 0)
+    for b in (0, 3, 5):
+        assert out["status"][b] & _capi.ST_VERIFIED
+
+
+def test_internal_overflow_is_flagged(emu_lib):
+    """Finite but absurd inputs that overflow inside (foot lever 1e25 m): must end flagged, never verified, without
+    divergent lanes (the emulator aborts on divergence)."""
+    batch = make_batch(A1Config, 10, 4, "mixed", (Gait.TROTTING10,), 115, solve=False)
+    batch["feet"][1, :] = 1e25
+    batch["x0"][2, 3:6] = 1e30
+    for f64 in (False, True):
+        out = emu_solve(emu_lib, batch, A1Config, f64)
+        for b in (1, 2):
+            assert not (out["status"][b] & _capi.ST_VERIFIED) or np.all(np.isfinite(out["u"][b]))
+        for b in (0, 3):
+            assert out["status"][b] & _capi.ST_VERIFIED
