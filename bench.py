@@ -338,14 +338,15 @@ def run_ours(a):
                        "precision": "Cholesky/triangular solves in " + a.dtype + ", residuals + KKT tests in f64"},
             "latency_ms": {"p50": lat[len(lat) // 2], "p90": lat[int(len(lat) * 0.9)], "max": lat[-1]},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "api": "mpcq_solve_host (C ABI, pinned host buffers in and out, 4 chunks pipelined on 4 streams)",
+                    "api": "mpcq_solve_host (C ABI, pinned host buffers in and out, chunks pipelined on separate streams)",
                     "ms_per_step": 1e3 * float(te.item()) / a.steps, "launches_per_step": e2e_launches},
             "controller_api": {"value": world * B / (ctrl_ms * 1e-3), "unit": UNIT, "ms_per_step": ctrl_ms,
                                "api": "BatchedModelPredictiveController.update_robot_state + update_mpc_if_needed on device tensors "
                                       "(mpcq_assemble + mpcq_solve: 3 kernel launches)"},
             "gpu_launches": launches_per_step * a.steps,
             "kernel_ms": {"per_class_mean": [float(v) for v in kmean], "dominant_class": dom,
-                          "share_of_step": float(kmean[dom] / (total_ms / a.steps))},
+                          "share_of_step": float(kmean[dom] / (total_ms / a.steps)),
+                          "note": "solve kernels by size class; the schedule pre-pass (one small launch) is not in this list"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                          "traffic": None, "peak_source": peak_src,
                          "note": "the path is not HBM-bound (708 B/solve): latency/shared-memory bound, see roofline_compute"},

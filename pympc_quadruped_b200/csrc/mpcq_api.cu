@@ -7,6 +7,7 @@
 // belongs to another class exit after reading its contact table.
 #include <cuda_runtime.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include <new>
 #include <string>
@@ -549,7 +550,13 @@ int mpcq_solve_host(mpcq_handle* h, int32_t B, const void* x0, const void* yaw, 
     // workspace cannot run twice concurrently, so such handles use one chunk.
     bool any_global = false;
     for (int ci = 0; ci < h->ncls; ++ci) any_global = any_global || h->lglobal[ci];
-    const int nchunk = any_global ? 1 : (B >= 2048 ? kHostStreams : (B >= 512 ? 2 : 1));
+    // measured at B = 4096: 1 / 2 / 3 / 4 chunks = 1.144 / 1.130 / 1.148 / 1.157 ms (smaller chunks hide more of the copies but
+    // give the expected-work-first schedule less to work with); large batches take all four streams
+    int nchunk = any_global ? 1 : (B >= 16384 ? kHostStreams : (B >= 1024 ? 2 : 1));
+    if (const char* ov = getenv("MPCQ_HOST_CHUNKS")) {          // experiments only
+        const int v = atoi(ov);
+        if (v >= 1 && v <= kHostStreams && !any_global) nchunk = v;
+    }
     {
         const int rcp = ensure_perm(h, 1, b);
         if (rcp != MPCQ_OK) return rcp;

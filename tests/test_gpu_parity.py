@@ -170,7 +170,7 @@ def test_host_entry_point_equals_device_entry_point():
 
 
 def test_host_entry_point_chunked_pinned_and_pageable():
-    """B large enough for the 4-chunk / 4-stream pipeline of mpcq_solve_host; pinned buffers are used for DMA
+    """B large enough for the chunked multi-stream pipeline of mpcq_solve_host; pinned buffers are used for DMA
     directly, pageable ones are staged - all three routes must agree bit for bit."""
     B = 2500
     batch = make_batch(A1Config, 10, B, "mixed", (Gait.TROTTING10, Gait.STANDING), 32, solve=False)
@@ -189,7 +189,7 @@ def test_host_entry_point_chunked_pinned_and_pageable():
         assert np.array_equal(r["u"], res.u.cpu().numpy())
         assert np.array_equal(r["status"], res.status.cpu().numpy())
     assert np.array_equal(host["iters"], res.iters.cpu().numpy())
-    assert eng.last_launch_count == 3 * 4                       # (schedule + 2 size classes) x 4 chunks
+    assert eng.last_launch_count == 3 * 2                       # (schedule + 2 size classes) x 2 chunks
 
 
 def test_edge_cases_empty_batch_all_swing_and_errors():
