@@ -598,6 +598,16 @@ int mpcq_solve_host(mpcq_handle* h, int32_t B, const void* x0, const void* yaw, 
 
 int mpcq_last_launch_count(const mpcq_handle* h) { return h ? h->last_launches : 0; }
 
+#ifdef MPCQ_PHASE_CLOCKS
+// development builds only (not declared in mpcq.h): read and clear the per-phase cycle table
+int mpcq_debug_phase_cycles(unsigned long long* out16) {
+    cudaDeviceSynchronize();
+    if (cudaMemcpyFromSymbol(out16, mpcq::g_phase_cycles, sizeof(unsigned long long) * 16) != cudaSuccess) return -1;
+    unsigned long long zero[16] = {};
+    return cudaMemcpyToSymbol(mpcq::g_phase_cycles, zero, sizeof zero) == cudaSuccess ? 0 : -1;
+}
+#endif
+
 int mpcq_set_profiling(mpcq_handle* h, int32_t enable) {
     if (!h) return MPCQ_ERR_INVALID;
     DeviceGuard guard(h->cfg.device);

@@ -29,6 +29,29 @@
 
 namespace mpcq {
 
+// Optional per-phase cycle accounting (-DMPCQ_PHASE_CLOCKS, development builds only): lane 0 of every team adds the
+// clock64() deltas of the phases it walks through to a global table read back by mpcq_debug_phase_cycles().
+#if defined(MPCQ_PHASE_CLOCKS) && !defined(MPCQ_HOST_EMU)
+__device__ unsigned long long g_phase_cycles[16];
+struct PhaseClock {
+    long long t0;
+    int id;
+    __device__ __forceinline__ explicit PhaseClock(int i) : t0(0), id(i) {
+#ifdef __CUDA_ARCH__
+        t0 = clock64();
+#endif
+    }
+    __device__ __forceinline__ ~PhaseClock() {
+#ifdef __CUDA_ARCH__
+        if ((threadIdx.x & 31) == 0) atomicAdd(&g_phase_cycles[id], (unsigned long long)(clock64() - t0));
+#endif
+    }
+};
+#define MPCQ_PHASE(id) PhaseClock _pc_##id(id)
+#else
+#define MPCQ_PHASE(id)
+#endif
+
 // ---------------------------------------------------------------------------------------------
 struct Consts {
     int horizon;
@@ -70,9 +93,9 @@ MPCQ_HD constexpr int l_elems(int n) { return n * n / 2 + 2 * n + 32; }   // +32
 
 template <class T> struct Work {
     // fp64
-    double *Md, *GW, *g, *u, *gam, *P0, *P1, *ucur, *utrial, *hd, *fmax;
+    double *Md, *GW, *g, *u, *gam, *P0, *P1, *ucur, *utrial, *hd, *fmax, *zero3;
     // precision T
-    T *L, *dblk, *vec, *cw, *zt, *Mf, *St;
+    T *L, *dblk, *vec, *cw, *zt, *Mf, *St, *r2;   // r2 = 2 * diag(R) in precision T
     int32_t* sinf;         // per slot: step | leg << 8 | foot << 16 | dead << 30
     // bytes
     uint8_t *fk;           // stance list: full foot-step index k = 4*step + leg
@@ -88,8 +111,8 @@ template <class T> struct Work {
 
 template <class T>
 MPCQ_HD constexpr size_t work_bytes(int H, int ncap, bool l_in_smem, bool with_md = false, int nmax = 0) {
-    size_t nd = (with_md ? 288 : 0) + 72 + 2 * 12 * (size_t)H + 6 * (size_t)ncap + ncap / 3 + 1 + 12;
-    size_t nt = (l_in_smem ? l_elems(nmax > 0 ? nmax : ncap) : 0) + 3 * (ncap / 4) * 4 + ncap + 256 + 3 * ncap + 288 + (size_t)H * H;
+    size_t nd = (with_md ? 288 : 0) + 72 + 2 * 12 * (size_t)H + 6 * (size_t)ncap + ncap / 3 + 1 + 12 + 4;
+    size_t nt = (l_in_smem ? l_elems(nmax > 0 ? nmax : ncap) : 0) + 3 * (ncap / 4) * 4 + ncap + 256 + 3 * ncap + 288 + (size_t)H * H + 12;
     size_t nb = (ncap / 3 + 1) * 11 + 4 * (size_t)H + 16 + 4 * (size_t)ncap;
     return align_up(nd * 8, 16) + align_up(nt * sizeof(T), 16) + align_up(nb, 16);
 }
@@ -109,8 +132,10 @@ MPCQ_DEV void carve(Work<T>& w, char* base, T* l_global, int H, int ncap, bool w
     w.hd = d; d += ncap;
     w.fmax = d; d += ncap / 3 + 1;
     w.t.red = d; d += 8;
+    w.zero3 = d + 4; // after redi (4 doubles); 4 doubles reserved
     w.t.redi = reinterpret_cast<int*>(d); d += 4;
-    size_t nd = (with_md ? 288 : 0) + 72 + 2 * 12 * (size_t)H + 6 * (size_t)ncap + ncap / 3 + 1 + 12;
+    d += 4;
+    size_t nd = (with_md ? 288 : 0) + 72 + 2 * 12 * (size_t)H + 6 * (size_t)ncap + ncap / 3 + 1 + 12 + 4;
     T* t = reinterpret_cast<T*>(base + align_up(nd * 8, 16));
     size_t used = 0;
     if (l_global) {
@@ -125,6 +150,7 @@ MPCQ_DEV void carve(Work<T>& w, char* base, T* l_global, int H, int ncap, bool w
     w.zt = t; t += 3 * ncap; used += 3 * ncap;
     w.Mf = t; t += 288; used += 288;
     w.St = t; t += H * H; used += (size_t)H * H;
+    w.r2 = t; t += 12; used += 12;
     uint8_t* b = reinterpret_cast<uint8_t*>(base + align_up(nd * 8, 16) + align_up(used * sizeof(T), 16));
     w.fk = b; b += ncap / 3 + 1;
     w.fo = b; b += ncap / 3 + 1;
@@ -178,6 +204,7 @@ MPCQ_DEV double dabs(double a) { return a < 0 ? -a : a; }
 // K1 + K2 (per-env part): model matrices M00, M11, horizon table S and the linear term g.
 template <class T>
 MPCQ_DEV void setup_model(const Consts& cs, Work<T>& w, const T* x0p, double yaw, const T* feetp, const T* xrefp) {
+    MPCQ_PHASE(0);
     const int lane = w.t.tid;
     const int H = cs.horizon;
     // --- Rz (float32-rounded like the reference), world inertia, its inverse: every lane, redundantly
@@ -238,6 +265,8 @@ MPCQ_DEV void setup_model(const Consts& cs, Work<T>& w, const T* x0p, double yaw
                 w.GW[18 * a + 9 + 3 * k + y] = acc;
             }
     }
+    if (lane < 12) w.r2[lane] = (T)(2.0 * cs.r[lane]);
+    if (lane < 4) w.zero3[lane] = 0.0;
     // --- horizon table S
     for (int idx = lane; idx < H * H; idx += w.t.nt) {
         const int i = idx / H, j = idx - i * H;
@@ -308,32 +337,26 @@ MPCQ_DEV void setup_model(const Consts& cs, Work<T>& w, const T* x0p, double yaw
 //   3. project back with G', W'.   u, gam in full [H][12] layout; P0 / P1 are scratch.
 template <class T>
 MPCQ_DEV void hess_apply(const Consts& cs, Work<T>& w, const double* uin, double* out, bool add_g) {
+    MPCQ_PHASE(1);
     const int lane = w.t.tid;
     const int H = cs.horizon;
     for (int idx = lane; idx < 9 * H; idx += w.t.nt) {
         const int i = idx / 9, k = idx - 9 * i;
+        // y = scale * sum_legs coef . u_leg with coef = row k of G (k < 3) / of W (k < 6) / the unit vector e_{k-6};
+        // written with selects instead of per-lane branches (k differs from lane to lane)
+        const bool rot = k < 6;
+        const double* gw = w.GW + (k < 3 ? 3 * k : (rot ? 9 + 3 * (k - 3) : 0));
+        const double e0 = k == 6 ? 1.0 : 0.0, e1 = k == 7 ? 1.0 : 0.0, e2 = k == 8 ? 1.0 : 0.0;
+        const double scale = k < 3 ? cs.q[6 + k] : (rot ? cs.q[k - 3] : cs.inv_mass);
         double y = 0;
-        if (k < 6) {
-            const double* gw = w.GW + (k < 3 ? 3 * k : 9 + 3 * (k - 3));
-            MPCQ_UNROLL
-            for (int a = 0; a < 4; ++a) {
-                const int s = w.cidx[4 * i + a];
-                if (s != 255) {
-                    const double* ua = uin + 3 * s;
-                    y += gw[18 * a] * ua[0] + gw[18 * a + 1] * ua[1] + gw[18 * a + 2] * ua[2];
-                }
-            }
-            y *= k < 3 ? cs.q[6 + k] : cs.q[k - 3];
-        } else {
-            const int x = k - 6;
-            MPCQ_UNROLL
-            for (int a = 0; a < 4; ++a) {
-                const int s = w.cidx[4 * i + a];
-                if (s != 255) y += uin[3 * s + x];
-            }
-            y *= cs.inv_mass;
+        MPCQ_UNROLL
+        for (int a = 0; a < 4; ++a) {
+            const int s = w.cidx[4 * i + a];
+            const double* ua = s != 255 ? uin + 3 * s : w.zero3;
+            const double c0 = rot ? gw[18 * a] : e0, c1 = rot ? gw[18 * a + 1] : e1, c2 = rot ? gw[18 * a + 2] : e2;
+            y += c0 * ua[0] + c1 * ua[1] + c2 * ua[2];
         }
-        w.P0[idx] = y;
+        w.P0[idx] = y * scale;
     }
     team::sync(w.t);
     for (int idx = lane; idx < 12 * H; idx += w.t.nt) {
@@ -371,6 +394,7 @@ MPCQ_DEV void hess_apply(const Consts& cs, Work<T>& w) { hess_apply(cs, w, w.u, 
 // slot v = 3p + comp of stance foot-step p; dead slots (z = 0) become identity rows.
 template <class T>
 MPCQ_DEV bool build_slots(const Consts& cs, Work<T>& w) {
+    MPCQ_PHASE(2);
     const int lane = w.t.tid;
     const T mu = (T)cs.mu;
     bool nonzero_c = false;
@@ -416,6 +440,7 @@ MPCQ_DEV bool build_slots(const Consts& cs, Work<T>& w) {
 // panel / beyond n compute garbage that is never stored.
 template <class T, int NCAP, int NW>
 MPCQ_DEV bool chol_factor(const Consts& cs, Work<T>& w, int k_start) {
+    MPCQ_PHASE(3);
     constexpr int NSLOT = NCAP / (32 * NW);
     constexpr int RSTEP = 32 * NW;                 // rows between two slots of a thread
     const int lane = wp::lane(), wid = w.t.wid;
@@ -481,12 +506,14 @@ MPCQ_DEV bool chol_factor(const Consts& cs, Work<T>& w, int k_start) {
                 const T t1 = zr[m][0] * s0 + zr[m][1] * s1 + zr[m][2] * s2;
                 const int mx = iv > jw ? iv : jw;
                 T e = (T)2 * ((T)(H - mx) * t0 + w.St[iv * H + jw] * t1);
-                if (((ri[m] ^ ci[c]) >> 16) == 0) {          // same foot-step (and same dead flag): R term / unit diagonal
-                    const T* zw = w.zt + 3 * (k0 + c);
-                    e += (T)2 * (zr[m][0] * zw[0] * (T)cs.r[3 * av] + zr[m][1] * zw[1] * (T)cs.r[3 * av + 1] +
-                                 zr[m][2] * zw[2] * (T)cs.r[3 * av + 2]);
-                    if (dead && v == k0 + c) e = 1;
-                }
+                // same foot-step (and same dead flag): R term / unit diagonal - branch-free (every lane executes a
+                // divergent branch body anyway as soon as one lane takes it)
+                const bool same = ((ri[m] ^ ci[c]) >> 16) == 0;
+                const T* zw = w.zt + 3 * (k0 + c);
+                const T* r2 = w.r2 + 3 * av;
+                const T rterm = (zr[m][0] * zw[0]) * r2[0] + (zr[m][1] * zw[1]) * r2[1] + (zr[m][2] * zw[2]) * r2[2];
+                e += same ? rterm : (T)0;
+                e = (same && dead && v == k0 + c) ? (T)1 : e;
                 acc[m][c] = e;
             }
         }
@@ -542,38 +569,44 @@ MPCQ_DEV bool chol_factor(const Consts& cs, Work<T>& w, int k_start) {
                 ok = ok && (piv > (T)0);
                 const T i3 = wp::rsqrt_(piv > (T)0 ? piv : (T)1);
                 if (lane == 0) {
+                    // dblk holds the INVERSE M of the 4x4 diagonal block (lower triangular): the block solves of the
+                    // panel and of the triangular sweeps become 4 independent dot products instead of a 4-deep chain
+                    const T m10 = -(l10 * i0) * i1, m21 = -(l21 * i1) * i2, m32 = -(l32 * i2) * i3;
+                    const T m20 = -(l20 * i0 + l21 * m10) * i2, m31 = -(l31 * i1 + l32 * m21) * i3;
+                    const T m30 = -(l30 * i0 + l31 * m10 + l32 * m20) * i3;
                     T* db = w.dblk + 3 * k0;          // 12 values per block of 4 columns
-                    db[0] = l10; db[1] = l20; db[2] = l21; db[3] = l30;
-                    db[4] = l31; db[5] = l32; db[6] = i0; db[7] = i1;
+                    db[0] = m10; db[1] = m20; db[2] = m21; db[3] = m30;
+                    db[4] = m31; db[5] = m32; db[6] = i0; db[7] = i1;
                     db[8] = i2; db[9] = i3; db[10] = 0; db[11] = 0;
                 }
             }
             team::sync(w.t);                                    // dblk visible to the team
         }
-        T l10, l20, l21, l30, l31, l32, i0, i1, i2, i3, pad0, pad1;
+        T m10, m20, m21, m30, m31, m32, m00, m11, m22, m33, pad0, pad1;
         {
             const T* db = w.dblk + 3 * k0;
-            load4(db, l10, l20, l21, l30);
-            load4(db + 4, l31, l32, i0, i1);
-            load4(db + 8, i2, i3, pad0, pad1);
+            load4(db, m10, m20, m21, m30);
+            load4(db + 4, m31, m32, m00, m11);
+            load4(db + 8, m22, m33, pad0, pad1);
         }
-        // ---- panel rows: x = acc * inv(Ld)'
+        // ---- panel rows: x = acc * inv(Ld)' = (M acc')'
         {
             const int stride = n - k0;
             T* c0 = const_cast<T*>(colg);
             MPCQ_UNROLL
             for (int m = 0; m < NSLOT; ++m) {
                 const int v = row0 + RSTEP * m;
-                if (m >= m0 && v >= row_lo && v < n) {
-                    const T x0 = acc[m][0] * i0;
-                    const T x1 = (acc[m][1] - x0 * l10) * i1;
-                    const T x2 = (acc[m][2] - x0 * l20 - x1 * l21) * i2;
-                    const T x3 = (acc[m][3] - x0 * l30 - x1 * l31 - x2 * l32) * i3;
-                    const int dv = v - k0;
+                if (m < m0) continue;
+                const int dv = v - k0;
+                const T x0 = m00 * acc[m][0];
+                const T x1 = dv >= 1 ? m10 * acc[m][0] + m11 * acc[m][1] : (T)0;
+                const T x2 = dv >= 2 ? (m20 * acc[m][0] + m21 * acc[m][1]) + m22 * acc[m][2] : (T)0;
+                const T x3 = dv >= 3 ? (m30 * acc[m][0] + m31 * acc[m][1]) + (m32 * acc[m][2] + m33 * acc[m][3]) : (T)0;
+                if (v >= row_lo && v < n) {
                     c0[v] = x0;
-                    c0[stride + v] = dv >= 1 ? x1 : (T)0;
-                    c0[2 * stride + v] = dv >= 2 ? x2 : (T)0;
-                    c0[3 * stride + v] = dv >= 3 ? x3 : (T)0;
+                    c0[stride + v] = x1;
+                    c0[2 * stride + v] = x2;
+                    c0[3 * stride + v] = x3;
                 }
             }
         }
@@ -583,9 +616,12 @@ MPCQ_DEV bool chol_factor(const Consts& cs, Work<T>& w, int k_start) {
     return team::any(w.t, !ok) == false;
 }
 
-// K4b: solve L L' x = vec in place (vec in shared memory, precision T)
+// K4b: solve L L' x = vec in place (vec in shared memory, precision T).  One warp; lane owns rows lane + 32 m.
+// The row updates are written branch-free (selects and zero-masked loads): per-lane if/else chains cost a divergent
+// branch region per slot and block (measured 400 cycles per 4-column block before, see profiles/r01_phase_cycles_*).
 template <class T, int NSLOT>
 MPCQ_DEV void tri_solve(Work<T>& w) {
+    MPCQ_PHASE(4);
     const int lane = wp::lane();
     const int n = w.n;
     const T* L = w.L;
@@ -602,28 +638,27 @@ MPCQ_DEV void tri_solve(Work<T>& w) {
         const int md = k0 >> 5, ld = k0 & 31;
         const T mine = pick<T, NSLOT>(bv, md);
         const T b0 = wp::shfl(mine, ld), b1 = wp::shfl(mine, ld + 1), b2 = wp::shfl(mine, ld + 2), b3 = wp::shfl(mine, ld + 3);
-        T l10, l20, l21, l30, l31, l32, i0, i1, i2, i3, pad0, pad1;
+        T m10, m20, m21, m30, m31, m32, m00, m11, m22, m33, pad0, pad1;
         const T* db = w.dblk + 3 * k0;
-        load4(db, l10, l20, l21, l30);
-        load4(db + 4, l31, l32, i0, i1);
-        load4(db + 8, i2, i3, pad0, pad1);
-        const T y0 = b0 * i0;
-        const T y1 = (b1 - l10 * y0) * i1;
-        const T y2 = (b2 - l20 * y0 - l21 * y1) * i2;
-        const T y3 = (b3 - l30 * y0 - l31 * y1 - l32 * y2) * i3;
+        load4(db, m10, m20, m21, m30);
+        load4(db + 4, m31, m32, m00, m11);
+        load4(db + 8, m22, m33, pad0, pad1);
+        const T y0 = m00 * b0;                                  // y = M b (M = inverse of the diagonal block)
+        const T y1 = m10 * b0 + m11 * b1;
+        const T y2 = (m20 * b0 + m21 * b1) + m22 * b2;
+        const T y3 = (m30 * b0 + m31 * b1) + (m32 * b2 + m33 * b3);
         const int stride = n - k0;
         const T* c0 = L + colbase(k0, n);
         MPCQ_UNROLL
         for (int m = 0; m < NSLOT; ++m) {
             const int v = lane + 32 * m;
-            if (m >= md && v < n) {
-                if (v >= k0 + 4) {
-                    bv[m] -= (c0[v] * y0 + c0[stride + v] * y1) + (c0[2 * stride + v] * y2 + c0[3 * stride + v] * y3);
-                } else if (v >= k0) {
-                    const int dv = v - k0;
-                    bv[m] = dv == 0 ? y0 : dv == 1 ? y1 : dv == 2 ? y2 : y3;
-                }
-            }
+            const int sel = v - k0;
+            const bool upd = sel >= 4 && v < n;
+            const T l0 = upd ? c0[v] : (T)0, l1 = upd ? c0[stride + v] : (T)0;
+            const T l2 = upd ? c0[2 * stride + v] : (T)0, l3 = upd ? c0[3 * stride + v] : (T)0;
+            const T contrib = (l0 * y0 + l1 * y1) + (l2 * y2 + l3 * y3);
+            const T yv = sel == 0 ? y0 : (sel == 1 ? y1 : (sel == 2 ? y2 : y3));
+            bv[m] = (sel >= 0 && sel < 4) ? yv : bv[m] - contrib;
         }
     }
     // backward: L' x = y
@@ -631,28 +666,26 @@ MPCQ_DEV void tri_solve(Work<T>& w) {
         const int md = k0 >> 5, ld = k0 & 31;
         const T mine = pick<T, NSLOT>(bv, md);
         const T b0 = wp::shfl(mine, ld), b1 = wp::shfl(mine, ld + 1), b2 = wp::shfl(mine, ld + 2), b3 = wp::shfl(mine, ld + 3);
-        T l10, l20, l21, l30, l31, l32, i0, i1, i2, i3, pad0, pad1;
+        T m10, m20, m21, m30, m31, m32, m00, m11, m22, m33, pad0, pad1;
         const T* db = w.dblk + 3 * k0;
-        load4(db, l10, l20, l21, l30);
-        load4(db + 4, l31, l32, i0, i1);
-        load4(db + 8, i2, i3, pad0, pad1);
-        const T x3 = b3 * i3;
-        const T x2 = (b2 - l32 * x3) * i2;
-        const T x1 = (b1 - l21 * x2 - l31 * x3) * i1;
-        const T x0 = (b0 - l10 * x1 - l20 * x2 - l30 * x3) * i0;
+        load4(db, m10, m20, m21, m30);
+        load4(db + 4, m31, m32, m00, m11);
+        load4(db + 8, m22, m33, pad0, pad1);
+        const T x3 = m33 * b3;                                  // x = M' b
+        const T x2 = m22 * b2 + m32 * b3;
+        const T x1 = (m11 * b1 + m21 * b2) + m31 * b3;
+        const T x0 = (m00 * b0 + m10 * b1) + (m20 * b2 + m30 * b3);
         MPCQ_UNROLL
         for (int m = 0; m < NSLOT; ++m) {
             const int v = lane + 32 * m;
-            if (m <= md && v < n) {
-                if (v < k0) {
-                    T a0, a1, a2, a3;
-                    load4(L + cbv[m] + k0, a0, a1, a2, a3);      // L[k0..k0+3, v]
-                    bv[m] -= (a0 * x0 + a1 * x1) + (a2 * x2 + a3 * x3);
-                } else if (v < k0 + 4) {
-                    const int dv = v - k0;
-                    bv[m] = dv == 0 ? x0 : dv == 1 ? x1 : dv == 2 ? x2 : x3;
-                }
-            }
+            const int sel = v - k0;
+            T a0, a1, a2, a3;
+            load4(L + cbv[m] + k0, a0, a1, a2, a3);              // L[k0..k0+3, v]; any row >= k0 reads in-bounds garbage, masked below
+            const bool upd = sel < 0;
+            a0 = upd ? a0 : (T)0; a1 = upd ? a1 : (T)0; a2 = upd ? a2 : (T)0; a3 = upd ? a3 : (T)0;
+            const T contrib = (a0 * x0 + a1 * x1) + (a2 * x2 + a3 * x3);
+            const T xv = sel == 0 ? x0 : (sel == 1 ? x1 : (sel == 2 ? x2 : x3));
+            bv[m] = (sel >= 0 && sel < 4) ? xv : bv[m] - contrib;
         }
     }
     MPCQ_UNROLL
@@ -676,6 +709,7 @@ MPCQ_DEV double slot_residual(int sx, int sy, int sz, int c, const double* gp, d
 // reduced gradient r = -Z' gam into vec (precision T); returns |r|_inf (fp64)
 template <class T>
 MPCQ_DEV double reduced_gradient(const Consts& cs, Work<T>& w) {
+    MPCQ_PHASE(5);
     const int lane = w.t.tid;
     double rmax = 0;
     for (int v = lane; v < w.n; v += w.t.nt) {
@@ -694,6 +728,7 @@ MPCQ_DEV double reduced_gradient(const Consts& cs, Work<T>& w) {
 // to double precision whatever T is
 template <class T>
 MPCQ_DEV void apply_step(const Consts& cs, Work<T>& w) {
+    MPCQ_PHASE(6);
     const int lane = w.t.tid;
     for (int p = lane; p < w.ns; p += w.t.nt) {
         const int sx = w.face[3 * p], sy = w.face[3 * p + 1], sz = w.face[3 * p + 2];
@@ -807,6 +842,7 @@ struct FaceCheck { int n_primal, n_dual; };
 
 template <class T>
 MPCQ_DEV FaceCheck pdas_update(const Consts& cs, Work<T>& w, bool write) {
+    MPCQ_PHASE(7);
     const int lane = w.t.tid;
     const double mu = cs.mu;
     int npv = 0, ndv = 0;
@@ -866,6 +902,7 @@ MPCQ_DEV FaceCheck pdas_update(const Consts& cs, Work<T>& w, bool write) {
 // factorisation restarts at the first changed column instead of column 0.  Returns that column (multiple of 4).
 template <class T, int NFS>
 MPCQ_DEV int reorder_feet(Work<T>& w) {
+    MPCQ_PHASE(8);
     const int lane = wp::lane();
     const int ns = w.ns;
     unsigned balc[NFS];
@@ -1086,6 +1123,7 @@ MPCQ_DEV void blocked_step(const Consts& cs, Work<T>& w, double alpha, int tag) 
 // the whole path for environment b.  NCAP = slot capacity of this size class.
 template <class T, int NCAP, int NW>
 MPCQ_DEV void solve_env(const Consts& cs, const IO<T>& io, int b, char* smem, T* l_global, int ns_lo, int ns_hi) {
+    MPCQ_PHASE(9);
     const int nmax = (3 * (ns_hi < NCAP / 3 ? ns_hi : NCAP / 3) + 3) & ~3;     // largest system of this size class
     const int H = cs.horizon;
     Work<T> w;
