@@ -62,26 +62,91 @@ def workload_name(a):
 
 
 class ClockSampler:
-    """nvidia-smi clocks/throttle reasons DURING the timed region."""
+    """SM clock and throttle reasons sampled DURING the timed region: an in-process NVML polling thread (2 ms period, so
+    that a 0.2 s timed region still yields ~100 samples); `nvidia-smi -lms` as the fallback when NVML cannot be loaded."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, gpu_index):
+    def __init__(self, gpu_index, uuid=None):
         self.idx = gpu_index
+        self.uuid = uuid
         self.proc = None
+        self.thread = None
+        self.samples = []          # (sm_mhz, reasons bit mask)
+        self.sm_max = None
+        self._stop = False
+        self.source = None
+
+    def _nvml_handle(self):
+        import pynvml
+        pynvml.nvmlInit()
+        if self.uuid is not None:
+            try:
+                return pynvml, pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + str(self.uuid)).encode())
+            except Exception:
+                pass
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+        idx = self.idx
+        if vis:
+            ent = vis.split(",")[self.idx].strip()
+            if ent.isdigit():
+                idx = int(ent)
+            else:
+                return pynvml, pynvml.nvmlDeviceGetHandleByUUID(ent.encode())
+        return pynvml, pynvml.nvmlDeviceGetHandleByIndex(idx)
 
     def start(self):
+        import threading
+        try:
+            nv, h = self._nvml_handle()
+            self.sm_max = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+            reasons_fn = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+
+            def poll():
+                while not self._stop:
+                    try:
+                        self.samples.append((float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)), int(reasons_fn(h))))
+                    except Exception:
+                        pass
+                    time.sleep(0.002)
+
+            self._nv = nv
+            self.thread = threading.Thread(target=poll, daemon=True)
+            self.thread.start()
+            self.source = "nvml"
+            return
+        except Exception:
+            self.thread = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.idx}", f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "50"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.source = "nvidia-smi"
         except OSError:
             self.proc = None
 
+    @staticmethod
+    def _summary(sm, mx, reasons, source):
+        # the first samples may precede the load; take the median of the upper half
+        sm_sorted = sorted(sm)
+        load = sm_sorted[len(sm_sorted) // 2:] if sm_sorted else []
+        return {"sm_mhz": statistics.median(load) if load else None, "sm_max_mhz": mx,
+                "reasons": sorted(reasons), "samples": len(sm), "source": source}
+
     def stop(self):
+        if self.thread is not None:
+            self._stop = True
+            self.thread.join(timeout=2)
+            nv = self._nv
+            names = {"hw_slowdown": nv.nvmlClocksThrottleReasonHwSlowdown,
+                     "hw_thermal_slowdown": nv.nvmlClocksThrottleReasonHwThermalSlowdown,
+                     "sw_thermal_slowdown": nv.nvmlClocksThrottleReasonSwThermalSlowdown,
+                     "sw_power_cap": nv.nvmlClocksThrottleReasonSwPowerCap}
+            reasons = {k for k, bit in names.items() if any(r & bit for _, r in self.samples)}
+            return self._summary([s for s, _ in self.samples], self.sm_max, reasons, "nvml")
         if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml and nvidia-smi unavailable"], "samples": 0}
         self.proc.terminate()
         try:
             out, _ = self.proc.communicate(timeout=5)
@@ -100,11 +165,7 @@ class ClockSampler:
             for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), p[4:8]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
-        # the first samples may precede the load; take the median of the upper half
-        sm_sorted = sorted(sm)
-        load = sm_sorted[len(sm_sorted) // 2:] if sm_sorted else []
-        return {"sm_mhz": statistics.median(load) if load else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        return self._summary(sm, max(mx) if mx else None, reasons, "nvidia-smi")
 
 
 def host_states(a, seed):
@@ -220,7 +281,7 @@ def run_ours(a):
     for s in range(a.warmup):
         step(s)
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(a.steps)]
-    sampler = ClockSampler(local)
+    sampler = ClockSampler(local, getattr(torch.cuda.get_device_properties(local), 'uuid', None))
     barrier()
     sampler.start()
     t_all0, t_all1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -322,6 +383,26 @@ def run_ours(a):
     fma_per_fact = nred ** 3 / 6 + 2.5 * nred ** 2 * 4 + 8 * nred ** 2 / 2
     exec_flops = 2.0 * fma_per_fact * facts.mean() * B / kern_s
 
+    # ---- measured denominators MEASURED_PEAKS.json does not hold (fp32 / fp64 FMA, shared-memory loads): micro-kernels
+    # through the C ABI, run after every timed region
+    import ctypes
+    pk = (ctypes.c_double * 4)()
+    peaks_ok = eng.lib.mpcq_measure_peaks(local, pk) == 0
+    fma_peak = (pk[1] if a.dtype == "f64" else pk[0]) if peaks_ok else None
+    # algorithmic flops of one solve as SURVEY.md 8d defines them for the reference's dense formulation:
+    # build 2 n^2 k + 2 n k, one Cholesky n^3/3, 2 n^2 per triangular-solve pair (n = 12H, k = 13H)
+    nfull, kfull = 12 * H, 13 * H
+    algo_flops = 2.0 * nfull * nfull * kfull + 2.0 * nfull * kfull + nfull ** 3 / 3.0 + 2.0 * nfull * nfull * float(facts.mean())
+    algo_tflops = algo_flops * B / kern_s / 1e12
+
+    # DRAM traffic of the dominant kernel from the committed `ncu --set full` capture of this same command
+    traffic, traffic_src = None, None
+    tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(tpath):
+        tj = json.load(open(tpath))
+        if tj.get("envs") == B and tj.get("horizon") == H and tj.get("dtype") == a.dtype:
+            traffic, traffic_src = tj["dram_bytes_read"] + tj["dram_bytes_write"], tj.get("source")
+
     cpu = None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
         cpu = cpu_baseline(a, st, tabs, out, eng, (x0, yaw, feet, xref, gait))
@@ -348,9 +429,21 @@ def run_ours(a):
                           "share_of_step": float(kmean[dom] / (total_ms / a.steps)),
                           "note": "solve kernels by size class; the schedule pre-pass (one small launch) is not in this list"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                         "traffic": None, "peak_source": peak_src,
-                         "note": "the path is not HBM-bound (708 B/solve): latency/shared-memory bound, see roofline_compute"},
-            "roofline_compute": {"executed_gflops_model": exec_flops / 1e9, "factorisations_per_solve_mean": float(facts.mean()),
+                         "traffic": traffic, "traffic_source": traffic_src, "algorithmic_bytes_per_launch": ALGO_BYTES(H) * (rs // 4) * B,
+                         "peak_source": peak_src,
+                         "note": "the path is not HBM-bound (732 B/solve): latency/shared-memory bound, see roofline_compute"},
+            "roofline_compute": {"bound": "fp64 fma" if a.dtype == "f64" else "fp32 fma",
+                                 "peak_tflops_measured": fma_peak, "fp32_fma_tflops": pk[0] if peaks_ok else None,
+                                 "fp64_fma_tflops": pk[1] if peaks_ok else None, "smem_load_gbs": pk[2] if peaks_ok else None,
+                                 "peak_source": "mpcq_measure_peaks micro-kernels, this run",
+                                 "algorithmic_tflops": algo_tflops, "algorithmic_mflop_per_solve": algo_flops / 1e6,
+                                 "frac_algorithmic": (algo_tflops / fma_peak) if fma_peak else None,
+                                 "executed_tflops_model": exec_flops / 1e12,
+                                 "frac_executed": (exec_flops / 1e12 / fma_peak) if fma_peak else None,
+                                 "note": "algorithmic = the reference's dense formulation (SURVEY 8d: 2n^2k build + n^3/3 Cholesky + 2n^2 per "
+                                         "solve pair); executed = what the kernel does (closed-form Hessian, swing steps eliminated, "
+                                         "factorisations x (n_red^3/6 + assembly) FMAs)",
+                                 "executed_gflops_model": exec_flops / 1e9, "factorisations_per_solve_mean": float(facts.mean()),
                                  "factorisations_p50": float(np.median(facts)), "factorisations_max": float(facts.max()),
                                  "reduced_dim_mean": float(nred)},
             "solver": {"fallback_envs": fallback, "unverified_envs": unverified, "envs_checked": int(S * B)},

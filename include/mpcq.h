@@ -165,6 +165,12 @@ int mpcq_last_launch_count(const mpcq_handle* h);
  */
 int mpcq_set_profiling(mpcq_handle* h, int32_t enable);
 int mpcq_last_kernel_ms(mpcq_handle* h, float* ms, int32_t cap);
+/*
+ * Denominators for the roofline of the solve kernel that MEASURED_PEAKS.json does not hold: runs three
+ * saturating micro-kernels on `device` (about 50 ms in total, synchronous) and writes
+ *   out4[0] = FP32 FMA TFLOP/s, out4[1] = FP64 FMA TFLOP/s, out4[2] = shared-memory load GB/s (LDS.128), out4[3] = SM count.
+ */
+int mpcq_measure_peaks(int32_t device, double* out4);
 
 #ifdef __cplusplus
 }

@@ -80,12 +80,14 @@ def bind(lib: C.CDLL) -> C.CDLL:
     lib.mpcq_set_profiling.restype = C.c_int
     lib.mpcq_last_kernel_ms.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.c_int32]
     lib.mpcq_last_kernel_ms.restype = C.c_int
+    lib.mpcq_measure_peaks.argtypes = [C.c_int32, C.POINTER(C.c_double)]
+    lib.mpcq_measure_peaks.restype = C.c_int
     return lib
 
 
 EXPORTS = ("mpcq_version", "mpcq_create", "mpcq_destroy", "mpcq_last_error", "mpcq_solve",
            "mpcq_solve_host", "mpcq_build_qp", "mpcq_assemble", "mpcq_last_launch_count", "mpcq_set_profiling",
-           "mpcq_last_kernel_ms")
+           "mpcq_last_kernel_ms", "mpcq_measure_peaks")
 
 _lib = None
 

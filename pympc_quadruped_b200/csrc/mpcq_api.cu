@@ -27,7 +27,12 @@ constexpr int kGlobalCtas = 148 * 2;       // resident CTAs of a class whose fac
 template <int NCAP> struct TeamWarps { static constexpr int value = NCAP <= 64 ? MPCQ_NW0 : (NCAP <= 128 ? MPCQ_NW1 : (NCAP <= 192 ? MPCQ_NW2 : MPCQ_NW3)); };
 
 template <class T, int NCAP, bool LGLOBAL>
-__global__ void __launch_bounds__(32 * TeamWarps<NCAP>::value, (NCAP <= 64 && MPCQ_NW0 > 1) ? 12 : 1)   // small class with 2-warp teams: 12 teams (24 warps) per SM
+// small class: shared memory allows 11 one-warp teams per SM (fp32), so cap the registers at 65536 / (11 * 32) -> 184
+// (with 2-warp teams: 12 teams = 24 warps per SM)
+#ifndef MPCQ_MINB0
+#define MPCQ_MINB0 (MPCQ_NW0 > 1 ? 12 : (sizeof(T) == 4 ? 11 : 1))
+#endif
+__global__ void __launch_bounds__(32 * TeamWarps<NCAP>::value, NCAP <= 64 ? MPCQ_MINB0 : 1)
 mpcq_solve_kernel(const __grid_constant__ Consts cs, const __grid_constant__ IO<T> io, T* gws, size_t gws_stride,
                   int ns_lo, int ns_hi) {
     extern __shared__ __align__(32) char smem[];
@@ -100,7 +105,7 @@ mpcq_build_qp_kernel(const __grid_constant__ Consts cs, const __grid_constant__ 
         for (int col = lane; col < n; col += 32) {
             const int j = col / 12, c = col - 12 * j;
             const int m = i > j ? i : j;
-            double v = 2.0 * ((double)(H - m) * w.Md[12 * r + c] + (double)w.St[i * H + j] * w.Md[144 + 12 * r + c]);
+            double v = 2.0 * (double)(H - m) * w.Md[12 * r + c] + (double)w.NS2[2 * (i * H + j) + 1] * w.Md[144 + 12 * r + c];
             if (row == col) v += 2.0 * cs.r[r];
             Hb[(size_t)row * n + col] = v;
         }

@@ -48,6 +48,10 @@ struct PhaseClock {
     }
 };
 #define MPCQ_PHASE(id) PhaseClock _pc_##id(id)
+#elif defined(MPCQ_HOST_EMU)
+// host emulation (tests only): count how often thread 0 of a team enters each phase
+static long g_emu_phase_calls[16];
+#define MPCQ_PHASE(id) do { if (::mpcq_emu::thread_id() == 0) ++g_emu_phase_calls[id]; } while (0)
 #else
 #define MPCQ_PHASE(id)
 #endif
@@ -94,8 +98,10 @@ MPCQ_HD constexpr int l_elems(int n) { return n * n / 2 + 2 * n + 32; }   // +32
 template <class T> struct Work {
     // fp64
     double *Md, *GW, *g, *u, *gam, *P0, *P1, *ucur, *utrial, *hd, *fmax, *zero3;
+    double *hs, *hq, *rd;  // hess_apply tables: stage-1 scales [9], stage-2 scales [12], diag(R) [12]
     // precision T
-    T *L, *dblk, *vec, *cw, *zt, *Mf, *St, *r2;   // r2 = 2 * diag(R) in precision T
+    T *L, *dblk, *vec, *cw, *zt, *Mf, *r2;   // r2 = 2 * diag(R) in precision T
+    T *NS2;                // [H][H][2]: (2 N_ij, 2 S_ij) pairs for the Hessian assembly
     int32_t* sinf;         // per slot: step | leg << 8 | foot << 16 | dead << 30
     // bytes
     uint8_t *fk;           // stance list: full foot-step index k = 4*step + leg
@@ -111,8 +117,8 @@ template <class T> struct Work {
 
 template <class T>
 MPCQ_HD constexpr size_t work_bytes(int H, int ncap, bool l_in_smem, bool with_md = false, int nmax = 0) {
-    size_t nd = (with_md ? 288 : 0) + 72 + 2 * 12 * (size_t)H + 6 * (size_t)ncap + ncap / 3 + 1 + 12 + 4;
-    size_t nt = (l_in_smem ? l_elems(nmax > 0 ? nmax : ncap) : 0) + 3 * (ncap / 4) * 4 + ncap + 256 + 3 * ncap + 288 + (size_t)H * H + 12;
+    size_t nd = (with_md ? 288 : 0) + 72 + 2 * 12 * (size_t)H + 6 * (size_t)ncap + ncap / 3 + 1 + 12 + 40;
+    size_t nt = (l_in_smem ? l_elems(nmax > 0 ? nmax : ncap) : 0) + 3 * (ncap / 4) * 4 + ncap + 256 + 3 * ncap + 288 + 2 * (size_t)H * H + 12;
     size_t nb = (ncap / 3 + 1) * 11 + 4 * (size_t)H + 16 + 4 * (size_t)ncap;
     return align_up(nd * 8, 16) + align_up(nt * sizeof(T), 16) + align_up(nb, 16);
 }
@@ -132,10 +138,12 @@ MPCQ_DEV void carve(Work<T>& w, char* base, T* l_global, int H, int ncap, bool w
     w.hd = d; d += ncap;
     w.fmax = d; d += ncap / 3 + 1;
     w.t.red = d; d += 8;
-    w.zero3 = d + 4; // after redi (4 doubles); 4 doubles reserved
     w.t.redi = reinterpret_cast<int*>(d); d += 4;
-    d += 4;
-    size_t nd = (with_md ? 288 : 0) + 72 + 2 * 12 * (size_t)H + 6 * (size_t)ncap + ncap / 3 + 1 + 12 + 4;
+    w.zero3 = d; d += 4;
+    w.hs = d; d += 12;
+    w.hq = d; d += 12;
+    w.rd = d; d += 12;
+    size_t nd = (with_md ? 288 : 0) + 72 + 2 * 12 * (size_t)H + 6 * (size_t)ncap + ncap / 3 + 1 + 12 + 40;
     T* t = reinterpret_cast<T*>(base + align_up(nd * 8, 16));
     size_t used = 0;
     if (l_global) {
@@ -149,8 +157,8 @@ MPCQ_DEV void carve(Work<T>& w, char* base, T* l_global, int H, int ncap, bool w
     w.cw = t; t += 256; used += 256;
     w.zt = t; t += 3 * ncap; used += 3 * ncap;
     w.Mf = t; t += 288; used += 288;
-    w.St = t; t += H * H; used += (size_t)H * H;
     w.r2 = t; t += 12; used += 12;
+    w.NS2 = t; t += 2 * H * H; used += 2 * (size_t)H * H;
     uint8_t* b = reinterpret_cast<uint8_t*>(base + align_up(nd * 8, 16) + align_up(used * sizeof(T), 16));
     w.fk = b; b += ncap / 3 + 1;
     w.fo = b; b += ncap / 3 + 1;
@@ -188,6 +196,25 @@ MPCQ_DEV void load4(const double* p, double& a, double& b, double& c, double& d)
     a = v0.x; b = v0.y; c = v1.x; d = v1.y;
 #endif
 }
+
+MPCQ_DEV void load2(const float* p, float& a, float& b) {
+#ifdef MPCQ_HOST_EMU
+    a = p[0]; b = p[1];
+#else
+    float2 v = *reinterpret_cast<const float2*>(p);
+    a = v.x; b = v.y;
+#endif
+}
+MPCQ_DEV void load2(const double* p, double& a, double& b) {
+#ifdef MPCQ_HOST_EMU
+    a = p[0]; b = p[1];
+#else
+    double2 v = *reinterpret_cast<const double2*>(p);
+    a = v.x; b = v.y;
+#endif
+}
+
+template <int V> struct IntC { static constexpr int value = V; };
 
 template <class T, int NS> MPCQ_DEV T pick(const T (&a)[NS], int m) {
     T v = a[0];
@@ -265,7 +292,13 @@ MPCQ_DEV void setup_model(const Consts& cs, Work<T>& w, const T* x0p, double yaw
                 w.GW[18 * a + 9 + 3 * k + y] = acc;
             }
     }
-    if (lane < 12) w.r2[lane] = (T)(2.0 * cs.r[lane]);
+    if (lane < 12) {
+        w.r2[lane] = (T)(2.0 * cs.r[lane]);
+        w.rd[lane] = cs.r[lane];
+        // hess_apply tables (shared memory instead of per-lane indexed constant-bank reads and branches)
+        w.hs[lane] = lane < 3 ? cs.q[6 + lane] : (lane < 6 ? cs.q[lane - 3] : cs.inv_mass);
+        w.hq[lane] = 0.5 * ((lane >= 3 && lane < 6) ? cs.q[6 + lane] : (lane >= 9 ? cs.q[lane - 6] : 1.0));   // 1/2: NS2 holds 2N, 2S
+    }
     if (lane < 4) w.zero3[lane] = 0.0;
     // --- horizon table S
     for (int idx = lane; idx < H * H; idx += w.t.nt) {
@@ -273,7 +306,8 @@ MPCQ_DEV void setup_model(const Consts& cs, Work<T>& w, const T* x0p, double yaw
         const int m = i > j ? i : j;
         const double a = m - i + 0.5, b = m - j + 0.5, Ln = H - m;
         const double sv = Ln * a * b + (a + b) * Ln * (Ln - 1) * 0.5 + (Ln - 1) * Ln * (2 * Ln - 1) / 6.0;
-        w.St[idx] = (T)sv;                                  // multiples of 1/4 below 2^17: exact in float
+        w.NS2[2 * idx] = (T)(2.0 * Ln);                     // 2 N_ij
+        w.NS2[2 * idx + 1] = (T)(2.0 * sv);                 // 2 S_ij: multiples of 1/2 below 2^18, exact in float
     }
     team::sync(w.t);
     // --- M00 = B0'QB0, M11 = B1'QB1
@@ -345,32 +379,34 @@ MPCQ_DEV void hess_apply(const Consts& cs, Work<T>& w, const double* uin, double
         // y = scale * sum_legs coef . u_leg with coef = row k of G (k < 3) / of W (k < 6) / the unit vector e_{k-6};
         // written with selects instead of per-lane branches (k differs from lane to lane)
         const bool rot = k < 6;
-        const double* gw = w.GW + (k < 3 ? 3 * k : (rot ? 9 + 3 * (k - 3) : 0));
-        const double e0 = k == 6 ? 1.0 : 0.0, e1 = k == 7 ? 1.0 : 0.0, e2 = k == 8 ? 1.0 : 0.0;
-        const double scale = k < 3 ? cs.q[6 + k] : (rot ? cs.q[k - 3] : cs.inv_mass);
+        const double* gw = w.GW + wp::sel(k < 3, 3 * k, wp::sel(rot, 9 + 3 * (k - 3), 0));
+        const double e0 = wp::sel(k == 6, 1.0, 0.0), e1 = wp::sel(k == 7, 1.0, 0.0), e2 = wp::sel(k == 8, 1.0, 0.0);
         double y = 0;
         MPCQ_UNROLL
         for (int a = 0; a < 4; ++a) {
             const int s = w.cidx[4 * i + a];
             const double* ua = s != 255 ? uin + 3 * s : w.zero3;
-            const double c0 = rot ? gw[18 * a] : e0, c1 = rot ? gw[18 * a + 1] : e1, c2 = rot ? gw[18 * a + 2] : e2;
+            const double c0 = wp::sel(rot, gw[18 * a], e0), c1 = wp::sel(rot, gw[18 * a + 1], e1), c2 = wp::sel(rot, gw[18 * a + 2], e2);
             y += c0 * ua[0] + c1 * ua[1] + c2 * ua[2];
         }
-        w.P0[idx] = y * scale;
+        w.P0[idx] = y * w.hs[k];
     }
     team::sync(w.t);
     for (int idx = lane; idx < 12 * H; idx += w.t.nt) {
         const int j = idx / 12, c = idx - 12 * j;
         const bool useN = c < 6;
-        const int src = c < 3 ? c : c < 6 ? 3 + c : c < 9 ? c - 3 : c - 3;     // y0r | fs | y1r | fs
-        double acc = 0;
-        for (int i = 0; i < H; ++i) {
-            const double wgt = useN ? (double)(H - (i > j ? i : j)) : (double)w.St[i * H + j];
-            acc += wgt * w.P0[9 * i + src];
+        const int src = wp::sel(c < 3, c, wp::sel(c < 6, 3 + c, c - 3));     // y0r | fs | y1r | fs
+        const T* ns = w.NS2 + 2 * j + (useN ? 0 : 1);          // column j of 2N (c < 6) or of 2S
+        const double* p0 = w.P0 + src;
+        double acc0 = 0, acc1 = 0;
+        int i = 0;
+        MPCQ_NOUNROLL                                          // hess_apply is inlined a dozen times: keep each copy small (I-cache)
+        for (; i + 1 < H; i += 2) {
+            acc0 += (double)ns[2 * H * i] * p0[9 * i];
+            acc1 += (double)ns[2 * H * (i + 1)] * p0[9 * (i + 1)];
         }
-        if (c >= 3 && c < 6) acc *= cs.q[9 + (c - 3)];
-        if (c >= 9) acc *= cs.q[3 + (c - 9)];
-        w.P1[idx] = acc;
+        if (i < H) acc0 += (double)ns[2 * H * i] * p0[9 * i];
+        w.P1[idx] = (acc0 + acc1) * w.hq[c];
     }
     team::sync(w.t);
     const double dt2 = cs.dt * cs.dt, dt4 = dt2 * dt2;
@@ -381,7 +417,7 @@ MPCQ_DEV void hess_apply(const Consts& cs, Work<T>& w, const double* uin, double
         const double* gw = w.GW + 18 * a + y;
         const double t0 = cs.inv_mass * Y[3 + y] + gw[0] * Y[0] + gw[3] * Y[1] + gw[6] * Y[2];
         const double t1 = cs.inv_mass * Y[9 + y] + gw[9] * Y[6] + gw[12] * Y[7] + gw[15] * Y[8];
-        out[o] = (add_g ? w.g[o] : 0.0) + 2.0 * (cs.r[3 * a + y] * uin[o] + dt2 * t0 + dt4 * t1);
+        out[o] = (add_g ? w.g[o] : 0.0) + 2.0 * (w.rd[3 * a + y] * uin[o] + dt2 * t0 + dt4 * t1);
     }
     team::sync(w.t);
 }
@@ -449,7 +485,7 @@ MPCQ_DEV bool chol_factor(const Consts& cs, Work<T>& w, int k_start) {
     bool ok = true;
     const int row0 = 4 * (NW * (lane >> 2) + wid) + (lane & 3);
     // row data of this thread, fixed for the whole factorisation
-    T zr[NSLOT][3];
+    T zr[NSLOT][3], zq[NSLOT][3];                  // z of the row and 2 R z (the R term of a same-foot entry)
     int ri[NSLOT];
     MPCQ_UNROLL
     for (int m = 0; m < NSLOT; ++m) {
@@ -459,6 +495,8 @@ MPCQ_DEV bool chol_factor(const Consts& cs, Work<T>& w, int k_start) {
         zr[m][0] = in ? w.zt[3 * v] : (T)0;
         zr[m][1] = in ? w.zt[3 * v + 1] : (T)0;
         zr[m][2] = in ? w.zt[3 * v + 2] : (T)0;
+        const T* r2 = w.r2 + 3 * ((ri[m] >> 8) & 3);
+        zq[m][0] = zr[m][0] * r2[0]; zq[m][1] = zr[m][1] * r2[1]; zq[m][2] = zr[m][2] * r2[2];
     }
     // cw[c][mat][leg][x] = sum_y M_mat[3 leg + x][3 b_c + y] z_c[y] for the 4 panel columns: one (c,mat,leg) per lane of
     // warp 0, double-buffered so the next panel's table can be written while other warps still read this one
@@ -480,7 +518,11 @@ MPCQ_DEV bool chol_factor(const Consts& cs, Work<T>& w, int k_start) {
     // Rows < k_start keep their factor (leading block unchanged since the previous factorisation, see
     // reorder_feet): for panels k0 < k_start only the rows >= k_start are recomputed (L21 = K21 L11^-T, using the
     // stored diagonal blocks); from k_start on it is the plain left-looking factorisation.
-    for (int k0 = 0; k0 < n; k0 += 4) {
+    // One panel.  M0 >= 0 fixes the first live row slot at compile time (slots below it hold only rows above the panel):
+    // with predication instead, a one-warp team would still ISSUE the dead slot's multiply-adds - half of all
+    // instructions of the later panels, and the kernel is issue-bound under load.  M0 = -1: decided at run time.
+    auto panel = [&](int k0, auto m0c) {
+        constexpr int M0 = decltype(m0c)::value;
         const bool keep_diag = k0 < k_start;
         const int row_lo = keep_diag ? k_start : k0;
         const T* cw = w.cw + 128 * ((k0 >> 2) & 1);
@@ -489,7 +531,9 @@ MPCQ_DEV bool chol_factor(const Consts& cs, Work<T>& w, int k_start) {
         for (int c = 0; c < 4; ++c) ci[c] = w.sinf[k0 + c];
         // ---- initial entries of the panel
         T acc[NSLOT][4];
-        const int m0 = row_lo / RSTEP;
+        const int m0 = M0 >= 0 ? M0 : row_lo / RSTEP;   // first live row slot (compile-time in the specialised bodies)
+        {
+        MPCQ_PHASE(10);
         MPCQ_UNROLL
         for (int m = 0; m < NSLOT; ++m) {
             if (m < m0) continue;
@@ -504,44 +548,89 @@ MPCQ_DEV bool chol_factor(const Consts& cs, Work<T>& w, int k_start) {
                 load4(cw + 4 * (8 * c + 4 + av), s0, s1, s2, s3);
                 const T t0 = zr[m][0] * q0 + zr[m][1] * q1 + zr[m][2] * q2;
                 const T t1 = zr[m][0] * s0 + zr[m][1] * s1 + zr[m][2] * s2;
-                const int mx = iv > jw ? iv : jw;
-                T e = (T)2 * ((T)(H - mx) * t0 + w.St[iv * H + jw] * t1);
+                T n2w, s2w;
+                load2(w.NS2 + 2 * (iv * H + jw), n2w, s2w);        // 2 N_ij, 2 S_ij
+                T e = n2w * t0 + s2w * t1;
                 // same foot-step (and same dead flag): R term / unit diagonal - branch-free (every lane executes a
                 // divergent branch body anyway as soon as one lane takes it)
                 const bool same = ((ri[m] ^ ci[c]) >> 16) == 0;
                 const T* zw = w.zt + 3 * (k0 + c);
-                const T* r2 = w.r2 + 3 * av;
-                const T rterm = (zr[m][0] * zw[0]) * r2[0] + (zr[m][1] * zw[1]) * r2[1] + (zr[m][2] * zw[2]) * r2[2];
-                e += same ? rterm : (T)0;
-                e = (same && dead && v == k0 + c) ? (T)1 : e;
+                const T rterm = zq[m][0] * zw[0] + zq[m][1] * zw[1] + zq[m][2] * zw[2];
+                e += wp::sel(same, rterm, (T)0);
+                e = wp::sel(same && dead && v == k0 + c, (T)1, e);
                 acc[m][c] = e;
             }
+        }
         }
         // ---- left-looking update with all previous columns
         const T* colg;
         {
+            MPCQ_PHASE(11);
             const T* col = L;
             int stride = n;
-            for (int g = 0; g < (k0 >> 2); ++g) {
+            // software-pipelined over groups of 4 columns: the loads of group g + 1 are issued before the multiply-adds
+            // of group g (a lone warp otherwise waits out the shared-memory latency once per group)
+            const int ng = k0 >> 2;
+            if constexpr (NSLOT > 2) {                        // many rows per thread: enough independent work, keep registers
+                for (int g = 0; g < ng; ++g) {
+                    MPCQ_UNROLL
+                    for (int t = 0; t < 4; ++t) {
+                        T p0, p1, p2, p3;
+                        load4(col + k0, p0, p1, p2, p3);
+                        MPCQ_UNROLL
+                        for (int m = 0; m < NSLOT; ++m) {
+                            if (m < m0) continue;
+                            const T lr = col[row0 + RSTEP * m];
+                            acc[m][0] -= lr * p0; acc[m][1] -= lr * p1; acc[m][2] -= lr * p2; acc[m][3] -= lr * p3;
+                        }
+                        col += stride;
+                    }
+                    col -= 4;
+                    stride -= 4;
+                }
+            } else {
+            T pa[4][4], la[4][NSLOT], pb[4][4], lb[4][NSLOT];   // two register sets, used alternately (no copies)
+            auto fetch = [&](T (&p)[4][4], T (&l)[4][NSLOT], const T* cc, int st) {
                 MPCQ_UNROLL
                 for (int t = 0; t < 4; ++t) {
-                    T p0, p1, p2, p3;
-                    load4(col + k0, p0, p1, p2, p3);
+                    load4(cc + k0, p[t][0], p[t][1], p[t][2], p[t][3]);
+                    MPCQ_UNROLL
+                    for (int m = 0; m < NSLOT; ++m)
+                        if (m >= m0) l[t][m] = cc[row0 + RSTEP * m];
+                    cc += st;
+                }
+            };
+            auto apply = [&](const T (&p)[4][4], const T (&l)[4][NSLOT]) {
+                MPCQ_UNROLL
+                for (int t = 0; t < 4; ++t) {
                     MPCQ_UNROLL
                     for (int m = 0; m < NSLOT; ++m) {
                         if (m < m0) continue;
-                        const T lr = col[row0 + RSTEP * m];
-                        acc[m][0] -= lr * p0; acc[m][1] -= lr * p1; acc[m][2] -= lr * p2; acc[m][3] -= lr * p3;
+                        const T lr = l[t][m];
+                        acc[m][0] -= lr * p[t][0]; acc[m][1] -= lr * p[t][1]; acc[m][2] -= lr * p[t][2]; acc[m][3] -= lr * p[t][3];
                     }
-                    col += stride;
                 }
-                col -= 4;
-                stride -= 4;
+            };
+            if (ng > 0) fetch(pa, la, col, stride);
+            int g = 0;
+            for (; g + 1 < ng; g += 2) {
+                col += 4 * stride - 4; stride -= 4;
+                fetch(pb, lb, col, stride);
+                apply(pa, la);
+                col += 4 * stride - 4; stride -= 4;
+                if (g + 2 < ng) fetch(pa, la, col, stride);
+                apply(pb, lb);
+            }
+            if (g < ng) {
+                apply(pa, la);
+                col += 4 * stride - 4; stride -= 4;
+            }
             }
             colg = col;                                       // == L + colbase(k0, n)
         }
         // ---- 4x4 diagonal block: kept, or factored by the warp that owns its rows and published through dblk
         if (!keep_diag) {
+            MPCQ_PHASE(12);
             const int kb = k0 >> 2, q = kb / NW;
             if (wid == kb - q * NW) {
                 const int ld = 4 * (q & 7), md = q >> 3;
@@ -582,6 +671,7 @@ MPCQ_DEV bool chol_factor(const Consts& cs, Work<T>& w, int k_start) {
             }
             team::sync(w.t);                                    // dblk visible to the team
         }
+        MPCQ_PHASE(13);
         T m10, m20, m21, m30, m31, m32, m00, m11, m22, m33, pad0, pad1;
         {
             const T* db = w.dblk + 3 * k0;
@@ -599,9 +689,9 @@ MPCQ_DEV bool chol_factor(const Consts& cs, Work<T>& w, int k_start) {
                 if (m < m0) continue;
                 const int dv = v - k0;
                 const T x0 = m00 * acc[m][0];
-                const T x1 = dv >= 1 ? m10 * acc[m][0] + m11 * acc[m][1] : (T)0;
-                const T x2 = dv >= 2 ? (m20 * acc[m][0] + m21 * acc[m][1]) + m22 * acc[m][2] : (T)0;
-                const T x3 = dv >= 3 ? (m30 * acc[m][0] + m31 * acc[m][1]) + (m32 * acc[m][2] + m33 * acc[m][3]) : (T)0;
+                const T x1 = wp::sel(dv >= 1, m10 * acc[m][0] + m11 * acc[m][1], (T)0);
+                const T x2 = wp::sel(dv >= 2, (m20 * acc[m][0] + m21 * acc[m][1]) + m22 * acc[m][2], (T)0);
+                const T x3 = wp::sel(dv >= 3, (m30 * acc[m][0] + m31 * acc[m][1]) + (m32 * acc[m][2] + m33 * acc[m][3]), (T)0);
                 if (v >= row_lo && v < n) {
                     c0[v] = x0;
                     c0[stride + v] = x1;
@@ -612,6 +702,14 @@ MPCQ_DEV bool chol_factor(const Consts& cs, Work<T>& w, int k_start) {
         }
         if (wid == 0 && k0 + 4 < n) write_cw(k0 + 4, w.cw + 128 * (((k0 >> 2) + 1) & 1));
         team::sync(w.t);                                        // panel columns + next cw visible
+    };
+    for (int k0 = 0; k0 < n; k0 += 4) {
+        const int row_lo = k0 < k_start ? k_start : k0;
+        if constexpr (NSLOT == 2) {
+            if (row_lo >= RSTEP) panel(k0, IntC<1>{}); else panel(k0, IntC<0>{});
+        } else {
+            panel(k0, IntC<-1>{});
+        }
     }
     return team::any(w.t, !ok) == false;
 }
@@ -633,10 +731,13 @@ MPCQ_DEV void tri_solve(Work<T>& w) {
         bv[m] = v < n ? w.vec[v] : (T)0;
         cbv[m] = v < n ? colbase(v, n) : 0;
     }
-    // forward: L y = b
-    for (int k0 = 0; k0 < n; k0 += 4) {
-        const int md = k0 >> 5, ld = k0 & 31;
-        const T mine = pick<T, NSLOT>(bv, md);
+    // One 4-column block of the forward / backward sweep.  MD = the slot that holds the block's rows when known at compile
+    // time (NSLOT == 2: slots below MD in the forward sweep / above MD in the backward sweep hold no row that still
+    // changes, and are not even issued); MD = -1: generic.
+    auto fwd = [&](int k0, auto mdc) {
+        constexpr int MD = decltype(mdc)::value;
+        const int md = MD >= 0 ? MD : (k0 >> 5), ld = k0 & 31;
+        const T mine = MD >= 0 ? bv[MD >= 0 ? MD : 0] : pick<T, NSLOT>(bv, md);
         const T b0 = wp::shfl(mine, ld), b1 = wp::shfl(mine, ld + 1), b2 = wp::shfl(mine, ld + 2), b3 = wp::shfl(mine, ld + 3);
         T m10, m20, m21, m30, m31, m32, m00, m11, m22, m33, pad0, pad1;
         const T* db = w.dblk + 3 * k0;
@@ -650,21 +751,21 @@ MPCQ_DEV void tri_solve(Work<T>& w) {
         const int stride = n - k0;
         const T* c0 = L + colbase(k0, n);
         MPCQ_UNROLL
-        for (int m = 0; m < NSLOT; ++m) {
+        for (int m = (MD >= 0 ? MD : 0); m < NSLOT; ++m) {
             const int v = lane + 32 * m;
-            const int sel = v - k0;
-            const bool upd = sel >= 4 && v < n;
+            const int dv = v - k0;
+            const bool upd = dv >= 4 && v < n;
             const T l0 = upd ? c0[v] : (T)0, l1 = upd ? c0[stride + v] : (T)0;
             const T l2 = upd ? c0[2 * stride + v] : (T)0, l3 = upd ? c0[3 * stride + v] : (T)0;
             const T contrib = (l0 * y0 + l1 * y1) + (l2 * y2 + l3 * y3);
-            const T yv = sel == 0 ? y0 : (sel == 1 ? y1 : (sel == 2 ? y2 : y3));
-            bv[m] = (sel >= 0 && sel < 4) ? yv : bv[m] - contrib;
+            const T yv = wp::sel(dv < 2, wp::sel(dv == 0, y0, y1), wp::sel(dv == 2, y2, y3));
+            bv[m] = wp::sel((unsigned)dv < 4u, yv, bv[m] - contrib);
         }
-    }
-    // backward: L' x = y
-    for (int k0 = n - 4; k0 >= 0; k0 -= 4) {
-        const int md = k0 >> 5, ld = k0 & 31;
-        const T mine = pick<T, NSLOT>(bv, md);
+    };
+    auto bwd = [&](int k0, auto mdc) {
+        constexpr int MD = decltype(mdc)::value;
+        const int md = MD >= 0 ? MD : (k0 >> 5), ld = k0 & 31;
+        const T mine = MD >= 0 ? bv[MD >= 0 ? MD : 0] : pick<T, NSLOT>(bv, md);
         const T b0 = wp::shfl(mine, ld), b1 = wp::shfl(mine, ld + 1), b2 = wp::shfl(mine, ld + 2), b3 = wp::shfl(mine, ld + 3);
         T m10, m20, m21, m30, m31, m32, m00, m11, m22, m33, pad0, pad1;
         const T* db = w.dblk + 3 * k0;
@@ -676,17 +777,25 @@ MPCQ_DEV void tri_solve(Work<T>& w) {
         const T x1 = (m11 * b1 + m21 * b2) + m31 * b3;
         const T x0 = (m00 * b0 + m10 * b1) + (m20 * b2 + m30 * b3);
         MPCQ_UNROLL
-        for (int m = 0; m < NSLOT; ++m) {
+        for (int m = 0; m < (MD >= 0 ? MD + 1 : NSLOT); ++m) {
             const int v = lane + 32 * m;
-            const int sel = v - k0;
+            const int dv = v - k0;
             T a0, a1, a2, a3;
             load4(L + cbv[m] + k0, a0, a1, a2, a3);              // L[k0..k0+3, v]; any row >= k0 reads in-bounds garbage, masked below
-            const bool upd = sel < 0;
-            a0 = upd ? a0 : (T)0; a1 = upd ? a1 : (T)0; a2 = upd ? a2 : (T)0; a3 = upd ? a3 : (T)0;
             const T contrib = (a0 * x0 + a1 * x1) + (a2 * x2 + a3 * x3);
-            const T xv = sel == 0 ? x0 : (sel == 1 ? x1 : (sel == 2 ? x2 : x3));
-            bv[m] = (sel >= 0 && sel < 4) ? xv : bv[m] - contrib;
+            const T xv = wp::sel(dv < 2, wp::sel(dv == 0, x0, x1), wp::sel(dv == 2, x2, x3));
+            bv[m] = wp::sel(dv < 0, bv[m] - contrib, wp::sel(dv < 4, xv, bv[m]));
         }
+    };
+    if constexpr (NSLOT == 2) {
+        const int nlo = n < 32 ? n : 32;
+        for (int k0 = 0; k0 < nlo; k0 += 4) fwd(k0, IntC<0>{});
+        for (int k0 = 32; k0 < n; k0 += 4) fwd(k0, IntC<1>{});
+        for (int k0 = n - 4; k0 >= 32; k0 -= 4) bwd(k0, IntC<1>{});
+        for (int k0 = nlo - 4; k0 >= 0; k0 -= 4) bwd(k0, IntC<0>{});
+    } else {
+        for (int k0 = 0; k0 < n; k0 += 4) fwd(k0, IntC<-1>{});
+        for (int k0 = n - 4; k0 >= 0; k0 -= 4) bwd(k0, IntC<-1>{});
     }
     MPCQ_UNROLL
     for (int m = 0; m < NSLOT; ++m) {
@@ -756,27 +865,27 @@ MPCQ_DEV void apply_step(const Consts& cs, Work<T>& w) {
 template <class T, int NSLOT>
 MPCQ_DEV double refine(const Consts& cs, Work<T>& w, double tol_abs, bool u_is_zero, bool use_cg) {
     const int lane = w.t.tid;
-    if (u_is_zero) {
-        for (int idx = lane; idx < w.nv; idx += w.t.nt) w.gam[idx] = w.g[idx];
-        team::sync(w.t);
-    } else {
-        hess_apply(cs, w);
-    }
-    double rmax = reduced_gradient(cs, w);                            // r = -Z' gam -> vec
     // Plain refinement (u += Z M^-1 r) first: with an accurate factor it gains 2-3 digits per step and is the cheapest.
     // Intermediate active-set rounds (use_cg = false) stop there - they only need the faces right.
+    // (one hess_apply site serves the initial gradient and the refinement steps: the function is inlined, code size matters)
+    double rmax = 0.0;
     {
         double prev = 0.0;
         const int cap = use_cg ? cs.refine_max : 3;
-        int it = 0;
-        for (; rmax > tol_abs && it < cap; ++it) {
+        for (int it = 0;; ++it) {
+            if (it == 0 && u_is_zero) {
+                for (int idx = lane; idx < w.nv; idx += w.t.nt) w.gam[idx] = w.g[idx];
+                team::sync(w.t);
+            } else {
+                hess_apply(cs, w);
+            }
+            rmax = reduced_gradient(cs, w);                          // r = -Z' gam -> vec
+            if (!(rmax > tol_abs && it < cap)) break;
             if (it > 0 && rmax > 0.2 * prev) break;              // converging too slowly: hand over to CG
             prev = rmax;
             if (w.t.wid == 0) tri_solve<T, NSLOT>(w);
             team::sync(w.t);
             apply_step(cs, w);
-            hess_apply(cs, w);
-            rmax = reduced_gradient(cs, w);
         }
         if (!use_cg || rmax <= tol_abs) return rmax;
     }
@@ -954,16 +1063,20 @@ MPCQ_DEV int reorder_feet(Work<T>& w) {
 
 // one factor-and-solve on the current faces: u = argmin on the faces (to tol), gam = Hu+g
 template <class T, int NCAP, int NW>
-MPCQ_DEV bool face_solve(const Consts& cs, Work<T>& w, double tol_abs, double& rmax, bool use_cg) {
+MPCQ_DEV bool face_solve(const Consts& cs, Work<T>& w, double tol_abs, double& rmax, bool use_cg, bool same_factor) {
     constexpr int NFS = (NCAP / 3 + 31) / 32;
+    bool ok = true, cnz = true;
+    if (!same_factor) {
     int k_start = 0;
     if (w.t.wid == 0) k_start = reorder_feet<T, NFS>(w);        // one warp permutes the stance list ...
     k_start = team::bcast(w.t, k_start);                           // ... and the team learns the restart column
 #if defined(MPCQ_HOST_EMU) && defined(MPCQ_TRACE)
     if (w.t.tid == 0) printf("   face_solve: k_start %d of n %d\n", k_start, w.n);
 #endif
-    const bool cnz = build_slots(cs, w);
-    const bool ok = k_start < w.n ? chol_factor<T, NCAP, NW>(cs, w, k_start) : true;
+    cnz = build_slots(cs, w);
+    ok = k_start < w.n ? chol_factor<T, NCAP, NW>(cs, w, k_start) : true;
+    }
+    // same_factor: faces and factor are those of the previous call and u is its solution - only improve it (to a tighter tol)
     rmax = refine<T, NCAP / 32>(cs, w, tol_abs, !cnz, use_cg);
     return ok;
 }
@@ -1200,54 +1313,64 @@ MPCQ_DEV void solve_env(const Consts& cs, const IO<T>& io, int b, char* smem, T*
             for (int idx = lane; idx < w.nv; idx += w.t.nt) w.u[idx] = 0.0;
             team::sync(w.t);
         }
-        // ---- primal-dual active-set rounds
-        for (int round = 0; round <= cs.pdas_cap && numeric_ok && !done; ++round) {
-            numeric_ok = face_solve<T, NCAP, NW>(cs, w, tol_loose, rmax, false) && numeric_ok;
-            ++nfac;
-            FaceCheck fc = pdas_update(cs, w, false);
-            if (fc.n_primal == 0 && fc.n_dual == 0) {
-                rmax = refine<T, NSLOT>(cs, w, tol_tight, false, true);   // tighten on the same factor (CG), re-test
-                fc = pdas_update(cs, w, false);
-                if (fc.n_primal == 0 && fc.n_dual == 0) {
+        // ---- ONE loop drives both methods, so that the factor-and-solve code exists once in the kernel (it is the bulk of
+        // the code and the kernel stalls on instruction fetch when warps run different copies of it):
+        //   PDAS   primal-dual active-set rounds: solve on the current faces (loose tolerance), test every foot, move all
+        //          offending feet at once;
+        //   TIGHT  no violation left: refine on the same factor to the tight tolerance, re-test -> verified, or back to PDAS;
+        //   AS     fallback after pdas_cap rounds - monotone projected active-set method.  Keeps a FEASIBLE iterate ucur
+        //          whose objective strictly decreases: from the face minimiser u either (a) u is feasible -> take it and
+        //          release every wrong-signed multiplier, or (b) the clamped point clamp(u) lowers the objective -> take it
+        //          with the faces it lands on (many rows change at once), or (c) step to the first blocking row (ratio test).
+        enum { M_PDAS = 0, M_TIGHT = 1, M_AS = 2 };
+        int mode = M_PDAS, round = 0;
+        double phi_cur = 0.0;
+        bool need_phi = false;
+        while (numeric_ok && !done) {
+            if (mode == M_AS && need_phi) { phi_cur = objective_of(cs, w, w.ucur); need_phi = false; }
+            const bool tight = mode != M_PDAS;
+            numeric_ok = face_solve<T, NCAP, NW>(cs, w, tight ? tol_tight : tol_loose, rmax, tight, mode == M_TIGHT) && numeric_ok;
+            if (mode != M_TIGHT) ++nfac;
+            if (mode != M_AS) {
+                const FaceCheck fc = pdas_update(cs, w, false);
+                const bool clean = fc.n_primal == 0 && fc.n_dual == 0;
+                if (clean && mode == M_PDAS) { mode = M_TIGHT; continue; }          // tighten on the same factor (CG), re-test
+                if (clean) {
                     // verified only with the stationarity residual actually at tolerance (a NaN fails this test)
                     if (rmax <= 10.0 * tol_tight) done = true; else numeric_ok = false;
                     break;
                 }
-            }
 #if defined(MPCQ_HOST_EMU) && defined(MPCQ_TRACE)
-            if (lane == 0) printf(" PDAS round %d: primal %d dual %d rmax %.2e\n", round, fc.n_primal, fc.n_dual, rmax);
+                if (lane == 0) printf(" PDAS round %d: primal %d dual %d rmax %.2e\n", round, fc.n_primal, fc.n_dual, rmax);
 #endif
-            pdas_update(cs, w, true);
-        }
-        // ---- fallback: monotone projected active-set method.  Keeps a FEASIBLE iterate ucur whose objective
-        // strictly decreases: from the face minimiser u either (a) u is feasible -> take it and release every
-        // wrong-signed multiplier, or (b) the clamped point clamp(u) lowers the objective -> take it with the
-        // faces it lands on (many rows change at once), or (c) step to the first blocking row (ratio test).
-        if (!done && numeric_ok) {
-            status |= ST_FALLBACK;
-            clamp_into(cs, w, w.u, w.ucur, w.face);
-            double phi_cur = objective_of(cs, w, w.ucur);
-            for (nas = 1; nas <= cs.as_cap; ++nas) {
-                numeric_ok = face_solve<T, NCAP, NW>(cs, w, tol_tight, rmax, true) && numeric_ok;
-                ++nfac;
+                mode = M_PDAS;
                 if (!numeric_ok) break;
-                double alpha;
-                int tag;
-                ratio_test(cs, w, alpha, tag);
+                if (round++ < cs.pdas_cap) { pdas_update(cs, w, true); continue; }
+                // the rounds cycle: hand over to the monotone method, started from the clamped last iterate (clamp_into
+                // derives the faces from the point)
+                status |= ST_FALLBACK;
+                clamp_into(cs, w, w.u, w.ucur, w.face);
+                mode = M_AS; need_phi = true; nas = 1;
+                continue;
+            }
+            // ---- AS iteration nas
+            if (!numeric_ok) break;
+            double alpha;
+            int tag;
+            ratio_test(cs, w, alpha, tag);
 #if defined(MPCQ_HOST_EMU) && defined(MPCQ_TRACE)
-                if (lane == 0) printf("  AS it %d: alpha %.3e tag %d phi_cur %.10e rmax %.2e\n", nas, alpha, tag, phi_cur, rmax);
+            if (lane == 0) printf("  AS it %d: alpha %.3e tag %d phi_cur %.10e rmax %.2e\n", nas, alpha, tag, phi_cur, rmax);
 #endif
-                if (tag == 0x7fffffff) {                    // (a)
-                    for (int idx = lane; idx < w.nv; idx += w.t.nt) w.ucur[idx] = w.u[idx];
-                    phi_cur = objective(cs, w);
-                    if (!(rmax <= 10.0 * tol_tight)) { numeric_ok = false; break; }   // the factor cannot deliver the residual
-                    const FaceCheck fc = pdas_update(cs, w, true);
+            if (tag == 0x7fffffff) {                    // (a)
+                for (int idx = lane; idx < w.nv; idx += w.t.nt) w.ucur[idx] = w.u[idx];
+                phi_cur = objective(cs, w);
+                if (!(rmax <= 10.0 * tol_tight)) { numeric_ok = false; break; }   // the factor cannot deliver the residual
+                const FaceCheck fc = pdas_update(cs, w, true);
 #if defined(MPCQ_HOST_EMU) && defined(MPCQ_TRACE)
-                    if (lane == 0) printf("     feasible minimiser: primal %d dual %d\n", fc.n_primal, fc.n_dual);
+                if (lane == 0) printf("     feasible minimiser: primal %d dual %d\n", fc.n_primal, fc.n_dual);
 #endif
-                    if (fc.n_primal == 0 && fc.n_dual == 0) { done = true; break; }
-                    continue;
-                }
+                if (fc.n_primal == 0 && fc.n_dual == 0) { done = true; break; }
+            } else {
                 clamp_into(cs, w, w.u, w.utrial, w.face2);
                 const double phi_t = objective_of(cs, w, w.utrial);
 #if defined(MPCQ_HOST_EMU) && defined(MPCQ_TRACE)
@@ -1262,14 +1385,14 @@ MPCQ_DEV void solve_env(const Consts& cs, const IO<T>& io, int b, char* smem, T*
                     block_all_at_zero(cs, w);
                 } else {                                    // (c)
                     blocked_step(cs, w, alpha, tag);
-                    phi_cur = objective_of(cs, w, w.ucur);
+                    need_phi = true;
                 }
             }
-            if (!done) {                                   // return the feasible iterate
-                for (int idx = lane; idx < w.nv; idx += w.t.nt) w.u[idx] = w.ucur[idx];
-                team::sync(w.t);
-                hess_apply(cs, w);
-            }
+            if (++nas > cs.as_cap) break;
+        }
+        if (mode == M_AS && !done && numeric_ok) {          // iteration cap: return the feasible iterate
+            for (int idx = lane; idx < w.nv; idx += w.t.nt) w.u[idx] = w.ucur[idx];
+            team::sync(w.t);
         }
         if (done) status |= ST_VERIFIED; else status |= numeric_ok ? ST_MAXITER : ST_NUMERIC;
         if (!done && !numeric_ok) {                            // never hand out the debris of a numerical breakdown

@@ -16,6 +16,7 @@
 #define MPCQ_DEV inline
 #define MPCQ_HD inline
 #define MPCQ_UNROLL
+#define MPCQ_NOUNROLL
 namespace mpcq_emu {
 int lane_id();                            // lane within the warp
 int thread_id();                          // thread within the team (CTA)
@@ -27,6 +28,7 @@ void team_barrier();                      // all threads of the team
 #define MPCQ_DEV __device__ __forceinline__
 #define MPCQ_HD __host__ __device__ inline
 #define MPCQ_UNROLL _Pragma("unroll")
+#define MPCQ_NOUNROLL _Pragma("unroll 1")
 #endif
 
 namespace wp {
@@ -65,12 +67,35 @@ MPCQ_DEV int popc(unsigned x) { return __popc(x); }
 // within 1 ulp with a much shorter dependency chain than 1 / sqrt (the pivot chain is the serial part of the
 // panel factorisation)
 MPCQ_DEV float rsqrt_(float x) {
-    const float y = rsqrtf(x);
+    float y;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));   // bare MUFU.RSQ: pivots are normal numbers (checked > 0 before)
     return y * (1.5f - 0.5f * x * y * y);
 }
 MPCQ_DEV double rsqrt_(double x) {
     const double y = rsqrt(x);
     return y * (1.5 - 0.5 * x * y * y);
+}
+#endif
+
+// sel(p, a, b) = p ? a : b as ONE select instruction.  nvcc turns nested ternaries on per-lane predicates into divergent
+// branch regions (BSSY / BRA / BSYNC) - measured in the triangular sweeps - so the hot loops spell the select out.
+#ifdef MPCQ_HOST_EMU
+template <class V> MPCQ_DEV V sel(bool p, V a, V b) { return p ? a : b; }
+#else
+MPCQ_DEV float sel(bool p, float a, float b) {
+    float r;
+    asm("{ .reg .pred q; setp.ne.s32 q, %3, 0; selp.f32 %0, %1, %2, q; }" : "=f"(r) : "f"(a), "f"(b), "r"((int)p));
+    return r;
+}
+MPCQ_DEV double sel(bool p, double a, double b) {
+    double r;
+    asm("{ .reg .pred q; setp.ne.s32 q, %3, 0; selp.f64 %0, %1, %2, q; }" : "=d"(r) : "d"(a), "d"(b), "r"((int)p));
+    return r;
+}
+MPCQ_DEV int sel(bool p, int a, int b) {
+    int r;
+    asm("{ .reg .pred q; setp.ne.s32 q, %3, 0; selp.s32 %0, %1, %2, q; }" : "=r"(r) : "r"(a), "r"(b), "r"((int)p));
+    return r;
 }
 #endif
 

@@ -157,6 +157,11 @@ int run(const mpcq_config* cfg, int B, const T* x0, const T* yaw, const T* feet,
 }  // namespace
 
 extern "C" {
+// read and clear the phase-call counters (thread 0 of every team): 0 setup 1 hess_apply 2 build_slots 3 chol_factor
+// 4 tri_solve 5 reduced_gradient 6 apply_step 7 pdas_update 8 reorder_feet 9 solve_env
+void mpcq_emu_phase_calls(long* out16) {
+    for (int i = 0; i < 16; ++i) { out16[i] = mpcq::g_emu_phase_calls[i]; mpcq::g_emu_phase_calls[i] = 0; }
+}
 int mpcq_emu_solve_f32(const mpcq_config* cs, int B, const float* x0, const float* yaw, const float* feet, const float* gait,
                        const float* xref, float* f_out, float* u_full, int32_t* iters, double* resid, int32_t* status,
                        uint8_t* active) {
