@@ -27,10 +27,11 @@ constexpr int kGlobalCtas = 148 * 2;       // resident CTAs of a class whose fac
 template <int NCAP> struct TeamWarps { static constexpr int value = NCAP <= 64 ? MPCQ_NW0 : (NCAP <= 128 ? MPCQ_NW1 : (NCAP <= 192 ? MPCQ_NW2 : MPCQ_NW3)); };
 
 template <class T, int NCAP, bool LGLOBAL>
-// small class: shared memory allows 11 one-warp teams per SM (fp32), so cap the registers at 65536 / (11 * 32) -> 184
+// small class: shared memory allows 12 one-warp teams per SM (fp32, 18 432 B each), so cap the registers at
+// 65536 / (12 * 32) -> 168
 // (with 2-warp teams: 12 teams = 24 warps per SM)
 #ifndef MPCQ_MINB0
-#define MPCQ_MINB0 (MPCQ_NW0 > 1 ? 12 : (sizeof(T) == 4 ? 11 : 1))
+#define MPCQ_MINB0 (MPCQ_NW0 > 1 ? 12 : (sizeof(T) == 4 ? 12 : 1))
 #endif
 __global__ void __launch_bounds__(32 * TeamWarps<NCAP>::value, NCAP <= 64 ? MPCQ_MINB0 : 1)
 mpcq_solve_kernel(const __grid_constant__ Consts cs, const __grid_constant__ IO<T> io, T* gws, size_t gws_stride,
@@ -321,10 +322,10 @@ cudaError_t configure(mpcq_handle* h) {
     for (int ci = 0; ci < h->ncls; ++ci) {
         const int ncap = mpcq::kClasses[ci].ncap;
         const int nmax = mpcq::class_nmax(mpcq::kClasses[ci]);
-        size_t s = mpcq::work_bytes<T>(H, ncap, true, false, nmax);
+        size_t s = mpcq::work_bytes<T>(H, ncap, true, false, nmax, mpcq::kClasses[ci].nw);
         h->lglobal[ci] = s > kMaxSmem || ncap >= 384;
         if (h->lglobal[ci]) {
-            s = mpcq::work_bytes<T>(H, ncap, false, false, nmax);
+            s = mpcq::work_bytes<T>(H, ncap, false, false, nmax, mpcq::kClasses[ci].nw);
             if (s > kMaxSmem) return cudaErrorInvalidValue;
             size_t need = (size_t)mpcq::l_elems(ncap);
             need = (need + 31) / 32 * 32;

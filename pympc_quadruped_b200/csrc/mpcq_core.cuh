@@ -115,57 +115,69 @@ template <class T> struct Work {
     team::Ctx t;             // the team of warps that owns this environment
 };
 
-template <class T>
-MPCQ_HD constexpr size_t work_bytes(int H, int ncap, bool l_in_smem, bool with_md = false, int nmax = 0) {
-    size_t nd = (with_md ? 288 : 0) + 72 + 2 * 12 * (size_t)H + 6 * (size_t)ncap + ncap / 3 + 1 + 12 + 40;
-    size_t nt = (l_in_smem ? l_elems(nmax > 0 ? nmax : ncap) : 0) + 3 * (ncap / 4) * 4 + ncap + 256 + 3 * ncap + 288 + 2 * (size_t)H * H + 12;
-    size_t nb = (ncap / 3 + 1) * 11 + 4 * (size_t)H + 16 + 4 * (size_t)ncap;
-    return align_up(nd * 8, 16) + align_up(nt * sizeof(T), 16) + align_up(nb, 16);
+// Shared-memory layout of one team's workspace.  nvc = capacity of everything indexed by slot (the largest system of the
+// size class, `nmax`, or `ncap` when not given); cw is double-buffered only for multi-warp teams.  The small class must
+// stay within 18 432 B (fp32) so that 12 one-warp teams fit in the 228 KB of an SM (12 x (18 432 + 1 024 reserved)).
+struct Layout { size_t nd, nt, nb; int nvc, cw; };
+MPCQ_HD constexpr Layout layout(int H, int ncap, bool l_in_smem, bool with_md, int nmax, int nw) {
+    Layout l{};
+    l.nvc = nmax > 0 ? nmax : ncap;
+    l.cw = nw > 1 ? 256 : 128;
+    const size_t nv = (size_t)l.nvc;
+    l.nd = (with_md ? 288 : 0) + 72 + 9 * (size_t)H + 12 * (size_t)H + 6 * nv + nv / 3 + 1 + 12 + 40;
+    l.nt = (l_in_smem ? (size_t)l_elems(l.nvc) : 0) + 3 * nv + nv + (size_t)l.cw + 3 * nv + 288 + 12 + 2 * (size_t)H * H;
+    l.nb = (nv / 3 + 1) * 11 + 4 * (size_t)H + 16 + 4 * nv;
+    return l;
 }
 
 template <class T>
-MPCQ_DEV void carve(Work<T>& w, char* base, T* l_global, int H, int ncap, bool with_md = false, int nmax = 0) {
+MPCQ_HD constexpr size_t work_bytes(int H, int ncap, bool l_in_smem, bool with_md = false, int nmax = 0, int nw = 2) {
+    const Layout l = layout(H, ncap, l_in_smem, with_md, nmax, nw);
+    return align_up(l.nd * 8, 16) + align_up(l.nt * sizeof(T), 16) + align_up(l.nb, 16);
+}
+
+template <class T>
+MPCQ_DEV void carve(Work<T>& w, char* base, T* l_global, int H, int ncap, bool with_md = false, int nmax = 0, int nw = 2) {
+    const Layout l = layout(H, ncap, l_global == nullptr, with_md, nmax, nw);
+    const int nv = l.nvc;
     double* d = reinterpret_cast<double*>(base);
     w.Md = with_md ? d : nullptr; d += with_md ? 288 : 0;
     w.GW = d; d += 72;
-    w.g = d; d += ncap;
-    w.u = d; d += ncap;
-    w.gam = d; d += ncap;
-    w.P0 = d; d += 12 * H;       // 9H used by hess_apply, 12H by setup_model
-    w.P1 = d; d += 12 * H;
-    w.ucur = d; d += ncap;
-    w.utrial = d; d += ncap;
-    w.hd = d; d += ncap;
-    w.fmax = d; d += ncap / 3 + 1;
+    w.g = d; d += nv;
+    w.u = d; d += nv;
+    w.gam = d; d += nv;
+    w.P0 = d; d += 9 * H;        // hess_apply stage 1
+    w.P1 = d; d += 12 * H;       // hess_apply stage 2; setup_model keeps its suffix sums here
+    w.ucur = d; d += nv;
+    w.utrial = d; d += nv;
+    w.hd = d; d += nv;
+    w.fmax = d; d += nv / 3 + 1;
     w.t.red = d; d += 8;
     w.t.redi = reinterpret_cast<int*>(d); d += 4;
     w.zero3 = d; d += 4;
     w.hs = d; d += 12;
     w.hq = d; d += 12;
     w.rd = d; d += 12;
-    size_t nd = (with_md ? 288 : 0) + 72 + 2 * 12 * (size_t)H + 6 * (size_t)ncap + ncap / 3 + 1 + 12 + 40;
-    T* t = reinterpret_cast<T*>(base + align_up(nd * 8, 16));
-    size_t used = 0;
+    T* t = reinterpret_cast<T*>(base + align_up(l.nd * 8, 16));
     if (l_global) {
         w.L = l_global;
     } else {
-        const int le = l_elems(nmax > 0 ? nmax : ncap);
-        w.L = t; t += le; used += le;
+        w.L = t; t += l_elems(nv);
     }
-    w.dblk = t; t += 3 * (ncap / 4) * 4; used += 3 * (ncap / 4) * 4;
-    w.vec = t; t += ncap; used += ncap;
-    w.cw = t; t += 256; used += 256;
-    w.zt = t; t += 3 * ncap; used += 3 * ncap;
-    w.Mf = t; t += 288; used += 288;
-    w.r2 = t; t += 12; used += 12;
-    w.NS2 = t; t += 2 * H * H; used += 2 * (size_t)H * H;
-    uint8_t* b = reinterpret_cast<uint8_t*>(base + align_up(nd * 8, 16) + align_up(used * sizeof(T), 16));
-    w.fk = b; b += ncap / 3 + 1;
-    w.fo = b; b += ncap / 3 + 1;
+    w.dblk = t; t += 3 * nv;     // 12 values per block of 4 columns
+    w.vec = t; t += nv;
+    w.cw = t; t += l.cw;
+    w.zt = t; t += 3 * nv;
+    w.Mf = t; t += 288;
+    w.r2 = t; t += 12;
+    w.NS2 = t; t += 2 * H * H;
+    uint8_t* b = reinterpret_cast<uint8_t*>(base + align_up(l.nd * 8, 16) + align_up(l.nt * sizeof(T), 16));
+    w.fk = b; b += nv / 3 + 1;
+    w.fo = b; b += nv / 3 + 1;
     w.cidx = b; b += 4 * H;
-    w.face = reinterpret_cast<int8_t*>(b); b += 3 * (ncap / 3 + 1);
-    w.face2 = reinterpret_cast<int8_t*>(b); b += 3 * (ncap / 3 + 1);
-    w.facef = reinterpret_cast<int8_t*>(b); b += 3 * (ncap / 3 + 1);
+    w.face = reinterpret_cast<int8_t*>(b); b += 3 * (nv / 3 + 1);
+    w.face2 = reinterpret_cast<int8_t*>(b); b += 3 * (nv / 3 + 1);
+    w.facef = reinterpret_cast<int8_t*>(b); b += 3 * (nv / 3 + 1);
     w.sinf = reinterpret_cast<int32_t*>(reinterpret_cast<uintptr_t>(b + 15) & ~uintptr_t(15));
     w.H = H;
 }
@@ -346,15 +358,14 @@ MPCQ_DEV void setup_model(const Consts& cs, Work<T>& w, const T* x0p, double yaw
             const double qe = cs.q[cidx] * (xc + t * acx + 0.5 * t * t * ac2x - (double)xrefp[13 * j + cidx]);
             E1 = E1 + E0 + 0.5 * qe;
             E0 = E0 + qe;
-            w.P0[12 * j + cidx] = E0;
-            w.P1[12 * j + cidx] = E1;
+            w.P1[12 * j + cidx] = cidx < 6 ? E1 : E0;           // only E1[0:6] and E0[6:12] are used below
         }
     }
     team::sync(w.t);
     for (int v = lane; v < w.nv; v += w.t.nt) {
         const int p = v / 3, y = v - 3 * p, j = w.fk[p] >> 2, a = w.fk[p] & 3;
-        const double* E0 = w.P0 + 12 * j;
-        const double* E1 = w.P1 + 12 * j;
+        const double* E0 = w.P1 + 12 * j;                       // components 6..11
+        const double* E1 = w.P1 + 12 * j;                       // components 0..5
         double t0 = cs.inv_mass * E0[9 + y], t1 = cs.inv_mass * E1[3 + y];
         MPCQ_UNROLL
         for (int k = 0; k < 3; ++k) {
@@ -525,7 +536,7 @@ MPCQ_DEV bool chol_factor(const Consts& cs, Work<T>& w, int k_start) {
         constexpr int M0 = decltype(m0c)::value;
         const bool keep_diag = k0 < k_start;
         const int row_lo = keep_diag ? k_start : k0;
-        const T* cw = w.cw + 128 * ((k0 >> 2) & 1);
+        const T* cw = w.cw + (NW > 1 ? 128 * ((k0 >> 2) & 1) : 0);   // double-buffered for multi-warp teams only
         int ci[4];
         MPCQ_UNROLL
         for (int c = 0; c < 4; ++c) ci[c] = w.sinf[k0 + c];
@@ -700,7 +711,8 @@ MPCQ_DEV bool chol_factor(const Consts& cs, Work<T>& w, int k_start) {
                 }
             }
         }
-        if (wid == 0 && k0 + 4 < n) write_cw(k0 + 4, w.cw + 128 * (((k0 >> 2) + 1) & 1));
+        if (NW == 1) wp::sync();                                // every lane is done reading this panel's cw
+        if (wid == 0 && k0 + 4 < n) write_cw(k0 + 4, w.cw + (NW > 1 ? 128 * (((k0 >> 2) + 1) & 1) : 0));
         team::sync(w.t);                                        // panel columns + next cw visible
     };
     for (int k0 = 0; k0 < n; k0 += 4) {
@@ -1240,7 +1252,7 @@ MPCQ_DEV void solve_env(const Consts& cs, const IO<T>& io, int b, char* smem, T*
     const int nmax = (3 * (ns_hi < NCAP / 3 ? ns_hi : NCAP / 3) + 3) & ~3;     // largest system of this size class
     const int H = cs.horizon;
     Work<T> w;
-    carve(w, smem, l_global, H, NCAP, false, nmax);
+    carve(w, smem, l_global, H, NCAP, false, nmax, NW);
     w.t.tid = NW == 1 ? wp::lane() : wp::team_tid();
     w.t.nt = 32 * NW;
     w.t.wid = NW == 1 ? 0 : (w.t.tid >> 5);

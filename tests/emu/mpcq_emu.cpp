@@ -140,7 +140,7 @@ int run(const mpcq_config* cfg, int B, const T* x0, const T* yaw, const T* feet,
     const mpcq::Consts* cs = &consts;
     for (int ci = 0; ci < mpcq::num_classes(cs->horizon); ++ci) {
         const int ncap = mpcq::kClasses[ci].ncap;
-        std::vector<char> smem(mpcq::work_bytes<T>(cs->horizon, ncap, true, false, mpcq::class_nmax(mpcq::kClasses[ci])) + 64);
+        std::vector<char> smem(mpcq::work_bytes<T>(cs->horizon, ncap, true, false, mpcq::class_nmax(mpcq::kClasses[ci]), mpcq::kClasses[ci].nw) + 64);
         for (int b = 0; b < B; ++b) {
             Job<T> j;
             j.cs = *cs;
