@@ -231,7 +231,10 @@ def run_ours(a):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":      # keep stdout to the one JSON line
+        # keep stdout to the one JSON line: whatever NCCL prints (the version banner with NCCL_DEBUG=VERSION, INFO logs)
+        # goes to stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
             os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=dev)
     tdt = torch.float64 if a.dtype == "f64" else torch.float32

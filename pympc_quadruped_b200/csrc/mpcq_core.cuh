@@ -827,18 +827,27 @@ MPCQ_DEV double slot_residual(int sx, int sy, int sz, int c, const double* gp, d
     return sz == 0 ? -(sx * mu * gp[0] + sy * mu * gp[1] + gp[2]) : 0.0;
 }
 
-// reduced gradient r = -Z' gam into vec (precision T); returns |r|_inf (fp64)
+// the three slot residuals -Z_p' gam_p of one foot-step, branch-free (faces differ from lane to lane)
+MPCQ_DEV void foot_residual(int sx, int sy, int sz, const double* gp, double mu, double& r0, double& r1, double& r2) {
+    const bool live = sz >= 0;
+    r0 = wp::sel(live && sx == 0, -gp[0], 0.0);
+    r1 = wp::sel(live && sy == 0, -gp[1], 0.0);
+    r2 = wp::sel(sz == 0, -((double)sx * mu * gp[0] + (double)sy * mu * gp[1] + gp[2]), 0.0);
+}
+
+// reduced gradient r = -Z' gam into vec (precision T); returns |r|_inf (fp64).  One lane per foot-step.
 template <class T>
 MPCQ_DEV double reduced_gradient(const Consts& cs, Work<T>& w) {
     MPCQ_PHASE(5);
     const int lane = w.t.tid;
     double rmax = 0;
-    for (int v = lane; v < w.n; v += w.t.nt) {
-        const int p = v / 3;
-        double r = 0;
-        if (p < w.ns) r = slot_residual(w.face[3 * p], w.face[3 * p + 1], w.face[3 * p + 2], v - 3 * p, w.gam + 3 * w.fo[p], cs.mu);
-        w.vec[v] = (T)r;
-        rmax = dmax(rmax, dabs(r));
+    for (int p = lane; p < w.n / 3 + 1; p += w.t.nt) {
+        double r0 = 0.0, r1 = 0.0, r2 = 0.0;
+        if (p < w.ns) foot_residual(w.face[3 * p], w.face[3 * p + 1], w.face[3 * p + 2], w.gam + 3 * w.fo[p], cs.mu, r0, r1, r2);
+        if (3 * p < w.n) w.vec[3 * p] = (T)r0;                   // the slots beyond 3 ns (padding of n to a multiple of 4) get 0
+        if (3 * p + 1 < w.n) w.vec[3 * p + 1] = (T)r1;
+        if (3 * p + 2 < w.n) w.vec[3 * p + 2] = (T)r2;
+        rmax = dmax(rmax, dmax(dabs(r0), dmax(dabs(r1), dabs(r2))));
     }
     rmax = team::reduce_max(w.t, rmax);
     team::sync(w.t);
@@ -877,35 +886,43 @@ MPCQ_DEV void apply_step(const Consts& cs, Work<T>& w) {
 template <class T, int NSLOT>
 MPCQ_DEV double refine(const Consts& cs, Work<T>& w, double tol_abs, bool u_is_zero, bool use_cg) {
     const int lane = w.t.tid;
-    // Plain refinement (u += Z M^-1 r) first: with an accurate factor it gains 2-3 digits per step and is the cheapest.
-    // Intermediate active-set rounds (use_cg = false) stop there - they only need the faces right.
-    // (one hess_apply site serves the initial gradient and the refinement steps: the function is inlined, code size matters)
-    double rmax = 0.0;
-    {
-        double prev = 0.0;
-        const int cap = use_cg ? cs.refine_max : 3;
-        for (int it = 0;; ++it) {
+    // ONE loop (one call site each for tri_solve and reduced_gradient - the kernel stalls on instruction fetch, code size
+    // matters) with two phases:
+    //  plain  u += Z M^-1 r, gam recomputed: with an accurate factor it gains 2-3 digits per step and is the cheapest.
+    //         Intermediate active-set rounds (use_cg = false) stop there - they only need the faces right.
+    //  cg     entered when the plain steps converge too slowly or run out: preconditioned CG, gam updated incrementally.
+    double rmax = 0.0, prev = 0.0, rz = 0.0;
+    double* d = w.utrial;
+    const int cap = use_cg ? cs.refine_max : 3;
+    bool cg = false;
+    int it = 0, itcg = 0;
+    for (;;) {
+        if (!cg) {
             if (it == 0 && u_is_zero) {
                 for (int idx = lane; idx < w.nv; idx += w.t.nt) w.gam[idx] = w.g[idx];
                 team::sync(w.t);
             } else {
                 hess_apply(cs, w);
             }
-            rmax = reduced_gradient(cs, w);                          // r = -Z' gam -> vec
-            if (!(rmax > tol_abs && it < cap)) break;
-            if (it > 0 && rmax > 0.2 * prev) break;              // converging too slowly: hand over to CG
-            prev = rmax;
-            if (w.t.wid == 0) tri_solve<T, NSLOT>(w);
-            team::sync(w.t);
-            apply_step(cs, w);
         }
-        if (!use_cg || rmax <= tol_abs) return rmax;
-    }
-    double rz = 0.0;
-    double* d = w.utrial;
-    for (int it = 0; rmax > tol_abs && it < cs.refine_max; ++it) {
+        rmax = reduced_gradient(cs, w);                              // r = -Z' gam -> vec
+        if (!cg) {
+            const bool stop = !(rmax > tol_abs && it < cap);
+            if (stop || (it > 0 && rmax > 0.2 * prev)) {         // done, out of steps, or converging too slowly: hand over to CG
+                if (!use_cg || rmax <= tol_abs) return rmax;
+                cg = true;
+            } else {
+                prev = rmax;
+            }
+        }
+        if (cg && !(rmax > tol_abs && itcg < cs.refine_max)) break;
         if (w.t.wid == 0) tri_solve<T, NSLOT>(w);               // z = M^-1 r; the serial chain runs on one warp
         team::sync(w.t);
+        if (!cg) {
+            apply_step(cs, w);
+            ++it;
+            continue;
+        }
         // rz = r'z (r recomputed from gam in fp64), beta, d = Z z + beta d
         double part = 0.0;
         for (int v = lane; v < w.n; v += w.t.nt) {
@@ -915,7 +932,7 @@ MPCQ_DEV double refine(const Consts& cs, Work<T>& w, double tol_abs, bool u_is_z
                         (double)w.vec[v];
         }
         const double rz_new = team::reduce_sum(w.t, part);
-        const double beta = it == 0 ? 0.0 : rz_new / rz;
+        const double beta = itcg == 0 ? 0.0 : rz_new / rz;
         rz = rz_new;
         if (!(rz > 0.0)) break;                                  // converged to rounding (or a broken factor)
         for (int p = lane; p < w.ns; p += w.t.nt) {
@@ -927,7 +944,7 @@ MPCQ_DEV double refine(const Consts& cs, Work<T>& w, double tol_abs, bool u_is_z
                 if (sz == 0) { z2 = w2; z0 = sx != 0 ? sx * cs.mu * w2 : w0; z1 = sy != 0 ? sy * cs.mu * w2 : w1; }
                 else { z0 = sx == 0 ? w0 : 0.0; z1 = sy == 0 ? w1 : 0.0; }
             }
-            if (it == 0) { dp[0] = z0; dp[1] = z1; dp[2] = z2; }
+            if (itcg == 0) { dp[0] = z0; dp[1] = z1; dp[2] = z2; }
             else { dp[0] = z0 + beta * dp[0]; dp[1] = z1 + beta * dp[1]; dp[2] = z2 + beta * dp[2]; }
         }
         team::sync(w.t);
@@ -942,7 +959,7 @@ MPCQ_DEV double refine(const Consts& cs, Work<T>& w, double tol_abs, bool u_is_z
             w.gam[idx] += alpha * w.hd[idx];
         }
         team::sync(w.t);
-        rmax = reduced_gradient(cs, w);
+        ++itcg;
     }
     // the face equalities hold to rounding after the updates; make them exact again (changes u by ~1 ulp)
     for (int p = lane; p < w.ns; p += w.t.nt) {
@@ -958,11 +975,18 @@ MPCQ_DEV double refine(const Consts& cs, Work<T>& w, double tol_abs, bool u_is_z
 }
 
 // ---------------------------------------------------------------------------------------------
-// face tests.  mode 0 (primal-dual round): rewrite every offending face, return counts.
+// face tests of a primal-dual round: the faces every offending foot should move to are written to face2 (all feet, so
+// that commit_faces() can adopt them without evaluating the tests a second time); returns the violation counts.
 struct FaceCheck { int n_primal, n_dual; };
 
 template <class T>
-MPCQ_DEV FaceCheck pdas_update(const Consts& cs, Work<T>& w, bool write) {
+MPCQ_DEV void commit_faces(Work<T>& w) {
+    for (int idx = w.t.tid; idx < 3 * w.ns; idx += w.t.nt) w.face[idx] = w.face2[idx];
+    team::sync(w.t);
+}
+
+template <class T>
+MPCQ_DEV FaceCheck pdas_update(const Consts& cs, Work<T>& w) {
     MPCQ_PHASE(7);
     const int lane = w.t.tid;
     const double mu = cs.mu;
@@ -1008,7 +1032,7 @@ MPCQ_DEV FaceCheck pdas_update(const Consts& cs, Work<T>& w, bool write) {
             }
             sx = nsx; sy = nsy; sz = nsz;
         }
-        if (write) { w.face[3 * p] = (int8_t)sx; w.face[3 * p + 1] = (int8_t)sy; w.face[3 * p + 2] = (int8_t)sz; }
+        w.face2[3 * p] = (int8_t)sx; w.face2[3 * p + 1] = (int8_t)sy; w.face2[3 * p + 2] = (int8_t)sz;
     }
     FaceCheck fc;
     fc.n_primal = team::reduce_sum(w.t, npv);
@@ -1344,7 +1368,7 @@ MPCQ_DEV void solve_env(const Consts& cs, const IO<T>& io, int b, char* smem, T*
             numeric_ok = face_solve<T, NCAP, NW>(cs, w, tight ? tol_tight : tol_loose, rmax, tight, mode == M_TIGHT) && numeric_ok;
             if (mode != M_TIGHT) ++nfac;
             if (mode != M_AS) {
-                const FaceCheck fc = pdas_update(cs, w, false);
+                const FaceCheck fc = pdas_update(cs, w);
                 const bool clean = fc.n_primal == 0 && fc.n_dual == 0;
                 if (clean && mode == M_PDAS) { mode = M_TIGHT; continue; }          // tighten on the same factor (CG), re-test
                 if (clean) {
@@ -1357,7 +1381,7 @@ MPCQ_DEV void solve_env(const Consts& cs, const IO<T>& io, int b, char* smem, T*
 #endif
                 mode = M_PDAS;
                 if (!numeric_ok) break;
-                if (round++ < cs.pdas_cap) { pdas_update(cs, w, true); continue; }
+                if (round++ < cs.pdas_cap) { commit_faces(w); continue; }
                 // the rounds cycle: hand over to the monotone method, started from the clamped last iterate (clamp_into
                 // derives the faces from the point)
                 status |= ST_FALLBACK;
@@ -1377,7 +1401,8 @@ MPCQ_DEV void solve_env(const Consts& cs, const IO<T>& io, int b, char* smem, T*
                 for (int idx = lane; idx < w.nv; idx += w.t.nt) w.ucur[idx] = w.u[idx];
                 phi_cur = objective(cs, w);
                 if (!(rmax <= 10.0 * tol_tight)) { numeric_ok = false; break; }   // the factor cannot deliver the residual
-                const FaceCheck fc = pdas_update(cs, w, true);
+                const FaceCheck fc = pdas_update(cs, w);
+                commit_faces(w);
 #if defined(MPCQ_HOST_EMU) && defined(MPCQ_TRACE)
                 if (lane == 0) printf("     feasible minimiser: primal %d dual %d\n", fc.n_primal, fc.n_dual);
 #endif
