@@ -332,3 +332,75 @@ def test_fused_assembly_equals_torch_statement_and_reference_sequence():
         ref = z[k + "forces__oracle_solver"][tick]
         assert np.abs(f - ref).max() <= max(1e-3, 1e-4 * np.abs(ref).max()), tick
         assert np.abs(ctrl.ref_traj - z[k + "ref_traj"][tick]).max() <= 1.2e-7 * max(1.0, np.abs(z[k + "ref_traj"][tick]).max())
+
+
+FULL_SIZE = [
+    # BASELINE.json configs[1], [2], [3] at their full sizes: name, robot, H, B, gaits, dtype, seed, oracle sample
+    ("cfg2_a1_trot_4096_f32", A1Config, 10, 4096, (Gait.TROTTING10,), torch.float32, 21, 48),
+    ("cfg3_aliengo_mix_16384_f64", AliengoConfig, 10, 16384, GAIT_MIX, torch.float64, 22, 48),
+    ("cfg4_a1_h30_4096_f32", A1Config, 30, 4096, (Gait.TROTTING10,), torch.float32, 23, 12),
+]
+
+
+@pytest.mark.parametrize("name,robot,H,B,gaits,dtype,seed,nsample", FULL_SIZE, ids=[c[0] for c in FULL_SIZE])
+def test_full_size_properties(name, robot, H, B, gaits, dtype, seed, nsample):
+    """BASELINE sizes: size-independent properties on every environment (verified status, fp64 KKT residuals, feasibility
+    of the returned forces recomputed here from u, swing forces exactly zero, f = u[:12]), agreement of the fp32 and fp64
+    modes within the parity tolerance, and the oracle on a random subsample."""
+    batch = make_batch(robot, H, B, "mixed", gaits, seed, solve=False)
+    eng = _engine(batch, robot, dtype)
+    x0, feet, gait, xref, yaw = _to_dev(batch, dtype)
+    res = eng.solve(x0, feet, gait, xref, yaw=yaw)
+    torch.cuda.synchronize()
+    u = res.u.double().cpu().numpy()
+    status = res.status.cpu().numpy()
+    resid = res.resid.cpu().numpy()
+    assert np.all(status & _capi.ST_VERIFIED) and not np.any(status & (_capi.ST_NUMERIC | _capi.ST_MAXITER))
+    assert np.array_equal(res.forces.double().cpu().numpy(), u[:, :12])
+    mu, fz_max = float(eng.consts["mu"]), float(eng.consts["fz_max"])
+    f = u.reshape(B, 4 * H, 3)
+    stance = batch["gait"].reshape(B, 4 * H) > 0
+    assert np.all(f[~stance] == 0.0)                                   # swing foot-steps carry exactly no force
+    out_tol = 1e-9 if dtype == torch.float64 else 2e-5                 # f32 mode: rounding of ~100 N outputs to float
+    assert np.all(f[..., 2] >= -out_tol) and np.all(f[..., 2] <= fz_max + out_tol)
+    assert np.all(np.abs(f[..., 0]) <= mu * f[..., 2] + out_tol) and np.all(np.abs(f[..., 1]) <= mu * f[..., 2] + out_tol)
+    gscale = 1.0 + np.abs(u).max()
+    assert resid[:, 1].max() <= 1e-9 * gscale                          # primal violation measured on the fp64 iterate
+    assert resid[:, 0].max() <= (1e-6 if dtype == torch.float64 else 1e-4)   # reduced gradient (f32: 2 min(R) * 2e-4 N cap)
+    # the other arithmetic mode solves the same QPs: same optimum within the parity tolerance
+    other = torch.float64 if dtype == torch.float32 else torch.float32
+    eng2 = _engine(batch, robot, other)
+    a2 = _to_dev(batch, other)
+    u2 = eng2.solve(a2[0], a2[1], a2[2], a2[3], yaw=a2[4]).u.double().cpu().numpy()
+    tol = np.maximum(ABS_TOL, REL_TOL * np.abs(u).max(axis=1))
+    assert np.all(np.abs(u - u2).max(axis=1) <= tol)
+    # oracle on a random subsample
+    from oracle.mpc_oracle import OracleMPC, RobotState
+    from oracle.qp_exact import solve_qp_exact
+    from pympc_quadruped_b200.synth import synth_states
+    st = synth_states(B, robot, "mixed", seed=seed)
+    rng = np.random.default_rng(seed)
+    worst = 0.0
+    for b in rng.choice(B, size=nsample, replace=False):
+        m = OracleMPC(batch["cfg"], robot)
+        m.update_robot_state(RobotState(st["quat_base"][b], st["pos_base"][b], st["ang_vel_base"][b], st["lin_vel_base"][b],
+                                        st["pos_base_feet"][b]))
+        Hm, g, _, _, ub = m.build_qp(batch["xref"][b], batch["gait"][b])
+        sol = solve_qp_exact(Hm, g, m.mu, ub[4::5])
+        assert sol.verified
+        t = max(ABS_TOL, REL_TOL * np.abs(sol.u).max())
+        err = np.abs(u[b] - sol.u).max()
+        assert err <= t, f"env {b}: |du| = {err:.3e} > {t:.3e}"
+        worst = max(worst, err / t)
+    print(f"{name}: all {B} verified, worst err/tol on {nsample} oracle samples {worst:.3f}, "
+          f"factorisations mean {res.iters[:, 0].float().mean():.2f} max {int(res.iters[:, 0].max())}")
+
+
+def test_measure_peaks_reports_plausible_numbers():
+    import ctypes
+    lib = _capi.load_library()
+    out = (ctypes.c_double * 4)()
+    assert lib.mpcq_measure_peaks(0, out) == 0
+    fp32, fp64, smem, sms = out[0], out[1], out[2], out[3]
+    assert sms >= 100 and 20.0 < fp32 < 200.0 and 5.0 < fp64 < 100.0 and 5e3 < smem < 1e5, (fp32, fp64, smem, sms)
+    assert lib.mpcq_measure_peaks(-1, out) == -1 and lib.mpcq_measure_peaks(0, None) == -1
