@@ -573,6 +573,10 @@ MPCQ_DEV bool chol_factor(const Consts& cs, Work<T>& w, int k_start) {
             }
         }
         }
+        if (NW == 1) {                                          // one-warp team: the table of the NEXT panel is written now, off
+            wp::sync();                                         // the serial end of this panel (every lane is done reading cw)
+            if (k0 + 4 < n) write_cw(k0 + 4, w.cw);
+        }
         // ---- left-looking update with all previous columns
         const T* colg;
         {
@@ -640,6 +644,7 @@ MPCQ_DEV bool chol_factor(const Consts& cs, Work<T>& w, int k_start) {
             colg = col;                                       // == L + colbase(k0, n)
         }
         // ---- 4x4 diagonal block: kept, or factored by the warp that owns its rows and published through dblk
+        T m10 = 0, m20 = 0, m21 = 0, m30 = 0, m31 = 0, m32 = 0, m00 = 0, m11 = 0, m22 = 0, m33 = 0;
         if (!keep_diag) {
             MPCQ_PHASE(12);
             const int kb = k0 >> 2, q = kb / NW;
@@ -668,23 +673,26 @@ MPCQ_DEV bool chol_factor(const Consts& cs, Work<T>& w, int k_start) {
                 piv = d33 - l30 * l30 - l31 * l31 - l32 * l32;
                 ok = ok && (piv > (T)0);
                 const T i3 = wp::rsqrt_(piv > (T)0 ? piv : (T)1);
+                // dblk holds the INVERSE M of the 4x4 diagonal block (lower triangular): the block solves of the
+                // panel and of the triangular sweeps become 4 independent dot products instead of a 4-deep chain.
+                // Every lane computes it (the pivots were broadcast by the shuffles), lane 0 stores it for later sweeps;
+                // a one-warp team goes on with the register copy instead of a store / barrier / load round trip.
+                m10 = -(l10 * i0) * i1; m21 = -(l21 * i1) * i2; m32 = -(l32 * i2) * i3;
+                m20 = -(l20 * i0 + l21 * m10) * i2; m31 = -(l31 * i1 + l32 * m21) * i3;
+                m30 = -(l30 * i0 + l31 * m10 + l32 * m20) * i3;
+                m00 = i0; m11 = i1; m22 = i2; m33 = i3;
                 if (lane == 0) {
-                    // dblk holds the INVERSE M of the 4x4 diagonal block (lower triangular): the block solves of the
-                    // panel and of the triangular sweeps become 4 independent dot products instead of a 4-deep chain
-                    const T m10 = -(l10 * i0) * i1, m21 = -(l21 * i1) * i2, m32 = -(l32 * i2) * i3;
-                    const T m20 = -(l20 * i0 + l21 * m10) * i2, m31 = -(l31 * i1 + l32 * m21) * i3;
-                    const T m30 = -(l30 * i0 + l31 * m10 + l32 * m20) * i3;
                     T* db = w.dblk + 3 * k0;          // 12 values per block of 4 columns
                     db[0] = m10; db[1] = m20; db[2] = m21; db[3] = m30;
                     db[4] = m31; db[5] = m32; db[6] = i0; db[7] = i1;
                     db[8] = i2; db[9] = i3; db[10] = 0; db[11] = 0;
                 }
             }
-            team::sync(w.t);                                    // dblk visible to the team
+            if (NW > 1) team::sync(w.t);                        // dblk visible to the team
         }
         MPCQ_PHASE(13);
-        T m10, m20, m21, m30, m31, m32, m00, m11, m22, m33, pad0, pad1;
-        {
+        if (NW > 1 || keep_diag) {
+            T pad0, pad1;
             const T* db = w.dblk + 3 * k0;
             load4(db, m10, m20, m21, m30);
             load4(db + 4, m31, m32, m00, m11);
@@ -711,8 +719,7 @@ MPCQ_DEV bool chol_factor(const Consts& cs, Work<T>& w, int k_start) {
                 }
             }
         }
-        if (NW == 1) wp::sync();                                // every lane is done reading this panel's cw
-        if (wid == 0 && k0 + 4 < n) write_cw(k0 + 4, w.cw + (NW > 1 ? 128 * (((k0 >> 2) + 1) & 1) : 0));
+        if (NW > 1 && wid == 0 && k0 + 4 < n) write_cw(k0 + 4, w.cw + 128 * (((k0 >> 2) + 1) & 1));
         team::sync(w.t);                                        // panel columns + next cw visible
     };
     for (int k0 = 0; k0 < n; k0 += 4) {
