@@ -351,17 +351,30 @@ def run_ours(a):
     e2e_value = world * B * a.steps / float(te.item())
     assert np.array_equal(r["forces"], hout["forces"])
 
-    # ---- the batched controller API on device tensors: update_robot_state + update_mpc_if_needed (fused assembly kernel +
-    # solve), i.e. the call sequence of scripts/isaacgym_a1.py:141-143 for the whole batch
+    # ---- the batched controller API on device tensors: gait schedule + update_robot_state + update_mpc_if_needed (gait kernel,
+    # fused assembly kernel, solve), i.e. the call sequence of scripts/isaacgym_a1.py:136-143 for the whole batch
     c2 = BatchedModelPredictiveController(with_horizon(H), robot, B, device=dev, dtype=tdt)
     dv = lambda key, k: torch.as_tensor(st[key][k * B:(k + 1) * B], device=dev)
     rds = [BatchedRobotData(dv("quat_base", k), dv("pos_base", k), dv("ang_vel_base", k), dv("lin_vel_base", k),
                             dv("pos_base_feet", k), dv("R_base", k)) for k in range(min(S, 8))]
     cmds = [(dv("vel_cmd_body", k), dv("yaw_rate_cmd", k)) for k in range(min(S, 8))]
+    # contact schedule on the device too (mpcq_gait_tables): same per-env patterns and phases as the precomputed tables
+    from pympc_quadruped_b200.synth import synth_gait_params
+    goff, gdur, gseg, git = synth_gait_params(n, gaits_for(a.gait), seed=SEED_BASE + 2 + 1000 * rank)
+    ibm = int(c2.iterations_between_mpc)
+    i32 = lambda v: torch.as_tensor(np.ascontiguousarray(v).astype(np.int32), device=dev)
+    gparams = [(i32(goff[k * B:(k + 1) * B]), i32(gdur[k * B:(k + 1) * B]), i32(gseg[k * B:(k + 1) * B]),
+                i32(git[k * B:(k + 1) * B] * ibm)) for k in range(min(S, 8))]
+    gtab = torch.empty((B, 4 * H), dtype=torch.float32, device=dev)
+
     def ctrl_step(s):
         k = s % len(rds)
+        eng2 = c2.engine
+        eng2.gait_tables(gparams[k][0], gparams[k][1], gparams[k][2], gparams[k][3], ibm, table=gtab)
         c2.update_robot_state(rds[k])
-        return c2.update_mpc_if_needed(0, cmds[k][0], cmds[k][1], gait[k])
+        return c2.update_mpc_if_needed(0, cmds[k][0], cmds[k][1], gtab)
+    ctrl_step(0)
+    assert torch.equal(gtab, gait[0]), "device gait tables differ from the host tables of the same schedule"
     for s in range(a.warmup):
         ctrl_step(s)
     barrier()
@@ -426,7 +439,7 @@ def run_ours(a):
                     "ms_per_step": 1e3 * float(te.item()) / a.steps, "launches_per_step": e2e_launches},
             "controller_api": {"value": world * B / (ctrl_ms * 1e-3), "unit": UNIT, "ms_per_step": ctrl_ms,
                                "api": "BatchedModelPredictiveController.update_robot_state + update_mpc_if_needed on device tensors "
-                                      "(mpcq_assemble + mpcq_solve: 3 kernel launches)"},
+                                      "(mpcq_gait_tables + mpcq_assemble + mpcq_solve: 4 kernel launches)"},
             "gpu_launches": launches_per_step * a.steps,
             "kernel_ms": {"per_class_mean": [float(v) for v in kmean], "dominant_class": dom,
                           "share_of_step": float(kmean[dom] / (total_ms / a.steps)),

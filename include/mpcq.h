@@ -136,6 +136,20 @@ int mpcq_assemble(mpcq_handle* h, int32_t B,
                   void* x0, void* yaw, void* x_ref, void* stream);
 
 /*
+ * replaces, for B robots, the contact schedule the reference computes per robot on the host before every MPC update:
+ * Gait.set_iteration + Gait.get_gait_table (linear_mpc/gait.py:76-100) and, when asked for, Gait.get_swing_state /
+ * get_stance_state (:102-135) - one elementwise kernel.  Device arrays:
+ *   stance_offsets [B,4], stance_durations [B,4], num_segment [B] (int32; the Enum payload, gait.py:16-22),
+ *   cur_iteration [B] (int32 control tick), iterations_between_mpc (LinearMpcConfig.iteration_between_mpc)
+ *   table [B,4H] float32, step-major / leg-minor, 1 = stance, first entry = step t+1 - exactly the `gait` mpcq_solve takes
+ *   swing_state, stance_state [B,4] float64 or NULL: phase progress in (0,1], 0 = not in that phase
+ * Rows with num_segment < 1 are undefined behaviour like the reference's division by zero; validate on the host.
+ */
+int mpcq_gait_tables(mpcq_handle* h, int32_t B, const int32_t* stance_offsets, const int32_t* stance_durations,
+                     const int32_t* num_segment, const int32_t* cur_iteration, int32_t iterations_between_mpc, float* table,
+                     double* swing_state, double* stance_state, void* stream);
+
+/*
  * Same call with HOST buffers (what a CPU-side simulator loop such as scripts/isaacgym_a1.py:119-164
  * would hand over): inputs are staged through pinned memory, copied to the device, solved and the
  * requested outputs copied back; returns after the results are in the caller's buffers.

@@ -4,7 +4,7 @@ Importing the package needs neither a GPU nor the built library; constructing an
 controller does (there is no CPU fallback).
 """
 from .configs import A1Config, AliengoConfig, LinearMpcConfig, RobotConfig, with_horizon  # noqa: F401
-from .gait import Gait, GaitSchedule, gait_tables  # noqa: F401
+from .gait import BatchedGaitSchedule, Gait, GaitSchedule, gait_tables  # noqa: F401
 
 
 def __getattr__(name):

@@ -35,6 +35,31 @@ class BatchedRobotData:
         self.pos_base_feet = pos_base_feet    # [B,4,3] world-frame base->foot, FL FR RL RR
         self.R_base = R_base                  # [B,3,3] or None (derived from the quaternion)
 
+    @classmethod
+    def from_isaacgym(cls, root_states, foot_positions_world=None, pos_base_feet=None, env_ids=None):
+        """Zero-copy-style glue for the Isaac Gym tensor API, replacing the per-robot
+        `.cpu().numpy()` loop of scripts/isaacgym_a1.py:119-133 for the whole batch on the device.
+
+        `root_states` is the wrapped actor-root-state tensor [num_actors, 13]: position 0:3, quaternion 3:7 in Isaac Gym's
+        (x, y, z, w) order, linear velocity 7:10, angular velocity 10:13 (world frame).  The reference reorders the
+        quaternion to (w, x, y, z) (isaacgym_a1.py:121-125); so does this.  Foot positions come either as world-frame
+        foot positions [B,4,3] (e.g. from the rigid-body state tensor; base->foot = foot - base, utils/robot_data.py:144-149)
+        or directly as `pos_base_feet`.  `env_ids` selects / orders the robots (LongTensor)."""
+        rs = root_states if env_ids is None else root_states.index_select(0, env_ids)
+        if rs.dim() != 2 or rs.shape[1] != 13:
+            raise ValueError("root_states must be [num_actors, 13]")
+        rs = rs.to(torch.float64)
+        pos = rs[:, 0:3].contiguous()
+        quat = torch.stack([rs[:, 6], rs[:, 3], rs[:, 4], rs[:, 5]], dim=1)
+        if (foot_positions_world is None) == (pos_base_feet is None):
+            raise ValueError("give exactly one of foot_positions_world / pos_base_feet")
+        if pos_base_feet is None:
+            fw = foot_positions_world.to(torch.float64).reshape(rs.shape[0], 4, 3)
+            pos_base_feet = fw - pos[:, None, :]
+        else:
+            pos_base_feet = pos_base_feet.to(torch.float64).reshape(rs.shape[0], 4, 3)
+        return cls(quat, pos, rs[:, 10:13].contiguous(), rs[:, 7:10].contiguous(), pos_base_feet.contiguous())
+
 
 def quat_to_matrix(q: torch.Tensor) -> torch.Tensor:
     """(w,x,y,z) -> R_base, batched (utils/kinematics.py:51-71)."""

@@ -120,6 +120,64 @@ mpcq_build_qp_kernel(const __grid_constant__ Consts cs, const __grid_constant__ 
     }
 }
 
+// Contact schedule on the device (reference linear_mpc/gait.py:76-135): one thread per environment writes
+// its 4H-entry contact table and, optionally, the swing / stance phase states the leg controller reads.  Integer modular
+// arithmetic for the table; the phase states follow the reference's float32 phase / float64 arithmetic mix.
+struct GaitArgs {
+    const int32_t *offsets, *durations, *num_segment, *cur_iteration;
+    int iterations_between_mpc, B, H;
+};
+
+__global__ void __launch_bounds__(128)
+mpcq_gait_kernel(GaitArgs a, float* table, double* swing_state, double* stance_state) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= a.B) return;
+    const int seg = a.num_segment[b], ibm = a.iterations_between_mpc;
+    const int cur = a.cur_iteration[b];
+    int off[4], dur[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { off[j] = a.offsets[4 * b + j]; dur[j] = a.durations[4 * b + j]; }
+    // set_iteration (gait.py:76-79): iteration = floor(cur / ibm) % seg, phase = (cur % (ibm seg)) / (ibm seg)
+    const int iteration = (cur / ibm) % seg;
+    float* t = table + (size_t)b * 4 * a.H;
+    for (int i = 0; i < a.H; ++i) {
+        const int ph = (i + 1 + iteration) % seg;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            int c = (ph - off[j]) % seg;
+            c += c < 0 ? seg : 0;                                  // Python's non-negative modulo (gait.py:93-97)
+            t[4 * i + j] = c < dur[j] ? 1.0f : 0.0f;
+        }
+    }
+    if (!swing_state && !stance_state) return;
+    const int period = ibm * seg;
+    const double phase = (double)(float)((double)(cur % period) / (double)period);   // np.full(4, phase, dtype=np.float32)
+    double offn[4], durn[4], swo[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { offn[j] = (double)off[j] / seg; durn[j] = (double)dur[j] / seg; swo[j] = offn[j] + durn[j]; }
+    // the reference subtracts 1 from the WHOLE vector each time one entry exceeds 1 (gait.py:104-106); reproduced as written
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+        if (swo[i] > 1.0) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) swo[j] -= 1.0;
+        }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        if (swing_state) {
+            const double sd = 1.0 - durn[j];
+            double s = phase - swo[j];
+            if (s < 0.0) s += 1.0;
+            swing_state[4 * b + j] = s > sd ? 0.0 : s / sd;
+        }
+        if (stance_state) {
+            double s = phase - offn[j];
+            if (s < 0.0) s += 1.0;
+            stance_state[4 * b + j] = s > durn[j] ? 0.0 : s / durn[j];
+        }
+    }
+}
+
 // state assembly + reference trajectory, one thread per environment (HBM-stream bound: ~34 doubles in, 13 + 13H reals out)
 struct AssembleArgs {
     const double *quat, *pos, *omega, *vel, *R, *vdes, *yawrate;
@@ -509,6 +567,24 @@ int mpcq_assemble(mpcq_handle* h, int32_t B, const double* quat, const double* p
         mpcq_assemble_kernel<float><<<grid, 128, 0, st>>>(a, static_cast<float*>(x0), static_cast<float*>(yaw), static_cast<float*>(x_ref));
     h->last_launches = 1;
     return cuda_ok(h, cudaGetLastError(), "mpcq_assemble launch") ? MPCQ_OK : MPCQ_ERR_CUDA;
+}
+
+int mpcq_gait_tables(mpcq_handle* h, int32_t B, const int32_t* stance_offsets, const int32_t* stance_durations,
+                     const int32_t* num_segment, const int32_t* cur_iteration, int32_t iterations_between_mpc, float* table,
+                     double* swing_state, double* stance_state, void* stream) {
+    if (!h) return MPCQ_ERR_INVALID;
+    if (B < 0 || iterations_between_mpc < 1 ||
+        (B > 0 && (!stance_offsets || !stance_durations || !num_segment || !cur_iteration || !table))) {
+        h->err = "mpcq_gait_tables: null pointer or iterations_between_mpc < 1";
+        return MPCQ_ERR_INVALID;
+    }
+    h->last_launches = 0;
+    if (B == 0) return MPCQ_OK;
+    DeviceGuard guard(h->cfg.device);
+    GaitArgs a{stance_offsets, stance_durations, num_segment, cur_iteration, iterations_between_mpc, B, h->cs.horizon};
+    mpcq_gait_kernel<<<(B + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(a, table, swing_state, stance_state);
+    h->last_launches = 1;
+    return cuda_ok(h, cudaGetLastError(), "mpcq_gait_tables launch") ? MPCQ_OK : MPCQ_ERR_CUDA;
 }
 
 int mpcq_solve_host(mpcq_handle* h, int32_t B, const void* x0, const void* yaw, const void* r_feet, const float* gait,

@@ -182,6 +182,33 @@ class MpcqEngine:
                                     int(bool(do_mpc)), _ptr(x0), _ptr(yaw), _ptr(x_ref), C.c_void_p(stream))
         self._err(rc, "mpcq_assemble")
 
+    def gait_tables(self, stance_offsets, stance_durations, num_segment, cur_iteration, iterations_between_mpc,
+                    table=None, swing_state=None, stance_state=None, want_states=False):
+        """Contact tables (and swing / stance phase states) for B robots on the device (`mpcq_gait_tables`): int32 device
+        tensors in, float32 [B, 4H] table out - the `gait` argument of `solve`."""
+        B, H = stance_offsets.shape[0], self.horizon
+        i32 = torch.int32
+        stance_offsets = self._check("stance_offsets", stance_offsets, (B, 4), i32)
+        stance_durations = self._check("stance_durations", stance_durations, (B, 4), i32)
+        num_segment = self._check("num_segment", num_segment, (B,), i32)
+        cur_iteration = self._check("cur_iteration", cur_iteration, (B,), i32)
+        if table is None:
+            table = torch.empty((B, 4 * H), dtype=torch.float32, device=self.device)
+        elif self._check("table", table, (B, 4 * H), torch.float32) is not table:
+            raise ValueError("table must be contiguous (it is written in place)")
+        if want_states:
+            swing_state = torch.empty((B, 4), dtype=torch.float64, device=self.device) if swing_state is None else swing_state
+            stance_state = torch.empty((B, 4), dtype=torch.float64, device=self.device) if stance_state is None else stance_state
+        for name, t in (("swing_state", swing_state), ("stance_state", stance_state)):
+            if t is not None and self._check(name, t, (B, 4), torch.float64) is not t:
+                raise ValueError(f"{name} must be contiguous (it is written in place)")
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        rc = self.lib.mpcq_gait_tables(self._h, B, _ptr(stance_offsets), _ptr(stance_durations), _ptr(num_segment),
+                                       _ptr(cur_iteration), int(iterations_between_mpc), _ptr(table), _ptr(swing_state),
+                                       _ptr(stance_state), C.c_void_p(stream))
+        self._err(rc, "mpcq_gait_tables")
+        return table, swing_state, stance_state
+
     def set_profiling(self, enable: bool) -> None:
         self._err(self.lib.mpcq_set_profiling(self._h, int(bool(enable))), "mpcq_set_profiling")
 

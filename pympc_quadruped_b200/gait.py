@@ -107,6 +107,50 @@ def gait_tables(stance_offsets, stance_durations, num_segment, iteration, horizo
     return (cur < dur).astype(np.float32).reshape(cur.shape[0], 4 * horizon)
 
 
+class BatchedGaitSchedule:
+    """Per-environment gait patterns kept on the device: the batch counterpart of the
+    reference's `Gait` members (linear_mpc/gait.py:76-135).  `set_iteration` + `get_gait_table` run as ONE elementwise
+    kernel (`mpcq_gait_tables`) and hand `update_mpc_if_needed` a device tensor; nothing is computed on the host."""
+
+    def __init__(self, engine, schedules):
+        import torch
+        self.engine = engine
+        self.horizon = engine.horizon
+        dev = engine.device
+        scheds = list(schedules)
+        self.num_envs = len(scheds)
+        seg = np.array([s.num_segment for s in scheds], dtype=np.int32)
+        if np.any(seg < 1):
+            raise ValueError("num_segment must be >= 1")
+        self.stance_offsets = torch.as_tensor(np.stack([s.stance_offsets for s in scheds]).astype(np.int32), device=dev)
+        self.stance_durations = torch.as_tensor(np.stack([s.stance_durations for s in scheds]).astype(np.int32), device=dev)
+        self.num_segment = torch.as_tensor(seg, device=dev)
+        self._table = torch.zeros((self.num_envs, 4 * self.horizon), dtype=torch.float32, device=dev)
+        self._swing = torch.zeros((self.num_envs, 4), dtype=torch.float64, device=dev)
+        self._stance = torch.zeros((self.num_envs, 4), dtype=torch.float64, device=dev)
+        self._cur = torch.zeros((self.num_envs,), dtype=torch.int32, device=dev)
+
+    def set_iteration(self, iterations_between_mpc: int, cur_iteration) -> None:
+        """`cur_iteration`: one control tick for all robots (int) or an int tensor [B] (robots out of phase)."""
+        import torch
+        if torch.is_tensor(cur_iteration):
+            self._cur.copy_(cur_iteration.to(torch.int32))
+        else:
+            self._cur.fill_(int(cur_iteration))
+        self.engine.gait_tables(self.stance_offsets, self.stance_durations, self.num_segment, self._cur,
+                                int(iterations_between_mpc), table=self._table, swing_state=self._swing,
+                                stance_state=self._stance)
+
+    def get_gait_table(self):
+        return self._table
+
+    def get_swing_state(self):
+        return self._swing
+
+    def get_stance_state(self):
+        return self._stance
+
+
 class Gait:
     """Named patterns, same names as the reference Enum (linear_mpc/gait.py:16-22)."""
     STANDING = GaitSchedule('standing', 16, [0, 0, 0, 0], [16, 16, 16, 16])

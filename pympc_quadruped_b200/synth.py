@@ -108,13 +108,20 @@ def synth_states(num_envs: int, robot_config, regime: str = "mixed", seed: int =
 GAIT_MIX = (Gait.TROTTING10, Gait.PACING10, Gait.BOUNDING10)
 
 
-def synth_gait_tables(num_envs: int, horizon: int, gaits=(Gait.TROTTING10,),
-                      seed: int = SEED_BASE) -> np.ndarray:
-    """Per-env random pattern from `gaits` and random phase -> float32 [B, 4*horizon]."""
+def synth_gait_params(num_envs: int, gaits=(Gait.TROTTING10,), seed: int = SEED_BASE):
+    """Per-env random pattern from `gaits` and random phase: (stance_offsets [B,4], stance_durations [B,4],
+    num_segment [B], iteration [B]) - the inputs of `gait_tables` / of the device kernel `mpcq_gait_tables`."""
     rng = np.random.default_rng(seed + 7919)
     which = rng.integers(0, len(gaits), size=num_envs)
     offs = np.stack([gaits[k].stance_offsets for k in which])
     durs = np.stack([gaits[k].stance_durations for k in which])
     segs = np.array([gaits[k].num_segment for k in which])
     iteration = rng.integers(0, segs)
+    return offs, durs, segs, iteration
+
+
+def synth_gait_tables(num_envs: int, horizon: int, gaits=(Gait.TROTTING10,),
+                      seed: int = SEED_BASE) -> np.ndarray:
+    """Per-env random pattern from `gaits` and random phase -> float32 [B, 4*horizon]."""
+    offs, durs, segs, iteration = synth_gait_params(num_envs, gaits, seed)
     return gait_tables(offs, durs, segs, iteration, horizon)

@@ -404,3 +404,41 @@ def test_measure_peaks_reports_plausible_numbers():
     fp32, fp64, smem, sms = out[0], out[1], out[2], out[3]
     assert sms >= 100 and 20.0 < fp32 < 200.0 and 5.0 < fp64 < 100.0 and 5e3 < smem < 1e5, (fp32, fp64, smem, sms)
     assert lib.mpcq_measure_peaks(-1, out) == -1 and lib.mpcq_measure_peaks(0, None) == -1
+
+
+def test_device_gait_tables_equal_the_reference_schedule():
+    """mpcq_gait_tables against the per-robot schedule objects (pinned to the reference's Gait in
+    test_oracle_golden.py): contact table bit for bit, swing / stance phase states exactly (same float32 phase, float64
+    arithmetic), robots out of phase, every named pattern."""
+    from pympc_quadruped_b200 import BatchedGaitSchedule
+    from pympc_quadruped_b200.engine import MpcqEngine
+    from pympc_quadruped_b200.configs import with_horizon
+    names = ["STANDING", "TROTTING16", "TROTTING10", "JUMPING16", "PACING16", "PACING10", "BOUNDING10"]
+    for H in (10, 16):
+        eng = MpcqEngine(with_horizon(H), A1Config, dtype=torch.float32, device="cuda:0")
+        rng = np.random.default_rng(H)
+        scheds = [getattr(Gait, names[i % len(names)]).with_horizon(H) for i in range(70)]
+        bg = BatchedGaitSchedule(eng, scheds)
+        for ibm in (20, 7):
+            cur = rng.integers(0, 5000, size=70)
+            bg.set_iteration(ibm, torch.as_tensor(cur, device="cuda:0"))
+            torch.cuda.synchronize()
+            tab = bg.get_gait_table().cpu().numpy()
+            sw, stn = bg.get_swing_state().cpu().numpy(), bg.get_stance_state().cpu().numpy()
+            for b, s in enumerate(scheds):
+                s.set_iteration(ibm, int(cur[b]))
+                assert np.array_equal(tab[b], s.get_gait_table()), (H, ibm, b)
+                with np.errstate(all="ignore"):
+                    assert np.array_equal(sw[b], np.asarray(s.get_swing_state(), dtype=np.float64), equal_nan=True), (H, ibm, b)
+                    assert np.array_equal(stn[b], np.asarray(s.get_stance_state(), dtype=np.float64), equal_nan=True), (H, ibm, b)
+        bg.set_iteration(20, 40)                                   # one tick for all robots
+        s = scheds[2]; s.set_iteration(20, 40)
+        assert np.array_equal(bg.get_gait_table()[2].cpu().numpy(), s.get_gait_table())
+    # the table feeds the solver directly
+    batch = make_batch(A1Config, 10, 8, "mixed", (Gait.TROTTING10,), 31)
+    eng = _engine(batch, A1Config, torch.float32)
+    bg = BatchedGaitSchedule(eng, [Gait.TROTTING10.with_horizon(10)] * 8)
+    bg.set_iteration(20, 60)
+    x0, feet, _, xref, yaw = _to_dev(batch, torch.float32)
+    res = eng.solve(x0, feet, bg.get_gait_table(), xref, yaw=yaw)
+    assert np.all(res.status.cpu().numpy() & _capi.ST_VERIFIED)

@@ -151,3 +151,29 @@ def test_config_extraction_validates():
         R = np.zeros((12, 12))
     with pytest.raises(ValueError):
         extract_mpc_constants(BadR, A1Config)
+
+
+def test_isaacgym_root_state_glue_reorders_like_the_reference_script():
+    """scripts/isaacgym_a1.py:119-133: pos 0:3, quaternion (x,y,z,w) -> (w,x,y,z), lin vel 7:10, ang vel 10:13; base->foot =
+    foot - base (utils/robot_data.py:144-149).  Fake tensors: the simulator is not in the image."""
+    import torch
+    from pympc_quadruped_b200.controller import BatchedRobotData
+    rng = np.random.default_rng(5)
+    rs = torch.as_tensor(rng.normal(size=(6, 13)).astype(np.float32))
+    feet_w = torch.as_tensor(rng.normal(size=(6, 4, 3)).astype(np.float32))
+    rd = BatchedRobotData.from_isaacgym(rs, foot_positions_world=feet_w)
+    for b in range(6):                                           # the reference's per-robot statements
+        q_imre = rs[b, 3:7].numpy()
+        q_reim = np.array([q_imre[3], q_imre[0], q_imre[1], q_imre[2]], dtype=np.float32)
+        assert np.array_equal(rd.quat_base[b].numpy(), q_reim.astype(np.float64))
+        assert np.array_equal(rd.pos_base[b].numpy(), rs[b, 0:3].numpy().astype(np.float64))
+        assert np.array_equal(rd.lin_vel_base[b].numpy(), rs[b, 7:10].numpy().astype(np.float64))
+        assert np.array_equal(rd.ang_vel_base[b].numpy(), rs[b, 10:13].numpy().astype(np.float64))
+        assert np.array_equal(rd.pos_base_feet[b].numpy(), feet_w[b].numpy().astype(np.float64) - rs[b, 0:3].numpy().astype(np.float64))
+    ids = torch.tensor([4, 1])
+    sub = BatchedRobotData.from_isaacgym(rs, pos_base_feet=rd.pos_base_feet[ids], env_ids=ids)
+    assert torch.equal(sub.quat_base, rd.quat_base[ids]) and torch.equal(sub.pos_base_feet, rd.pos_base_feet[ids])
+    with pytest.raises(ValueError):
+        BatchedRobotData.from_isaacgym(rs)
+    with pytest.raises(ValueError):
+        BatchedRobotData.from_isaacgym(rs[:, :12], pos_base_feet=rd.pos_base_feet)
