@@ -423,6 +423,9 @@ def run_ours(a):
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
         cpu = cpu_baseline(a, st, tabs, out, eng, (x0, yaw, feet, xref, gait))
 
+    set_mb = S * B * ALGO_BYTES(H) * rs // 4 / 1e6
+    l2_note = f"{S} distinct input sets rotated ({set_mb:.0f} MB total, " + (
+        "> 126 MB L2)" if set_mb > 126 else "BELOW the 126 MB L2: raise --sets for an L2-cold number)")
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
@@ -431,7 +434,7 @@ def run_ours(a):
             "config": {"workload": workload_name(a), "envs_per_gpu": B, "horizon": H, "robot": a.robot, "gait": a.gait,
                        "regime": a.regime, "parallelism": f"env-sharded x{world}, no collective in the solve loop"
                                                           + (" + all-gather of GRFs" if gathered is not None else ""),
-                       "l2": f"{S} distinct input sets rotated ({S * B * ALGO_BYTES(H) * rs // 4 / 1e6:.0f} MB total > 126 MB L2)",
+                       "l2": l2_note,
                        "precision": "Cholesky/triangular solves in " + a.dtype + ", residuals + KKT tests in f64"},
             "latency_ms": {"p50": lat[len(lat) // 2], "p90": lat[int(len(lat) * 0.9)], "max": lat[-1]},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
