@@ -412,12 +412,22 @@ def run_ours(a):
     algo_tflops = algo_flops * B / kern_s / 1e12
 
     # DRAM traffic of the dominant kernel from the committed `ncu --set full` capture of this same command
-    traffic, traffic_src = None, None
+    traffic, traffic_src, smem = None, None, None
     tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     if os.path.exists(tpath):
         tj = json.load(open(tpath))
         if tj.get("envs") == B and tj.get("horizon") == H and tj.get("dtype") == a.dtype:
             traffic, traffic_src = tj["dram_bytes_read"] + tj["dram_bytes_write"], tj.get("source")
+            if peaks_ok and tj.get("smem_wavefronts"):
+                # shared-memory data pipe: wavefronts per launch (ncu capture of this command; one wavefront = one 128-byte pass
+                # of the LSU data pipe, 1 per clock per SM) over the kernel duration measured live, against the LDS.128 probe
+                ach = tj["smem_wavefronts"] * 128.0 / kern_s / 1e9
+                smem = {"bound": "shared-memory data pipe (LSU wavefronts x 128 B)", "achieved": ach, "peak": pk[2], "unit": "GB/s",
+                        "frac": ach / pk[2], "wavefronts_per_launch": tj["smem_wavefronts"],
+                        "ncu_pct_of_peak_elapsed": tj.get("smem_pipe_pct_of_peak_elapsed_ncu"),
+                        "ncu_l1tex_pct_of_peak_active": tj.get("l1tex_throughput_pct_active_ncu"),
+                        "note": "the busiest unit of the solve kernel in the ncu capture (l1tex__data_pipe_lsu_wavefronts_mem_shared): "
+                                "the factor lives in shared memory and every multiply-add of the left-looking update reads it"}
 
     cpu = None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
@@ -468,6 +478,8 @@ def run_ours(a):
             "solver": {"fallback_envs": fallback, "unverified_envs": unverified, "envs_checked": int(S * B)},
             "clocks": clocks,
         }
+        if smem is not None:
+            line["roofline_smem"] = smem
         if cpu is not None:
             line["cpu_baseline"] = cpu
         print(json.dumps(line), flush=True)
