@@ -117,6 +117,19 @@ int mpcq_solve(mpcq_handle* h, int32_t B,
                void* stream);
 
 /*
+ * Warm start of the active-set rounds (no reference counterpart: its solver starts cold at every update, mpc.py:277-286).
+ * `faces_in` / `faces_out` are device arrays [B,4H], one byte per foot-step: (sx & 3) | (sy & 3) << 2 | (sz & 3) << 4 with
+ * sx, sy in {-1,0,+1} (fx = sx mu fz / free; -1 stored as 3), sz in {-1,0,+1} (f = 0 / free / fz = fz_max); a zero byte = all
+ * free, so a zeroed buffer is a cold start.  Until changed, every following mpcq_solve of this handle starts from `faces_in`
+ * (NULL = cold) and writes the faces of the point it returns to `faces_out` (NULL = not wanted; zeros for unverified
+ * environments).  In a control loop hand the previous update's `faces_out`, shifted by one horizon step (4 bytes), back as
+ * `faces_in`: consecutive updates share most of their active set, and a correct guess is verified with ONE factorisation.
+ * The optimum is unique, so the result does not depend on the guess (only the number of rounds does).
+ * mpcq_solve_host always starts cold.
+ */
+int mpcq_set_warm_start(mpcq_handle* h, const uint8_t* faces_in, uint8_t* faces_out);
+
+/*
  * replaces, for B robots and in ONE elementwise kernel, everything the reference does between the simulator
  * state and _solve_mpc: ModelPredictiveController.update_robot_state (mpc.py:55-79, quat -> ZYX angles,
  * kinematics.py:40-49), the preamble of update_mpc_if_needed (:83-93, command rotation and the dt_control

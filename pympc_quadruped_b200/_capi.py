@@ -82,6 +82,8 @@ def bind(lib: C.CDLL) -> C.CDLL:
     lib.mpcq_last_kernel_ms.restype = C.c_int
     lib.mpcq_gait_tables.argtypes = [C.c_void_p, C.c_int32] + [C.c_void_p] * 4 + [C.c_int32] + [C.c_void_p] * 4
     lib.mpcq_gait_tables.restype = C.c_int
+    lib.mpcq_set_warm_start.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.mpcq_set_warm_start.restype = C.c_int
     lib.mpcq_measure_peaks.argtypes = [C.c_int32, C.POINTER(C.c_double)]
     lib.mpcq_measure_peaks.restype = C.c_int
     return lib
@@ -89,7 +91,7 @@ def bind(lib: C.CDLL) -> C.CDLL:
 
 EXPORTS = ("mpcq_version", "mpcq_create", "mpcq_destroy", "mpcq_last_error", "mpcq_solve",
            "mpcq_solve_host", "mpcq_build_qp", "mpcq_assemble", "mpcq_last_launch_count", "mpcq_set_profiling",
-           "mpcq_last_kernel_ms", "mpcq_measure_peaks", "mpcq_gait_tables")
+           "mpcq_last_kernel_ms", "mpcq_measure_peaks", "mpcq_gait_tables", "mpcq_set_warm_start")
 
 _lib = None
 

@@ -82,9 +82,11 @@ def quat_to_zyx(q: torch.Tensor) -> torch.Tensor:
 
 class BatchedModelPredictiveController:
     def __init__(self, mpc_config, robot_config, num_envs: int, device="cuda:0", dtype=torch.float32, engine=None,
-                 fused=None, **solver_knobs):
+                 fused=None, warm_start=False, **solver_knobs):
         """`engine` is for dependency injection in tests (an object with MpcqEngine.solve's signature);
-        by default the CUDA engine is created and a missing GPU / library raises."""
+        by default the CUDA engine is created and a missing GPU / library raises.
+        `warm_start`: start every MPC update from the previous update's active faces shifted by one horizon step
+        (`mpcq_set_warm_start`); the optimum is unique, so only the number of active-set rounds changes."""
         c = extract_mpc_constants(mpc_config, robot_config)
         self.num_envs = int(num_envs)
         self.device = torch.device(device)
@@ -116,6 +118,9 @@ class BatchedModelPredictiveController:
         self.contact_forces = torch.zeros((B, 12), dtype=dtype, device=dev)
         self.ref_traj = torch.zeros((B, 13 * self.horizon), dtype=dtype if self._fused else torch.float32, device=dev)
         self.last_result = None
+        self.warm_start = bool(warm_start)
+        self._faces = torch.zeros((B, 4 * self.horizon), dtype=torch.uint8, device=dev) if self.warm_start else None
+        self._faces_in = torch.zeros_like(self._faces) if self.warm_start else None
 
     # reference attribute names (mpc.py:85-92,143-150) as views of the packed state
     xpos_base_desired = property(lambda self: self._xy_des[:, 0], lambda self, v: self._xy_des[:, 0].copy_(torch.as_tensor(v)))
@@ -224,8 +229,14 @@ class BatchedModelPredictiveController:
         gait = gait.to(device=self.device, dtype=torch.float32).reshape(-1, gait.shape[-1])[:, :4 * H]
         if gait.shape[0] == 1 and B > 1:
             gait = gait.expand(B, 4 * H)
+        warm = {}
+        if self.warm_start:
+            # the previous update's faces, one horizon step later (the contact table advances one step per update)
+            self._faces_in[:, :4 * (H - 1)] = self._faces[:, 4:]
+            self._faces_in[:, 4 * (H - 1):] = self._faces[:, 4 * (H - 1):]
+            warm = dict(faces_in=self._faces_in, faces_out=self._faces)
         res = self.engine.solve(self.current_state.to(self.dtype), self.pos_base_feet.to(self.dtype),
-                                gait.contiguous(), ref_traj.to(self.dtype), yaw=self.yaw.to(self.dtype))
+                                gait.contiguous(), ref_traj.to(self.dtype), yaw=self.yaw.to(self.dtype), **warm)
         self.last_result = res
         return res.forces
 

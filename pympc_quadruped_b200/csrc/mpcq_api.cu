@@ -284,6 +284,9 @@ struct mpcq_handle {
     uint8_t* bucket[2] = {nullptr, nullptr};
     size_t perm_cap[2] = {0, 0};
     bool schedule = true;
+    // warm start of the next mpcq_solve calls (mpcq_set_warm_start)
+    const uint8_t* face_in = nullptr;
+    uint8_t* face_out = nullptr;
 };
 
 namespace {
@@ -428,6 +431,8 @@ IO<T> make_io(int B, const void* x0, const void* yaw, const void* r_feet, const 
     io.active = active;
     io.perm = nullptr;
     io.B = B;
+    io.face_in = nullptr;
+    io.face_out = nullptr;
     return io;
 }
 
@@ -508,10 +513,16 @@ static int solve_impl(mpcq_handle* h, int32_t B, const void* x0, const void* yaw
     int32_t* perm = (h->schedule && h->perm[slot]) ? h->perm[slot] + off : nullptr;
     uint8_t* bucket = (h->schedule && h->bucket[slot]) ? h->bucket[slot] + off : nullptr;
     cudaError_t e;
-    if (h->cfg.dtype == MPCQ_F64)
-        e = launch_all<double>(h, make_io<double>(B, x0, yaw, r_feet, gait, x_ref, f_out, u_full, iters, resid, status, active), perm, bucket, st);
-    else
-        e = launch_all<float>(h, make_io<float>(B, x0, yaw, r_feet, gait, x_ref, f_out, u_full, iters, resid, status, active), perm, bucket, st);
+    const bool warm = slot == 0;                               // the device entry point honours mpcq_set_warm_start
+    if (h->cfg.dtype == MPCQ_F64) {
+        IO<double> io = make_io<double>(B, x0, yaw, r_feet, gait, x_ref, f_out, u_full, iters, resid, status, active);
+        if (warm) { io.face_in = h->face_in; io.face_out = h->face_out; }
+        e = launch_all<double>(h, io, perm, bucket, st);
+    } else {
+        IO<float> io = make_io<float>(B, x0, yaw, r_feet, gait, x_ref, f_out, u_full, iters, resid, status, active);
+        if (warm) { io.face_in = h->face_in; io.face_out = h->face_out; }
+        e = launch_all<float>(h, io, perm, bucket, st);
+    }
     return cuda_ok(h, e, "mpcq_solve launch") ? MPCQ_OK : MPCQ_ERR_CUDA;
 }
 
@@ -526,6 +537,13 @@ int mpcq_solve(mpcq_handle* h, int32_t B, const void* x0, const void* yaw, const
     const int rc = ensure_perm(h, 0, (size_t)B);
     if (rc != MPCQ_OK) return rc;
     return solve_impl(h, B, x0, yaw, r_feet, gait, x_ref, f_out, u_full, iters, resid, status, active, 0, 0, static_cast<cudaStream_t>(stream));
+}
+
+int mpcq_set_warm_start(mpcq_handle* h, const uint8_t* faces_in, uint8_t* faces_out) {
+    if (!h) return MPCQ_ERR_INVALID;
+    h->face_in = faces_in;
+    h->face_out = faces_out;
+    return MPCQ_OK;
 }
 
 int mpcq_build_qp(mpcq_handle* h, int32_t B, const void* x0, const void* yaw, const void* r_feet, const float* gait,

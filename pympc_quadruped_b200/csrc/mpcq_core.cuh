@@ -86,7 +86,14 @@ template <class T> struct IO {
     uint8_t* active;       // [B,4H] or null
     const int32_t* perm;   // [B] launch order (expected-work-first schedule) or null = natural order
     int B;
+    // warm start (mpcq_set_warm_start): one face code per foot-step, (sx & 3) | (sy & 3) << 2 | (sz & 3) << 4 with -1 stored
+    // as 3, so that a zeroed buffer means "every face free" = cold start
+    const uint8_t* face_in;   // [B,4H] or null
+    uint8_t* face_out;        // [B,4H] or null
 };
+
+MPCQ_DEV int face_decode(int c) { c &= 3; return c == 3 ? -1 : (c == 2 ? 0 : c); }
+MPCQ_DEV int face_encode(int sx, int sy, int sz) { return (sx & 3) | ((sy & 3) << 2) | ((sz & 3) << 4); }
 
 enum : int { ST_VERIFIED = 1, ST_FALLBACK = 2, ST_MAXITER = 4, ST_NUMERIC = 8, ST_NO_STANCE = 32 };
 
@@ -1307,7 +1314,9 @@ MPCQ_DEV void solve_env(const Consts& cs, const IO<T>& io, int b, char* smem, T*
                 if (k >= 0) w.cidx[k] = (uint8_t)((st && pos < NCAP / 3) ? pos : 255);
                 if (st && pos < NCAP / 3) {
                     w.fk[pos] = (uint8_t)k; w.fo[pos] = (uint8_t)pos; w.fmax[pos] = fm;
-                    w.face[3 * pos] = 0; w.face[3 * pos + 1] = 0; w.face[3 * pos + 2] = 0;
+                    const int code = io.face_in ? io.face_in[(size_t)b * 4 * H + k] : 0;      // 0 = all free (cold start)
+                    w.face[3 * pos] = (int8_t)face_decode(code); w.face[3 * pos + 1] = (int8_t)face_decode(code >> 2);
+                    w.face[3 * pos + 2] = (int8_t)face_decode(code >> 4);
                     w.facef[3 * pos] = 99; w.facef[3 * pos + 1] = 99; w.facef[3 * pos + 2] = 99;
                 }
             }
@@ -1469,6 +1478,17 @@ MPCQ_DEV void solve_env(const Consts& cs, const IO<T>& io, int b, char* smem, T*
             T* fo = io.f_out + (size_t)b * 12 + 3 * k;
             fo[0] = (T)f[0]; fo[1] = (T)f[1]; fo[2] = (T)f[2];
         }
+    }
+    if (io.face_out) {                                          // faces of the returned point, for the next update's warm start
+        uint8_t* fo = io.face_out + (size_t)b * 4 * H;
+        for (int k = lane; k < 4 * H; k += w.t.nt) fo[k] = 0;
+        team::sync(w.t);
+        if ((status & ST_VERIFIED) && ns > 0)
+            for (int p = lane; p < w.ns; p += w.t.nt)
+            {
+                const int sz = w.face[3 * p + 2];                // apex: sx, sy carry no information - canonical code
+                fo[w.fk[p]] = (uint8_t)face_encode(sz < 0 ? 0 : w.face[3 * p], sz < 0 ? 0 : w.face[3 * p + 1], sz);
+            }
     }
     pviol = team::reduce_max(w.t, pviol);
     if (lane == 0) {

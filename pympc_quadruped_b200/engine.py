@@ -78,8 +78,10 @@ class MpcqEngine:
         if rc != 0:
             raise RuntimeError(f"{what} failed ({rc}): {self.lib.mpcq_last_error(self._h).decode()}")
 
-    def solve(self, x0, r_feet, gait, x_ref, yaw=None, want=("u", "iters", "resid", "status", "active"), out=None):
-        """x0 [B,13], r_feet [B,12] or [B,4,3], gait float32 [B,4H], x_ref [B,13H], yaw [B] optional."""
+    def solve(self, x0, r_feet, gait, x_ref, yaw=None, want=("u", "iters", "resid", "status", "active"), out=None,
+              faces_in=None, faces_out=None):
+        """x0 [B,13], r_feet [B,12] or [B,4,3], gait float32 [B,4H], x_ref [B,13H], yaw [B] optional.
+        `faces_in` / `faces_out`: uint8 [B,4H] warm-start face codes (`mpcq_set_warm_start`); zeros = cold start."""
         B, H = x0.shape[0], self.horizon
         x0 = self._check("x0", x0, (B, 13), self.dtype)
         r_feet = self._check("r_feet", r_feet.reshape(B, 12), (B, 12), self.dtype)
@@ -97,9 +99,19 @@ class MpcqEngine:
                 status=mk((B,), torch.int32) if "status" in want else None,
                 active=mk((B, 4 * H), torch.uint8) if "active" in want else None)
         stream = torch.cuda.current_stream(self.device).cuda_stream
-        rc = self.lib.mpcq_solve(self._h, B, _ptr(x0), _ptr(yaw), _ptr(r_feet), _ptr(gait), _ptr(x_ref),
-                                 _ptr(out.forces), _ptr(out.u), _ptr(out.iters), _ptr(out.resid), _ptr(out.status),
-                                 _ptr(out.active), C.c_void_p(stream))
+        warm = faces_in is not None or faces_out is not None
+        if warm:
+            for name, t in (("faces_in", faces_in), ("faces_out", faces_out)):
+                if t is not None and self._check(name, t, (B, 4 * H), torch.uint8) is not t:
+                    raise ValueError(f"{name} must be a contiguous uint8 tensor on the engine's device")
+            self._err(self.lib.mpcq_set_warm_start(self._h, _ptr(faces_in), _ptr(faces_out)), "mpcq_set_warm_start")
+        try:
+            rc = self.lib.mpcq_solve(self._h, B, _ptr(x0), _ptr(yaw), _ptr(r_feet), _ptr(gait), _ptr(x_ref),
+                                     _ptr(out.forces), _ptr(out.u), _ptr(out.iters), _ptr(out.resid), _ptr(out.status),
+                                     _ptr(out.active), C.c_void_p(stream))
+        finally:
+            if warm:
+                self.lib.mpcq_set_warm_start(self._h, None, None)
         self._err(rc, "mpcq_solve")
         return out
 

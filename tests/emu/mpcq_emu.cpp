@@ -133,7 +133,8 @@ template <class T> void lane_entry(void* p) {
 
 template <class T>
 int run(const mpcq_config* cfg, int B, const T* x0, const T* yaw, const T* feet, const float* gait, const T* xref,
-        T* f_out, T* u_full, int32_t* iters, double* resid, int32_t* status, uint8_t* active) {
+        T* f_out, T* u_full, int32_t* iters, double* resid, int32_t* status, uint8_t* active,
+        const uint8_t* faces_in = nullptr, uint8_t* faces_out = nullptr) {
     mpcq::Consts consts;
     std::string err;
     if (!mpcq::consts_from_config(*cfg, consts, err)) return MPCQ_ERR_INVALID;
@@ -144,7 +145,7 @@ int run(const mpcq_config* cfg, int B, const T* x0, const T* yaw, const T* feet,
         for (int b = 0; b < B; ++b) {
             Job<T> j;
             j.cs = *cs;
-            j.io = mpcq::IO<T>{x0, yaw, feet, gait, xref, f_out, u_full, iters, resid, status, active, nullptr, B};
+            j.io = mpcq::IO<T>{x0, yaw, feet, gait, xref, f_out, u_full, iters, resid, status, active, nullptr, B, faces_in, faces_out};
             j.b = b;
             j.smem = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(smem.data()) + 31) & ~uintptr_t(31));
             j.lglobal = nullptr;
@@ -166,6 +167,11 @@ int mpcq_emu_solve_f32(const mpcq_config* cs, int B, const float* x0, const floa
                        const float* xref, float* f_out, float* u_full, int32_t* iters, double* resid, int32_t* status,
                        uint8_t* active) {
     return run<float>(cs, B, x0, yaw, feet, gait, xref, f_out, u_full, iters, resid, status, active);
+}
+int mpcq_emu_solve_warm_f32(const mpcq_config* cs, int B, const float* x0, const float* yaw, const float* feet, const float* gait,
+                            const float* xref, float* f_out, float* u_full, int32_t* iters, double* resid, int32_t* status,
+                            uint8_t* active, const uint8_t* faces_in, uint8_t* faces_out) {
+    return run<float>(cs, B, x0, yaw, feet, gait, xref, f_out, u_full, iters, resid, status, active, faces_in, faces_out);
 }
 int mpcq_emu_solve_f64(const mpcq_config* cs, int B, const double* x0, const double* yaw, const double* feet, const float* gait,
                        const double* xref, double* f_out, double* u_full, int32_t* iters, double* resid, int32_t* status,

@@ -442,3 +442,109 @@ def test_device_gait_tables_equal_the_reference_schedule():
     x0, feet, _, xref, yaw = _to_dev(batch, torch.float32)
     res = eng.solve(x0, feet, bg.get_gait_table(), xref, yaw=yaw)
     assert np.all(res.status.cpu().numpy() & _capi.ST_VERIFIED)
+
+
+def test_warm_start_same_optimum_one_factorisation():
+    """mpcq_set_warm_start on the device: a solve's own faces are verified with ONE factorisation; arbitrary guesses end at
+    the same (unique) optimum; zeroed faces are the cold start bit for bit."""
+    batch = make_batch(A1Config, 10, 256, "mixed", (Gait.TROTTING10,), 51, solve=False)
+    eng = _engine(batch, A1Config, torch.float32)
+    x0, feet, gait, xref, yaw = _to_dev(batch, torch.float32)
+    cold = eng.solve(x0, feet, gait, xref, yaw=yaw)
+    faces = torch.full((256, 40), 0xEE, dtype=torch.uint8, device="cuda:0")
+    zero = torch.zeros_like(faces)
+    c2 = eng.solve(x0, feet, gait, xref, yaw=yaw, faces_in=zero, faces_out=faces)
+    assert torch.equal(c2.u, cold.u) and torch.equal(c2.iters, cold.iters)
+    assert torch.all(faces[gait == 0] == 0) and torch.all((faces & 0xC0) == 0)
+    out2 = torch.empty_like(faces)
+    warm = eng.solve(x0, feet, gait, xref, yaw=yaw, faces_in=faces, faces_out=out2)
+    assert torch.all(warm.status & _capi.ST_VERIFIED) and torch.all(warm.iters[:, 0] == 1)
+    assert torch.equal(out2, faces)
+    assert (warm.u.double() - cold.u.double()).abs().max() <= 2e-4
+    assert float(cold.iters[:, 0].float().mean()) > 3.0
+    guess = torch.randint(0, 256, faces.shape, dtype=torch.uint8, device="cuda:0")
+    rnd = eng.solve(x0, feet, gait, xref, yaw=yaw, faces_in=guess)
+    assert torch.all(rnd.status & _capi.ST_VERIFIED)
+    tol = torch.clamp(REL_TOL * cold.u.double().abs().amax(dim=1), min=ABS_TOL)
+    assert torch.all((rnd.u.double() - cold.u.double()).abs().amax(dim=1) <= tol)
+    # the handle is back to cold starts afterwards
+    again = eng.solve(x0, feet, gait, xref, yaw=yaw)
+    assert torch.equal(again.u, cold.u)
+
+
+def test_controller_warm_start_tracks_the_cold_controller():
+    """BatchedModelPredictiveController(warm_start=True) over a drifting state sequence with an advancing gait: same forces
+    as the cold controller within the parity tolerance, fewer factorisations."""
+    from pympc_quadruped_b200.controller import BatchedModelPredictiveController, BatchedRobotData
+    from pympc_quadruped_b200.configs import with_horizon
+    from pympc_quadruped_b200.synth import synth_states
+    from pympc_quadruped_b200 import BatchedGaitSchedule
+    B, H = 512, 10
+    st = synth_states(B, A1Config, "mixed", seed=61)
+    rng = np.random.default_rng(61)
+    drift = {k: rng.normal(size=st[k].shape) for k in ("pos_base", "ang_vel_base", "lin_vel_base")}
+    ctrls = [BatchedModelPredictiveController(with_horizon(H), A1Config, B, warm_start=w) for w in (False, True)]
+    gaits = BatchedGaitSchedule(ctrls[0].engine, [Gait.TROTTING10.with_horizon(H)] * B)
+    dv = lambda a: torch.as_tensor(a, device="cuda:0")
+    nfac = [[], []]
+    for t in range(8):
+        rd = BatchedRobotData(dv(st["quat_base"]), dv(st["pos_base"] + 0.001 * t * drift["pos_base"]),
+                              dv(st["ang_vel_base"] + 0.01 * t * drift["ang_vel_base"]),
+                              dv(st["lin_vel_base"] + 0.01 * t * drift["lin_vel_base"]), dv(st["pos_base_feet"]), dv(st["R_base"]))
+        it = t * ctrls[0].iterations_between_mpc
+        gaits.set_iteration(ctrls[0].iterations_between_mpc, it)
+        forces = []
+        for i, c in enumerate(ctrls):
+            c.update_robot_state(rd)
+            forces.append(c.update_mpc_if_needed(it, dv(st["vel_cmd_body"]), dv(st["yaw_rate_cmd"]), gaits.get_gait_table()).double())
+            assert torch.all(c.last_result.status & _capi.ST_VERIFIED)
+            nfac[i].append(float(c.last_result.iters[:, 0].float().mean()))
+        tol = torch.clamp(REL_TOL * forces[0].abs().amax(dim=1), min=ABS_TOL)
+        assert torch.all((forces[0] - forces[1]).abs().amax(dim=1) <= tol), t
+    # (the states here do not follow the model's prediction, so the shifted faces are only a rough guess)
+    assert np.mean(nfac[1][1:]) <= np.mean(nfac[0][1:]) + 0.05, nfac
+    print(f"factorisations per update: cold {np.mean(nfac[0][1:]):.2f}, warm {np.mean(nfac[1][1:]):.2f}")
+
+
+def test_warm_start_on_a_model_consistent_rollout():
+    """Closed loop in the MPC's own model: the state advances one horizon step under the first-step forces (Ad, Bd of the
+    reference construction), the contact table and the reference trajectory shift by one step.  By the principle of
+    optimality the shifted previous faces are then (nearly) the new optimum's faces: the warm-started solves must give the
+    cold solves' forces with far fewer factorisations."""
+    from oracle.mpc_oracle import state_space_model, discretize
+    from pympc_quadruped_b200.gait import gait_tables
+    from pympc_quadruped_b200.synth import synth_gait_params
+    B, H, T = 96, 10, 6
+    batch = make_batch(A1Config, H, B, "mixed", (Gait.TROTTING10,), 71, solve=False)
+    eng = _engine(batch, A1Config, torch.float32)
+    off, dur, seg, it0 = synth_gait_params(B, (Gait.TROTTING10,), 71)
+    x0 = batch["x0"].astype(np.float64); feet = batch["feet"].astype(np.float64).copy(); xref = batch["xref"].astype(np.float64).reshape(B, H, 13).copy()
+    yaw = batch["yaw"].astype(np.float64).copy()
+    inertia = np.asarray(A1Config.base_inertia_base, dtype=np.float32)
+    faces = torch.zeros((B, 4 * H), dtype=torch.uint8, device="cuda:0")
+    fin = torch.zeros_like(faces)
+    t32 = lambda a: torch.as_tensor(np.ascontiguousarray(a), dtype=torch.float32, device="cuda:0")
+    nf_cold, nf_warm = [], []
+    for t in range(T):
+        gait = gait_tables(off, dur, seg, it0 + t, H)
+        args = (t32(x0), t32(feet), t32(gait), t32(xref.reshape(B, 13 * H)))
+        cold = eng.solve(*args, yaw=t32(yaw))
+        fin[:, :4 * (H - 1)] = faces[:, 4:]
+        fin[:, 4 * (H - 1):] = faces[:, 4 * (H - 1):]
+        warm = eng.solve(*args, yaw=t32(yaw), faces_in=fin if t > 0 else None, faces_out=faces)
+        assert torch.all(cold.status & _capi.ST_VERIFIED) and torch.all(warm.status & _capi.ST_VERIFIED)
+        tol = torch.clamp(REL_TOL * cold.u.double().abs().amax(dim=1), min=ABS_TOL)
+        assert torch.all((warm.u.double() - cold.u.double()).abs().amax(dim=1) <= tol), t
+        nf_cold.append(float(cold.iters[:, 0].float().mean())); nf_warm.append(float(warm.iters[:, 0].float().mean()))
+        u0 = cold.forces.double().cpu().numpy()
+        for b in range(B):                                    # one model step under the applied forces
+            Ac, Bc = state_space_model(yaw[b], feet[b].reshape(4, 3), inertia, float(A1Config.mass_base))
+            Ad, Bd = discretize(Ac, Bc, 0.05)
+            xn = Ad.astype(np.float64) @ x0[b] + Bd.astype(np.float64) @ u0[b]
+            feet[b] -= np.tile(xn[3:6] - x0[b, 3:6], 4)       # feet stay where they are in the world
+            x0[b] = xn
+            yaw[b] = xn[2]
+        xref[:, :-1] = xref[:, 1:].copy()
+        xref[:, -1, 2:5] += xref[:, -1, 2:5] - xref[:, -3, 2:5] if H > 2 else 0.0
+    print(f"model-consistent rollout: factorisations per update cold {np.mean(nf_cold[1:]):.2f}, warm {np.mean(nf_warm[1:]):.2f}")
+    assert np.mean(nf_warm[1:]) < 0.75 * np.mean(nf_cold[1:]), (nf_cold, nf_warm)

@@ -117,3 +117,42 @@ def test_internal_overflow_is_flagged(emu_lib):
             assert not (out["status"][b] & _capi.ST_VERIFIED) or np.all(np.isfinite(out["u"][b]))
         for b in (0, 3):
             assert out["status"][b] & _capi.ST_VERIFIED
+
+
+def emu_solve_warm(lib, batch, robot, faces_in, **knobs):
+    B, H = batch["B"], batch["horizon"]
+    cfg = _capi.make_config(extract_mpc_constants(batch["cfg"], robot), _capi.MPCQ_F32, **knobs)
+    rt = np.float32
+    x0, yaw, feet, xref = (batch[k].astype(rt) for k in ("x0", "yaw", "feet", "xref"))
+    gait = np.ascontiguousarray(batch["gait"], dtype=np.float32)
+    out = dict(f=np.zeros((B, 12), rt), u=np.zeros((B, 12 * H), rt), iters=np.zeros((B, 2), np.int32),
+               resid=np.zeros((B, 2)), status=np.zeros(B, np.int32), active=np.zeros((B, 4 * H), np.uint8),
+               faces=np.full((B, 4 * H), 0xEE, np.uint8))
+    p = lambda a: None if a is None else a.ctypes.data_as(C.c_void_p)
+    rc = lib.mpcq_emu_solve_warm_f32(C.byref(cfg), B, p(x0), p(yaw), p(feet), p(gait), p(xref), p(out["f"]), p(out["u"]),
+                                     p(out["iters"]), p(out["resid"]), p(out["status"]), p(out["active"]), p(faces_in), p(out["faces"]))
+    assert rc == 0
+    return out
+
+
+def test_warm_start_same_optimum_fewer_rounds(emu_lib):
+    """mpcq_set_warm_start: the faces a solve returns, handed back, are verified with ONE factorisation; a wrong guess
+    (all apex / random codes) still ends at the same (unique) optimum; swing foot-steps report code 0."""
+    batch = make_batch(A1Config, 10, 10, "aggressive", (Gait.TROTTING10,), 41)
+    cold = emu_solve_warm(emu_lib, batch, A1Config, None)
+    check_against_oracle(cold, batch, False)
+    assert np.array_equal(cold["u"], emu_solve(emu_lib, batch, A1Config, False)["u"])        # NULL faces_in = the cold path
+    assert cold["iters"][:, 0].max() > 2
+    stance = batch["gait"] > 0
+    assert np.all(cold["faces"][~stance] == 0) and np.all((cold["faces"] & 0xC0) == 0)
+    warm = emu_solve_warm(emu_lib, batch, A1Config, cold["faces"])
+    check_against_oracle(warm, batch, False)
+    assert np.all(warm["iters"][:, 0] == 1), warm["iters"][:, 0]
+    assert np.array_equal(warm["faces"], cold["faces"])
+    assert np.abs(warm["u"].astype(np.float64) - cold["u"]).max() <= 2e-4
+    rng = np.random.default_rng(3)
+    for guess in (np.full_like(cold["faces"], 0x30), rng.integers(0, 256, size=cold["faces"].shape).astype(np.uint8)):
+        out = emu_solve_warm(emu_lib, batch, A1Config, guess)
+        check_against_oracle(out, batch, False)                  # same optimum, same constraint activity
+        # the face codes may differ only on weakly active rows (tight with a zero multiplier: in or out of the face)
+        assert (out["faces"] != cold["faces"]).sum() <= 2
