@@ -628,8 +628,7 @@ MPCQ_DEV bool chol_factor(const Consts& cs, Work<T>& w, int k_start) {
                     MPCQ_UNROLL
                     for (int m = 0; m < NSLOT; ++m) {
                         if (m < m0) continue;
-                        const T lr = l[t][m];
-                        acc[m][0] -= lr * p[t][0]; acc[m][1] -= lr * p[t][1]; acc[m][2] -= lr * p[t][2]; acc[m][3] -= lr * p[t][3];
+                        wp::fma4_sub(acc[m], l[t][m], p[t]);       // acc[m][c] -= l * p[c] (packed FFMA2 pairs in fp32)
                     }
                 }
             };

@@ -99,6 +99,20 @@ MPCQ_DEV int sel(bool p, int a, int b) {
 }
 #endif
 
+// a[c] -= l * p[c], c = 0..3.  fp32 on sm_100a: two packed FFMA2 (fma.rn.f32x2, two IEEE fmas per instruction - same
+// results as four scalar FFMAs) with the negated multiplier duplicated into a register pair.
+template <class V> MPCQ_DEV void fma4_sub(V (&a)[4], V l, const V (&p)[4]) {
+    a[0] -= l * p[0]; a[1] -= l * p[1]; a[2] -= l * p[2]; a[3] -= l * p[3];
+}
+#if !defined(MPCQ_HOST_EMU) && !defined(MPCQ_NO_FFMA2)
+MPCQ_DEV void fma4_sub(float (&a)[4], float l, const float (&p)[4]) {
+    const float2 nl = make_float2(-l, -l);
+    const float2 r01 = __ffma2_rn(nl, make_float2(p[0], p[1]), make_float2(a[0], a[1]));
+    const float2 r23 = __ffma2_rn(nl, make_float2(p[2], p[3]), make_float2(a[2], a[3]));
+    a[0] = r01.x; a[1] = r01.y; a[2] = r23.x; a[3] = r23.y;
+}
+#endif
+
 #ifdef MPCQ_HOST_EMU
 MPCQ_DEV int team_tid() { return mpcq_emu::thread_id(); }
 MPCQ_DEV void team_sync() { mpcq_emu::team_barrier(); }
