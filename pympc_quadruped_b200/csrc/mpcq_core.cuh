@@ -597,13 +597,12 @@ MPCQ_DEV bool chol_factor(const Consts& cs, Work<T>& w, int k_start) {
                 for (int g = 0; g < ng; ++g) {
                     MPCQ_UNROLL
                     for (int t = 0; t < 4; ++t) {
-                        T p0, p1, p2, p3;
-                        load4(col + k0, p0, p1, p2, p3);
+                        T p[4];
+                        load4(col + k0, p[0], p[1], p[2], p[3]);
                         MPCQ_UNROLL
                         for (int m = 0; m < NSLOT; ++m) {
                             if (m < m0) continue;
-                            const T lr = col[row0 + RSTEP * m];
-                            acc[m][0] -= lr * p0; acc[m][1] -= lr * p1; acc[m][2] -= lr * p2; acc[m][3] -= lr * p3;
+                            wp::fma4_sub(acc[m], col[row0 + RSTEP * m], p);
                         }
                         col += stride;
                     }
