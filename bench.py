@@ -526,7 +526,8 @@ def run_ours(a):
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                          "traffic": traffic, "traffic_source": traffic_src, "algorithmic_bytes_per_launch": ALGO_BYTES(H) * (rs // 4) * B,
                          "peak_source": peak_src,
-                         "note": "the path is not HBM-bound (732 B/solve): latency/shared-memory bound, see roofline_compute"},
+                         "note": "the path is not HBM-bound (732 B/solve; traffic = algorithmic bytes, nothing re-read): the busiest unit is the "
+                                 "shared-memory data pipe (roofline_smem, ~50 % of peak in the ncu capture); flop rates in roofline_compute"},
             "roofline_compute": {"bound": "fp64 fma" if a.dtype == "f64" else "fp32 fma",
                                  "peak_tflops_measured": fma_peak, "fp32_fma_tflops": pk[0] if peaks_ok else None,
                                  "fp64_fma_tflops": pk[1] if peaks_ok else None, "smem_load_gbs": pk[2] if peaks_ok else None,
