@@ -163,6 +163,54 @@ int mpcq_gait_tables(mpcq_handle* h, int32_t B, const int32_t* stance_offsets, c
                      double* swing_state, double* stance_state, void* stream);
 
 /*
+ * Constants of the per-leg layer: RobotConfig.Kp_swing / Kd_swing / swing_height (config/robot_configs.py:16-18,35-37,54-56),
+ * LinearMpcConfig.dt_control / gravity (config/linear_mpc_configs.py), and the landing height the reference hard-codes
+ * (linear_mpc/swing_foot_trajectory_generator.py:117).  Note the reference reads AliengoConfig.swing_height for every robot (:33).
+ */
+typedef struct mpcq_leg_params {
+    double kp_swing[9];             /* row-major 3x3 */
+    double kd_swing[9];
+    double swing_height;
+    double dt_control;
+    double gravity;                 /* positive */
+    double foot_z_final;            /* -0.0255 in the reference */
+} mpcq_leg_params;
+
+/*
+ * replaces, for B robots x 4 legs, SwingFootTrajectoryGenerator.set_foot_placement + compute_traj_swingfoot
+ * (linear_mpc/swing_foot_trajectory_generator.py:82-129, :65-80, :38-63) as called from the simulator loop
+ * (scripts/isaacgym_a1.py:143-158): one elementwise kernel, one thread per leg.  Device arrays, float64:
+ *   pos_base, lin_vel_base [B,3], R_base [B,9] (RobotData, utils/robot_data.py:70-76), base_pos_base_thighs [B,4,3] (:178-184),
+ *   pos_feet [B,4,3] world frame (:135-142), swing_state [B,4] (Gait.get_swing_state, e.g. from mpcq_gait_tables),
+ *   v_des_body [B,3], yaw_rate_des [B], swing_time, stance_time [B] (Gait.swing_time / stance_time, gait.py:68-74)
+ *   generator state, in/out, zero-initialised by the caller: swing_active [B,4] uint8 (0 = the next swing tick starts a new swing,
+ *   the reference's is_first_swing), remaining_swing_time [B,4], footpos_init, footpos_final [B,4,3] (world frame)
+ *   outputs: pos_targets, vel_targets [B,4,3]: swing-foot target relative to the base in the base frame; zero for legs with
+ *   swing_state <= 0, whose state is left untouched (the reference only calls the generator for swinging legs).
+ * The trajectory is Drake's PiecewisePolynomial.CubicHermite through (init, midpoint at swing_height, final) with zero slopes
+ * and float32 break points, evaluated with the time clamped to the break range.
+ */
+int mpcq_swing_targets(mpcq_handle* h, int32_t B, const mpcq_leg_params* lp, const double* pos_base, const double* lin_vel_base,
+                       const double* R_base, const double* base_pos_base_thighs, const double* pos_feet, const double* swing_state,
+                       const double* v_des_body, const double* yaw_rate_des, const double* swing_time, const double* stance_time,
+                       uint8_t* swing_active, double* remaining_swing_time, double* footpos_init, double* footpos_final,
+                       double* pos_targets, double* vel_targets, void* stream);
+
+/*
+ * replaces, for B robots, LegController.update (linear_mpc/leg_controller.py:38-91): stance legs tau = Jv^T (-f), swing legs
+ * tau = Jv^T (Kp (R p_des - R p) + Kd (R v_des - R v)), joint torques float32 [B,12] like the reference's torque_cmds.
+ *   Jv_feet [B,4,3,ncol] float64: ncol = 18 is RobotData.Jv_feet (utils/robot_data.py:119-133; columns 6+3 leg .. 6+3 leg+2 are
+ *   used, leg_controller.py:84,88), ncol = 3 is those joint blocks alone
+ *   R_base [B,9], base_pos_base_feet, base_vel_base_feet [B,4,3] float64 (utils/robot_data.py:151-167)
+ *   contact_forces [B,12] `real` (the f_out of mpcq_solve), swing_state [B,4] float64 (non-zero = swing),
+ *   pos_targets, vel_targets [B,4,3] float64 (mpcq_swing_targets)
+ */
+int mpcq_leg_torques(mpcq_handle* h, int32_t B, const mpcq_leg_params* lp, const double* Jv_feet, int32_t ncol, const double* R_base,
+                     const double* base_pos_base_feet, const double* base_vel_base_feet, const void* contact_forces,
+                     const double* swing_state, const double* pos_targets, const double* vel_targets, float* torque_cmds,
+                     void* stream);
+
+/*
  * Same call with HOST buffers (what a CPU-side simulator loop such as scripts/isaacgym_a1.py:119-164
  * would hand over): inputs are staged through pinned memory, copied to the device, solved and the
  * requested outputs copied back; returns after the results are in the caller's buffers.

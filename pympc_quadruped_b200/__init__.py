@@ -14,4 +14,7 @@ def __getattr__(name):
     if name in ("BatchedModelPredictiveController", "ModelPredictiveController", "BatchedRobotData"):
         from . import controller
         return getattr(controller, name)
+    if name in ("BatchedSwingFootTrajectoryGenerator", "BatchedLegController", "BatchedLegKinematics"):
+        from . import legs
+        return getattr(legs, name)
     raise AttributeError(name)

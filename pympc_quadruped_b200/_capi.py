@@ -58,6 +58,21 @@ def make_config(consts: dict, dtype: int = MPCQ_F32, device: int = 0, **knobs) -
 _SOLVE_ARGS = [C.c_void_p] * 5 + [C.c_void_p] * 6          # x0,yaw,feet,gait,xref | f,u,iters,resid,status,active
 
 
+class MpcqLegParams(C.Structure):
+    """mirror of `mpcq_leg_params` (include/mpcq.h)"""
+    _fields_ = [("kp_swing", C.c_double * 9), ("kd_swing", C.c_double * 9), ("swing_height", C.c_double),
+                ("dt_control", C.c_double), ("gravity", C.c_double), ("foot_z_final", C.c_double)]
+
+
+def make_leg_params(kp_swing, kd_swing, swing_height, dt_control, gravity, foot_z_final=-0.0255) -> MpcqLegParams:
+    import numpy as np
+    lp = MpcqLegParams()
+    lp.kp_swing[:] = [float(v) for v in np.asarray(kp_swing, dtype=np.float64).reshape(9)]
+    lp.kd_swing[:] = [float(v) for v in np.asarray(kd_swing, dtype=np.float64).reshape(9)]
+    lp.swing_height, lp.dt_control, lp.gravity, lp.foot_z_final = float(swing_height), float(dt_control), float(gravity), float(foot_z_final)
+    return lp
+
+
 def bind(lib: C.CDLL) -> C.CDLL:
     lib.mpcq_version.restype = C.c_int
     lib.mpcq_create.argtypes = [C.POINTER(MpcqConfig), C.POINTER(C.c_void_p)]
@@ -84,6 +99,10 @@ def bind(lib: C.CDLL) -> C.CDLL:
     lib.mpcq_gait_tables.restype = C.c_int
     lib.mpcq_set_warm_start.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     lib.mpcq_set_warm_start.restype = C.c_int
+    lib.mpcq_swing_targets.argtypes = [C.c_void_p, C.c_int32, C.POINTER(MpcqLegParams)] + [C.c_void_p] * 16 + [C.c_void_p]
+    lib.mpcq_swing_targets.restype = C.c_int
+    lib.mpcq_leg_torques.argtypes = [C.c_void_p, C.c_int32, C.POINTER(MpcqLegParams), C.c_void_p, C.c_int32] + [C.c_void_p] * 8 + [C.c_void_p]
+    lib.mpcq_leg_torques.restype = C.c_int
     lib.mpcq_measure_peaks.argtypes = [C.c_int32, C.POINTER(C.c_double)]
     lib.mpcq_measure_peaks.restype = C.c_int
     return lib
@@ -91,7 +110,8 @@ def bind(lib: C.CDLL) -> C.CDLL:
 
 EXPORTS = ("mpcq_version", "mpcq_create", "mpcq_destroy", "mpcq_last_error", "mpcq_solve",
            "mpcq_solve_host", "mpcq_build_qp", "mpcq_assemble", "mpcq_last_launch_count", "mpcq_set_profiling",
-           "mpcq_last_kernel_ms", "mpcq_measure_peaks", "mpcq_gait_tables", "mpcq_set_warm_start")
+           "mpcq_last_kernel_ms", "mpcq_measure_peaks", "mpcq_gait_tables", "mpcq_set_warm_start",
+           "mpcq_swing_targets", "mpcq_leg_torques")
 
 _lib = None
 

@@ -221,6 +221,55 @@ class MpcqEngine:
         self._err(rc, "mpcq_gait_tables")
         return table, swing_state, stance_state
 
+    def swing_targets(self, leg_params, pos_base, lin_vel_base, R_base, base_pos_base_thighs, pos_feet, swing_state, v_des_body,
+                      yaw_rate_des, swing_time, stance_time, state, pos_targets=None, vel_targets=None):
+        """Swing-foot targets of B robots x 4 legs (`mpcq_swing_targets`); `state` = (swing_active uint8 [B,4], remaining [B,4],
+        footpos_init [B,4,3], footpos_final [B,4,3]) is advanced in place."""
+        B, f64 = pos_base.shape[0], torch.float64
+        ins = [self._check(n, t, sh, f64) for n, t, sh in (
+            ("pos_base", pos_base, (B, 3)), ("lin_vel_base", lin_vel_base, (B, 3)), ("R_base", R_base.reshape(B, 9), (B, 9)),
+            ("base_pos_base_thighs", base_pos_base_thighs, (B, 4, 3)), ("pos_feet", pos_feet, (B, 4, 3)),
+            ("swing_state", swing_state, (B, 4)), ("v_des_body", v_des_body, (B, 3)), ("yaw_rate_des", yaw_rate_des, (B,)),
+            ("swing_time", swing_time, (B,)), ("stance_time", stance_time, (B,)))]
+        active, remaining, init, final = state
+        if pos_targets is None:
+            pos_targets = torch.empty((B, 4, 3), dtype=f64, device=self.device)
+        if vel_targets is None:
+            vel_targets = torch.empty((B, 4, 3), dtype=f64, device=self.device)
+        for n, t, sh, dt in (("swing_active", active, (B, 4), torch.uint8), ("remaining_swing_time", remaining, (B, 4), f64),
+                             ("footpos_init", init, (B, 4, 3), f64), ("footpos_final", final, (B, 4, 3), f64),
+                             ("pos_targets", pos_targets, (B, 4, 3), f64), ("vel_targets", vel_targets, (B, 4, 3), f64)):
+            if self._check(n, t, sh, dt) is not t:
+                raise ValueError(f"{n} must be contiguous (it is written in place)")
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        rc = self.lib.mpcq_swing_targets(self._h, B, C.byref(leg_params), *[_ptr(t) for t in ins], _ptr(active), _ptr(remaining),
+                                         _ptr(init), _ptr(final), _ptr(pos_targets), _ptr(vel_targets), C.c_void_p(stream))
+        self._err(rc, "mpcq_swing_targets")
+        return pos_targets, vel_targets
+
+    def leg_torques(self, leg_params, Jv_feet, R_base, base_pos_base_feet, base_vel_base_feet, contact_forces, swing_state,
+                    pos_targets, vel_targets, torque_cmds=None):
+        """Joint torques [B,12] float32 of B robots (`mpcq_leg_torques`); Jv_feet is [B,4,3,18] (reference layout) or [B,4,3,3]."""
+        B, f64 = R_base.shape[0], torch.float64
+        if Jv_feet.dim() != 4 or Jv_feet.shape[-1] not in (3, 18):
+            raise ValueError("Jv_feet must have shape [B,4,3,18] or [B,4,3,3]")
+        ncol = int(Jv_feet.shape[-1])
+        Jv_feet = self._check("Jv_feet", Jv_feet, (B, 4, 3, ncol), f64)
+        R_base = self._check("R_base", R_base.reshape(B, 9), (B, 9), f64)
+        ins = [self._check(n, t, sh, dt) for n, t, sh, dt in (
+            ("base_pos_base_feet", base_pos_base_feet, (B, 4, 3), f64), ("base_vel_base_feet", base_vel_base_feet, (B, 4, 3), f64),
+            ("contact_forces", contact_forces, (B, 12), self.dtype), ("swing_state", swing_state, (B, 4), f64),
+            ("pos_targets", pos_targets, (B, 4, 3), f64), ("vel_targets", vel_targets, (B, 4, 3), f64))]
+        if torque_cmds is None:
+            torque_cmds = torch.empty((B, 12), dtype=torch.float32, device=self.device)
+        elif self._check("torque_cmds", torque_cmds, (B, 12), torch.float32) is not torque_cmds:
+            raise ValueError("torque_cmds must be contiguous (it is written in place)")
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        rc = self.lib.mpcq_leg_torques(self._h, B, C.byref(leg_params), _ptr(Jv_feet), ncol, _ptr(R_base), *[_ptr(t) for t in ins],
+                                       _ptr(torque_cmds), C.c_void_p(stream))
+        self._err(rc, "mpcq_leg_torques")
+        return torque_cmds
+
     def set_profiling(self, enable: bool) -> None:
         self._err(self.lib.mpcq_set_profiling(self._h, int(bool(enable))), "mpcq_set_profiling")
 

@@ -129,6 +129,9 @@ class BatchedGaitSchedule:
         self._swing = torch.zeros((self.num_envs, 4), dtype=torch.float64, device=dev)
         self._stance = torch.zeros((self.num_envs, 4), dtype=torch.float64, device=dev)
         self._cur = torch.zeros((self.num_envs,), dtype=torch.int32, device=dev)
+        # Gait.swing_time / stance_time per robot (linear_mpc/gait.py:68-74), float64 like the reference's np.float64 products
+        self.swing_time = torch.as_tensor(np.array([float(s.swing_time) for s in scheds]), device=dev)
+        self.stance_time = torch.as_tensor(np.array([float(s.stance_time) for s in scheds]), device=dev)
 
     def set_iteration(self, iterations_between_mpc: int, cur_iteration) -> None:
         """`cur_iteration`: one control tick for all robots (int) or an int tensor [B] (robots out of phase)."""
