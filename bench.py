@@ -386,6 +386,57 @@ def run_ours(a):
     barrier()
     ctrl_ms = c0.elapsed_time(c1) / a.steps
 
+    # ---- the whole loop body of scripts/isaacgym_a1.py:136-162 for the batch on the device: controller tick above + swing-foot
+    # targets + joint torque map (mpcq_swing_targets, mpcq_leg_torques); synthetic kinematics (random foot
+    # Jacobians in the reference's 3x18 layout, thigh / foot positions) since pinocchio is the caller's side of the boundary
+    from pympc_quadruped_b200 import BatchedGaitSchedule, BatchedLegController, BatchedLegKinematics, BatchedSwingFootTrajectoryGenerator
+    from pympc_quadruped_b200.gait import GaitSchedule
+    f64 = torch.float64
+    lrng = torch.Generator(device=dev); lrng.manual_seed(SEED_BASE + 77 + rank)
+    ru = lambda *sh: torch.rand(*sh, generator=lrng, device=dev, dtype=f64) - 0.5
+    gs = BatchedGaitSchedule(c2.engine, [GaitSchedule("bench", int(gseg[i]), goff[i], gdur[i], horizon=H) for i in range(B)])
+    kins = [BatchedLegKinematics(rd.pos_base, rd.lin_vel_base, rd.R_base, 0.4 * ru(B, 4, 3), rd.pos_base[:, None, :] + rd.pos_base_feet,
+                                 ru(B, 4, 3), 2 * ru(B, 4, 3), ru(B, 4, 3, 18)) for rd in rds]
+    swing_gen = BatchedSwingFootTrajectoryGenerator(c2.engine, B, robot_config=robot)
+    leg_ctrl = BatchedLegController(c2.engine, B, robot.Kp_swing, robot.Kd_swing)
+    tick0 = gparams[0][3].clone()
+
+    def leg_step(s, forces):
+        k = s % len(rds)
+        gs.set_iteration(ibm, tick0 + s)                                           # swing states advance one control tick per step
+        pt, vt = swing_gen.update(kins[k], gs, cmds[k][0], cmds[k][1])
+        return leg_ctrl.update(kins[k], forces, gs.get_swing_state(), pt, vt)
+
+    def tick_step(s):
+        return leg_step(s, ctrl_step(s))
+    for s in range(a.warmup):
+        tick_step(s)
+    barrier()
+    c0.record()
+    for s in range(a.steps):
+        tick_step(a.warmup + s)
+    c1.record()
+    barrier()
+    tick_ms = c0.elapsed_time(c1) / a.steps
+    f_last = ctrl_step(0)
+    barrier()
+    c0.record()
+    for s in range(a.steps):
+        leg_step(a.warmup + a.steps + s, f_last)
+    c1.record()
+    barrier()
+    leg_ms = c0.elapsed_time(c1) / a.steps
+    # algorithmic HBM bytes per robot of the two leg kernels (all four legs, every array the call reads or writes once; of the
+    # 3x18 Jacobian only the leg's own 3x3 block is algorithmic): swing 392 in + 360 state + 192 out, torque 824 in + 48 out
+    LEG_BYTES = 944 + 872
+    robot_tick = {"value": world * B / (tick_ms * 1e-3), "unit": "robot control ticks/s (each with an MPC update)", "ms_per_step": tick_ms,
+                  "api": "BatchedGaitSchedule.set_iteration + update_robot_state + update_mpc_if_needed + "
+                         "BatchedSwingFootTrajectoryGenerator.update + BatchedLegController.update on device tensors (7 kernel launches)",
+                  "leg_layer_ms": leg_ms, "leg_layer_launches": 3,
+                  "leg_layer_hbm_gbs": B * LEG_BYTES / (leg_ms * 1e-3) / 1e9,
+                  "note": "leg layer = gait kernel + mpcq_swing_targets + mpcq_leg_torques, launch-latency bound at this batch "
+                          "(1.8 KB per robot); see tools/leg_layer_stream.py for the HBM-stream figure at 1M robots"}
+
     # ---- closed loop in the MPC's own model (warm start, mpcq_set_warm_start): from input set 0 the state advances one
     # horizon step per update under the first-step forces (x+ = x + dt w + dt^2/2 Ac w, w = Ac x + Bc u: Ac is nilpotent),
     # the contact table and the reference trajectory shift by one step; every update is solved cold and warm-started
@@ -519,6 +570,7 @@ def run_ours(a):
             "controller_api": {"value": world * B / (ctrl_ms * 1e-3), "unit": UNIT, "ms_per_step": ctrl_ms,
                                "api": "BatchedModelPredictiveController.update_robot_state + update_mpc_if_needed on device tensors "
                                       "(mpcq_gait_tables + mpcq_assemble + mpcq_solve: 4 kernel launches)"},
+            "robot_tick": robot_tick,
             "gpu_launches": launches_per_step * a.steps,
             "kernel_ms": {"per_class_mean": [float(v) for v in kmean], "dominant_class": dom,
                           "share_of_step": float(kmean[dom] / (total_ms / a.steps)),
