@@ -12,7 +12,7 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "..", "..", "pympc_quadruped_b200", "csrc")
 OUT = os.path.join(HERE, "_build", "libmpcq_emu.so")
-DEPS = [os.path.join(HERE, "mpcq_emu.cpp")] + [os.path.join(CSRC, f) for f in ("mpcq_core.cuh", "mpcq_warp.cuh", "mpcq_host.h")]
+DEPS = [os.path.join(HERE, "mpcq_emu.cpp")] + [os.path.join(CSRC, f) for f in ("mpcq_core.cuh", "mpcq_legs.cuh", "mpcq_warp.cuh", "mpcq_host.h")]
 
 
 def build() -> str:

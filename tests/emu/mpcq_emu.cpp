@@ -14,6 +14,7 @@
 #include <vector>
 
 #include "../../pympc_quadruped_b200/csrc/mpcq_host.h"
+#include "../../pympc_quadruped_b200/csrc/mpcq_legs.cuh"
 
 namespace mpcq_emu {
 // A team of NT threads (NT / 32 warps) runs as coroutines on one host thread, switched round-robin at every
@@ -177,5 +178,28 @@ int mpcq_emu_solve_f64(const mpcq_config* cs, int B, const double* x0, const dou
                        const double* xref, double* f_out, double* u_full, int32_t* iters, double* resid, int32_t* status,
                        uint8_t* active) {
     return run<double>(cs, B, x0, yaw, feet, gait, xref, f_out, u_full, iters, resid, status, active);
+}
+}
+
+// the per-leg layer (mpcq_legs.cuh): the device bodies run over all (environment, leg) pairs in index order
+extern "C" {
+void mpcq_emu_swing_targets(int B, const mpcq_leg_params* lp, const double* pos_base, const double* lin_vel_base, const double* R_base,
+                            const double* thighs, const double* pos_feet, const double* swing_state, const double* v_des,
+                            const double* yaw_rate, const double* swing_time, const double* stance_time, uint8_t* active,
+                            double* remaining, double* foot_init, double* foot_final, double* pos_t, double* vel_t) {
+    mpcq::SwingArgs a{pos_base, lin_vel_base, R_base, thighs, pos_feet, swing_state, v_des, yaw_rate, swing_time, stance_time,
+                      active, remaining, foot_init, foot_final, pos_t, vel_t,
+                      lp->swing_height, lp->dt_control, lp->gravity, lp->foot_z_final, B};
+    for (int idx = 0; idx < 4 * B; ++idx) mpcq::swing_leg(a, idx);
+}
+void mpcq_emu_leg_torques(int B, const mpcq_leg_params* lp, const double* Jv, int ncol, const double* R_base, const double* bpf,
+                          const double* bvf, const void* forces, int forces_f64, const double* swing_state, const double* pos_t,
+                          const double* vel_t, float* tau) {
+    mpcq::TorqueArgs a{Jv, R_base, bpf, bvf, swing_state, pos_t, vel_t, forces, tau, {}, {}, B, ncol};
+    for (int i = 0; i < 9; ++i) { a.kp[i] = lp->kp_swing[i]; a.kd[i] = lp->kd_swing[i]; }
+    for (int idx = 0; idx < 4 * B; ++idx) {
+        if (forces_f64) mpcq::torque_leg<double>(a, idx);
+        else mpcq::torque_leg<float>(a, idx);
+    }
 }
 }

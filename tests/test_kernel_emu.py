@@ -156,3 +156,49 @@ def test_warm_start_same_optimum_fewer_rounds(emu_lib):
         check_against_oracle(out, batch, False)                  # same optimum, same constraint activity
         # the face codes may differ only on weakly active rows (tight with a zero multiplier: in or out of the face)
         assert (out["faces"] != cold["faces"]).sum() <= 2
+
+
+def test_leg_layer_device_code_reproduces_the_reference_sequence(emu_lib):
+    """The device bodies of `mpcq_swing_targets` / `mpcq_leg_torques` (csrc/mpcq_legs.cuh, compiled for the host) over the
+    340-tick x 8-robot sequence recorded from the unmodified reference classes (tests/golden/reference_legs.npz).
+    Tolerances as in tests/test_gpu_legs.py: 1e-8 m, 1e-7 m/s, 2 float32 ulp of the largest torque term."""
+    import ctypes as C
+    import os
+    from oracle.leg_oracle import expand_jacobians
+    from pympc_quadruped_b200 import _capi
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_legs.npz"))
+    R, T = z["pos_base"].shape[:2]
+    d = {k: np.ascontiguousarray(z[k].astype(np.float64)) for k in z.files if z[k].dtype == np.float32 and k != "torque_cmds"}
+    Jv = np.ascontiguousarray(expand_jacobians(d["Jv_blocks"]))
+    P = lambda a: a.ctypes.data_as(C.c_void_p)
+    emu_lib.mpcq_emu_swing_targets.argtypes = [C.c_int, C.POINTER(_capi.MpcqLegParams)] + [C.c_void_p] * 16
+    emu_lib.mpcq_emu_leg_torques.argtypes = [C.c_int, C.POINTER(_capi.MpcqLegParams), C.c_void_p, C.c_int] + [C.c_void_p] * 4 + \
+        [C.c_int] + [C.c_void_p] * 4
+    emu_lib.mpcq_emu_swing_targets.restype = emu_lib.mpcq_emu_leg_torques.restype = None
+    kp = {0: np.diag([700.0] * 3), 1: np.diag([200.0] * 3)}                # robot 0 = A1Config, 1 = AliengoConfig
+    worst = [0.0, 0.0, 0.0]
+    for r in range(R):                                                     # one robot per "batch" (per-robot gains)
+        lp = _capi.make_leg_params(kp[int(z["robot"][r])], np.diag([20.0] * 3), 0.1, 0.001, 9.81)
+        active, rem = np.zeros((1, 4), np.uint8), np.zeros((1, 4))
+        init, fin = np.zeros((1, 4, 3)), np.zeros((1, 4, 3))
+        tsw, tst = np.array([z["swing_stance_time"][r, 0]]), np.array([z["swing_stance_time"][r, 1]])
+        vdes, yr = np.ascontiguousarray(d["v_des"][r:r + 1]), np.ascontiguousarray(d["yaw_rate"][r:r + 1])
+        for t in range(T):
+            g = lambda k: np.ascontiguousarray(d[k][r, t])
+            ss = np.ascontiguousarray(z["swing_state"][r, t])
+            pt, vt, tau = np.empty((1, 4, 3)), np.empty((1, 4, 3)), np.empty((1, 12), np.float32)
+            Rb, bpf, bvf = g("R_base"), g("base_pos_base_feet"), g("base_vel_base_feet")
+            ins = [g("pos_base"), g("lin_vel_base"), Rb, g("base_pos_base_thighs"), g("pos_feet"), ss, vdes, yr, tsw, tst]
+            emu_lib.mpcq_emu_swing_targets(1, C.byref(lp), *[P(a) for a in ins], P(active), P(rem), P(init), P(fin), P(pt), P(vt))
+            for f64 in (0, 1):
+                f = np.ascontiguousarray(d["contact_forces"][r, t].astype(np.float64 if f64 else np.float32))
+                Jt = np.ascontiguousarray(Jv[r, t])
+                emu_lib.mpcq_emu_leg_torques(1, C.byref(lp), P(Jt), 18, P(Rb), P(bpf), P(bvf), P(f), f64, P(ss), P(pt), P(vt), P(tau))
+                ref = z["torque_cmds"][r, t].astype(np.float64)
+                dt = np.abs(tau[0].astype(np.float64) - ref)
+                assert np.all(dt <= 4e-7 * (1.0 + 60.0 * np.abs(ref).max() + 1e3)), (r, t, dt.max())
+                worst[2] = max(worst[2], float((dt / (1.0 + np.abs(ref))).max()))
+            dp, dv = np.abs(pt[0] - z["pos_targets"][r, t]).max(), np.abs(vt[0] - z["vel_targets"][r, t]).max()
+            assert dp <= 1e-8 and dv <= 1e-7, (r, t, dp, dv)
+            worst[0], worst[1] = max(worst[0], dp), max(worst[1], dv)
+    assert worst[2] <= 2e-6, worst            # relative torque error: float32 rounding level
