@@ -16,6 +16,8 @@
  *     synchronise or throw: 0 = success, negative = error (text via mpcq_last_error);
  *   - the factor workspace is allocated by mpcq_create; a launch-order buffer (5 bytes per environment) and the pinned /
  *     device staging of the `*_host` calls grow to the largest batch seen (a growing call synchronises the device);
+ *   - mpcq_solve may run its size-class kernels side by side on private streams of the handle; they are forked from and joined
+ *     back to `stream` with events, so to the caller the call is still one ordered operation on `stream` (graph-capturable);
  *   - one call in flight per handle: do not overlap two mpcq_solve calls of one handle on different streams;
  *   - a handle is bound to one device and is not thread-safe;
  *   - there is no CPU fallback: without a CUDA device mpcq_create fails.

@@ -83,6 +83,69 @@ mpcq_schedule_kernel(const __grid_constant__ Consts cs, const __grid_constant__ 
     for (int b = tid; b < io.B; b += blockDim.x) perm[atomicAdd(&start[bucket[b]], 1)] = b;
 }
 
+// The same schedule as two small multi-CTA launches (used by the device entry point): with one CTA the 4 096-robot pre-pass
+// is a chain of four dependent DRAM round trips per thread plus two passes over the bucket array (16 us on the critical
+// path of a 0.68 ms step); here every robot has its own thread in the scoring pass, each CTA keeps its own histogram, and the
+// scatter pass derives each CTA's offsets from the per-CTA histograms - no atomics on global memory, no grid barrier.
+constexpr int kSchedThreads = 256, kSchedMaxCtas = 64;
+
+template <class T>
+MPCQ_DEV int schedule_bucket(const Consts& cs, const IO<T>& io, int b) {
+    const T* x0 = io.x0 + (size_t)b * 13;
+    const T* xr = io.x_ref + (size_t)b * 13 * cs.horizon;
+    float s = 0.f;
+    for (int c = 0; c < 12; ++c) {
+        if (c == 2) continue;
+        const float e = (float)x0[c] - (float)xr[c];
+        s += (float)cs.q[c] * e * e;
+    }
+    s = sqrtf(s);
+    const int k = (int)(64.f * s / (1.f + s));
+    return !(s == s) ? 63 : (k > 63 ? 63 : (k < 0 ? 0 : k));
+}
+
+template <class T>
+__global__ void __launch_bounds__(kSchedThreads)
+mpcq_score_kernel(const __grid_constant__ Consts cs, const __grid_constant__ IO<T> io, uint8_t* bucket, int* cta_hist) {
+    __shared__ int hist[64];
+    const int tid = threadIdx.x;
+    if (tid < 64) hist[tid] = 0;
+    __syncthreads();
+    for (int b = blockIdx.x * kSchedThreads + tid; b < io.B; b += gridDim.x * kSchedThreads) {
+        const int k = schedule_bucket<T>(cs, io, b);
+        bucket[b] = (uint8_t)k;
+        atomicAdd(&hist[k], 1);
+    }
+    __syncthreads();
+    if (tid < 64) cta_hist[blockIdx.x * 64 + tid] = hist[tid];
+}
+
+__global__ void __launch_bounds__(kSchedThreads)
+mpcq_scatter_kernel(int B, const uint8_t* bucket, const int* cta_hist, int32_t* perm) {
+    __shared__ int total[64];
+    __shared__ int start[64];
+    const int tid = threadIdx.x;
+    int before = 0;
+    if (tid < 64) {
+        int tot = 0;
+        for (int c = 0; c < (int)gridDim.x; ++c) {
+            const int v = cta_hist[c * 64 + tid];
+            before += c < (int)blockIdx.x ? v : 0;
+            tot += v;
+        }
+        total[tid] = tot;
+    }
+    __syncthreads();
+    if (tid < 64) {
+        int higher = 0;
+        for (int k = tid + 1; k < 64; ++k) higher += total[k];            // highest score first
+        start[tid] = higher + before;
+    }
+    __syncthreads();
+    for (int b = blockIdx.x * kSchedThreads + tid; b < B; b += gridDim.x * kSchedThreads)
+        perm[atomicAdd(&start[bucket[b]], 1)] = b;
+}
+
 // stage kernel for parity tests: dense (H, g, ub) exactly as the reference hands them to its solver
 template <class T>
 __global__ void __launch_bounds__(32)
@@ -302,9 +365,13 @@ struct mpcq_handle {
     uint8_t* bucket[2] = {nullptr, nullptr};
     size_t perm_cap[2] = {0, 0};
     bool schedule = true;
+    int* cta_hist = nullptr;              // per-CTA histograms of the two-launch schedule (mpcq_solve only)
     // warm start of the next mpcq_solve calls (mpcq_set_warm_start)
     const uint8_t* face_in = nullptr;
     uint8_t* face_out = nullptr;
+    // mpcq_solve runs its size classes side by side: classes 1.. are forked onto these streams and joined back (launch_all)
+    cudaStream_t aux[3] = {nullptr, nullptr, nullptr};
+    cudaEvent_t fork_ev = nullptr, join_ev[3] = {nullptr, nullptr, nullptr};
 };
 
 namespace {
@@ -354,24 +421,53 @@ cudaError_t launch_class_lg(mpcq_handle* h, const IO<T>& io, int ci, cudaStream_
 }
 
 template <class T>
-cudaError_t launch_all(mpcq_handle* h, IO<T> io, int32_t* perm, uint8_t* bucket, cudaStream_t st) {
+cudaError_t launch_one(mpcq_handle* h, const IO<T>& io, int ci, cudaStream_t st) {
+    switch (ci) {
+        case 0: return launch_class_lg<T, 64>(h, io, ci, st);
+        case 1: return launch_class_lg<T, 128>(h, io, ci, st);
+        case 2: return launch_class_lg<T, 192>(h, io, ci, st);
+        default: return launch_class_lg<T, 384>(h, io, ci, st);
+    }
+}
+
+template <typename T>
+cudaError_t launch_all(mpcq_handle* h, IO<T> io, int32_t* perm, uint8_t* bucket, cudaStream_t st, bool overlap) {
     cudaError_t e = cudaSuccess;
     h->last_launches = 0;
     h->ev_launches = 0;
     if (perm && io.B >= 512) {                                 // below ~one wave the order cannot matter
-        mpcq_schedule_kernel<T><<<1, 1024, 0, st>>>(h->cs, io, perm, bucket);
+        if (overlap && h->cta_hist) {
+            int g = (io.B + kSchedThreads - 1) / kSchedThreads;
+            g = g > kSchedMaxCtas ? kSchedMaxCtas : g;
+            mpcq_score_kernel<T><<<g, kSchedThreads, 0, st>>>(h->cs, io, bucket, h->cta_hist);
+            mpcq_scatter_kernel<<<g, kSchedThreads, 0, st>>>(io.B, bucket, h->cta_hist, perm);
+            h->last_launches += 2;
+        } else {
+            mpcq_schedule_kernel<T><<<1, 1024, 0, st>>>(h->cs, io, perm, bucket);
+            ++h->last_launches;
+        }
         e = cudaGetLastError();
         io.perm = perm;
-        ++h->last_launches;
+    }
+    if (overlap && !h->profiling && h->ncls > 1 && h->fork_ev && e == cudaSuccess) {
+        // every environment belongs to exactly one class and the launches share nothing but read-only inputs, so the classes
+        // run side by side: the larger ones (more work per environment) start first on their own streams, class 0 follows
+        // on the caller's stream, which then waits for the others.  A class that is empty for this batch (trot at H = 10:
+        // everything is in class 0) costs nothing on the critical path instead of a grid of CTAs that exit at once.
+        cudaEventRecord(h->fork_ev, st);
+        for (int ci = h->ncls - 1; ci >= 1 && e == cudaSuccess; --ci) {
+            cudaStreamWaitEvent(h->aux[ci - 1], h->fork_ev, 0);
+            e = launch_one<T>(h, io, ci, h->aux[ci - 1]);
+            cudaEventRecord(h->join_ev[ci - 1], h->aux[ci - 1]);
+            ++h->last_launches;
+        }
+        if (e == cudaSuccess) { e = launch_one<T>(h, io, 0, st); ++h->last_launches; }
+        for (int ci = 1; ci < h->ncls; ++ci) cudaStreamWaitEvent(st, h->join_ev[ci - 1], 0);
+        return e;
     }
     for (int ci = 0; ci < h->ncls && e == cudaSuccess; ++ci) {
         if (h->profiling) cudaEventRecord(h->ev[2 * ci], st);
-        switch (ci) {
-            case 0: e = launch_class_lg<T, 64>(h, io, ci, st); break;
-            case 1: e = launch_class_lg<T, 128>(h, io, ci, st); break;
-            case 2: e = launch_class_lg<T, 192>(h, io, ci, st); break;
-            default: e = launch_class_lg<T, 384>(h, io, ci, st); break;
-        }
+        e = launch_one<T>(h, io, ci, st);
         if (h->profiling) { cudaEventRecord(h->ev[2 * ci + 1], st); ++h->ev_launches; }
         ++h->last_launches;
     }
@@ -489,6 +585,12 @@ int mpcq_create(const mpcq_config* cfg, mpcq_handle** out) {
             delete h;
             return MPCQ_ERR_CUDA;
         }
+    // side streams of mpcq_solve's class overlap; without them (creation failed) the classes simply run in sequence
+    bool side = cudaEventCreateWithFlags(&h->fork_ev, cudaEventDisableTiming) == cudaSuccess;
+    for (int i = 0; i < 3 && side; ++i)
+        side = cudaStreamCreateWithFlags(&h->aux[i], cudaStreamNonBlocking) == cudaSuccess &&
+               cudaEventCreateWithFlags(&h->join_ev[i], cudaEventDisableTiming) == cudaSuccess;
+    if (!side) { cudaGetLastError(); if (h->fork_ev) cudaEventDestroy(h->fork_ev); h->fork_ev = nullptr; }
     *out = h;
     return MPCQ_OK;
 }
@@ -496,6 +598,11 @@ int mpcq_create(const mpcq_config* cfg, mpcq_handle** out) {
 void mpcq_destroy(mpcq_handle* h) {
     if (!h) return;
     DeviceGuard guard(h->cfg.device);
+    for (int i = 0; i < 3; ++i) {
+        if (h->aux[i]) { cudaStreamSynchronize(h->aux[i]); cudaStreamDestroy(h->aux[i]); }
+        if (h->join_ev[i]) cudaEventDestroy(h->join_ev[i]);
+    }
+    if (h->fork_ev) cudaEventDestroy(h->fork_ev);
     for (int i = 0; i < kHostStreams; ++i)
         if (h->streams[i]) { cudaStreamSynchronize(h->streams[i]); cudaStreamDestroy(h->streams[i]); }
     for (int i = 0; i < 8; ++i)
@@ -505,6 +612,7 @@ void mpcq_destroy(mpcq_handle* h) {
         if (h->perm[i]) cudaFree(h->perm[i]);
         if (h->bucket[i]) cudaFree(h->bucket[i]);
     }
+    if (h->cta_hist) cudaFree(h->cta_hist);
     if (h->dev) cudaFree(h->dev);
     if (h->pin) cudaFreeHost(h->pin);
     delete h;
@@ -520,6 +628,8 @@ static int ensure_perm(mpcq_handle* h, int slot, size_t envs) {
     const size_t cap = envs < 4096 ? 4096 : envs;
     if (!cuda_ok(h, cudaMalloc(&h->perm[slot], cap * sizeof(int32_t)), "cudaMalloc schedule")) return MPCQ_ERR_CUDA;
     if (!cuda_ok(h, cudaMalloc(&h->bucket[slot], cap), "cudaMalloc schedule")) return MPCQ_ERR_CUDA;
+    if (slot == 0 && !h->cta_hist &&
+        !cuda_ok(h, cudaMalloc(&h->cta_hist, (size_t)kSchedMaxCtas * 64 * sizeof(int)), "cudaMalloc schedule")) return MPCQ_ERR_CUDA;
     h->perm_cap[slot] = cap;
     return MPCQ_OK;
 }
@@ -535,11 +645,11 @@ static int solve_impl(mpcq_handle* h, int32_t B, const void* x0, const void* yaw
     if (h->cfg.dtype == MPCQ_F64) {
         IO<double> io = make_io<double>(B, x0, yaw, r_feet, gait, x_ref, f_out, u_full, iters, resid, status, active);
         if (warm) { io.face_in = h->face_in; io.face_out = h->face_out; }
-        e = launch_all<double>(h, io, perm, bucket, st);
+        e = launch_all<double>(h, io, perm, bucket, st, warm);
     } else {
         IO<float> io = make_io<float>(B, x0, yaw, r_feet, gait, x_ref, f_out, u_full, iters, resid, status, active);
         if (warm) { io.face_in = h->face_in; io.face_out = h->face_out; }
-        e = launch_all<float>(h, io, perm, bucket, st);
+        e = launch_all<float>(h, io, perm, bucket, st, warm);
     }
     return cuda_ok(h, e, "mpcq_solve launch") ? MPCQ_OK : MPCQ_ERR_CUDA;
 }
