@@ -11,6 +11,7 @@
 
 #include <new>
 #include <string>
+#include <unordered_map>
 
 #include "mpcq_host.h"
 #include "mpcq_legs.cuh"
@@ -356,6 +357,7 @@ struct mpcq_handle {
     char* dev = nullptr;
     size_t stage_cap = 0;
     cudaStream_t streams[4] = {nullptr, nullptr, nullptr, nullptr};
+    std::unordered_map<const void*, bool> pinned_cache;   // caller buffer -> page-locked?
     // measurement hooks
     bool profiling = false;
     cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -365,7 +367,7 @@ struct mpcq_handle {
     uint8_t* bucket[2] = {nullptr, nullptr};
     size_t perm_cap[2] = {0, 0};
     bool schedule = true;
-    int* cta_hist = nullptr;              // per-CTA histograms of the two-launch schedule (mpcq_solve only)
+    int* cta_hist = nullptr;              // per-CTA histograms of the two-launch schedule: [1 + kHostStreams][kSchedMaxCtas][64]
     // warm start of the next mpcq_solve calls (mpcq_set_warm_start)
     const uint8_t* face_in = nullptr;
     uint8_t* face_out = nullptr;
@@ -431,16 +433,17 @@ cudaError_t launch_one(mpcq_handle* h, const IO<T>& io, int ci, cudaStream_t st)
 }
 
 template <typename T>
-cudaError_t launch_all(mpcq_handle* h, IO<T> io, int32_t* perm, uint8_t* bucket, cudaStream_t st, bool overlap) {
+cudaError_t launch_all(mpcq_handle* h, IO<T> io, int32_t* perm, uint8_t* bucket, cudaStream_t st, int* cta_hist) {
+    const bool overlap = cta_hist != nullptr;
     cudaError_t e = cudaSuccess;
     h->last_launches = 0;
     h->ev_launches = 0;
     if (perm && io.B >= 512) {                                 // below ~one wave the order cannot matter
-        if (overlap && h->cta_hist) {
+        if (overlap) {
             int g = (io.B + kSchedThreads - 1) / kSchedThreads;
             g = g > kSchedMaxCtas ? kSchedMaxCtas : g;
-            mpcq_score_kernel<T><<<g, kSchedThreads, 0, st>>>(h->cs, io, bucket, h->cta_hist);
-            mpcq_scatter_kernel<<<g, kSchedThreads, 0, st>>>(io.B, bucket, h->cta_hist, perm);
+            mpcq_score_kernel<T><<<g, kSchedThreads, 0, st>>>(h->cs, io, bucket, cta_hist);
+            mpcq_scatter_kernel<<<g, kSchedThreads, 0, st>>>(io.B, bucket, cta_hist, perm);
             h->last_launches += 2;
         } else {
             mpcq_schedule_kernel<T><<<1, 1024, 0, st>>>(h->cs, io, perm, bucket);
@@ -628,8 +631,8 @@ static int ensure_perm(mpcq_handle* h, int slot, size_t envs) {
     const size_t cap = envs < 4096 ? 4096 : envs;
     if (!cuda_ok(h, cudaMalloc(&h->perm[slot], cap * sizeof(int32_t)), "cudaMalloc schedule")) return MPCQ_ERR_CUDA;
     if (!cuda_ok(h, cudaMalloc(&h->bucket[slot], cap), "cudaMalloc schedule")) return MPCQ_ERR_CUDA;
-    if (slot == 0 && !h->cta_hist &&
-        !cuda_ok(h, cudaMalloc(&h->cta_hist, (size_t)kSchedMaxCtas * 64 * sizeof(int)), "cudaMalloc schedule")) return MPCQ_ERR_CUDA;
+    if (!h->cta_hist &&
+        !cuda_ok(h, cudaMalloc(&h->cta_hist, (size_t)(1 + kHostStreams) * kSchedMaxCtas * 64 * sizeof(int)), "cudaMalloc schedule")) return MPCQ_ERR_CUDA;
     h->perm_cap[slot] = cap;
     return MPCQ_OK;
 }
@@ -637,19 +640,21 @@ static int ensure_perm(mpcq_handle* h, int slot, size_t envs) {
 // solve envs [0,B) of the given arrays; `slot`/`off` select the region of the launch-order buffers this call may use
 static int solve_impl(mpcq_handle* h, int32_t B, const void* x0, const void* yaw, const void* r_feet, const float* gait,
                       const void* x_ref, void* f_out, void* u_full, int32_t* iters, double* resid, int32_t* status,
-                      uint8_t* active, int slot, size_t off, cudaStream_t st) {
+                      uint8_t* active, int slot, size_t off, cudaStream_t st, int chunk = 0) {
     int32_t* perm = (h->schedule && h->perm[slot]) ? h->perm[slot] + off : nullptr;
     uint8_t* bucket = (h->schedule && h->bucket[slot]) ? h->bucket[slot] + off : nullptr;
     cudaError_t e;
     const bool warm = slot == 0;                               // the device entry point honours mpcq_set_warm_start
+    // per-CTA histograms of the two-launch schedule: region 0 for mpcq_solve, 1 + chunk for the chunks of mpcq_solve_host
+    int* hist = h->cta_hist ? h->cta_hist + (size_t)(slot == 0 ? 0 : 1 + chunk) * kSchedMaxCtas * 64 : nullptr;
     if (h->cfg.dtype == MPCQ_F64) {
         IO<double> io = make_io<double>(B, x0, yaw, r_feet, gait, x_ref, f_out, u_full, iters, resid, status, active);
         if (warm) { io.face_in = h->face_in; io.face_out = h->face_out; }
-        e = launch_all<double>(h, io, perm, bucket, st, warm);
+        e = launch_all<double>(h, io, perm, bucket, st, hist);
     } else {
         IO<float> io = make_io<float>(B, x0, yaw, r_feet, gait, x_ref, f_out, u_full, iters, resid, status, active);
         if (warm) { io.face_in = h->face_in; io.face_out = h->face_out; }
-        e = launch_all<float>(h, io, perm, bucket, st, warm);
+        e = launch_all<float>(h, io, perm, bucket, st, hist);
     }
     return cuda_ok(h, e, "mpcq_solve launch") ? MPCQ_OK : MPCQ_ERR_CUDA;
 }
@@ -816,9 +821,15 @@ int mpcq_solve_host(mpcq_handle* h, int32_t B, const void* x0, const void* yaw, 
         const void* p = i < 5 ? src[i] : dst[i - 5];
         pinned[i] = false;
         if (p && width[i]) {
+            // the driver query costs 1-2 us per pointer; remember the answer per address.  A stale answer is harmless: a
+            // pageable buffer taken for page-locked is still copied correctly by cudaMemcpyAsync (synchronously), a page-locked
+            // one taken for pageable merely goes through the staging copy.
+            auto it = h->pinned_cache.find(p);
+            if (it != h->pinned_cache.end()) { pinned[i] = it->second; continue; }
             cudaPointerAttributes at;
             if (cudaPointerGetAttributes(&at, p) == cudaSuccess) pinned[i] = at.type == cudaMemoryTypeHost;
             else cudaGetLastError();
+            if (h->pinned_cache.size() < 4096) h->pinned_cache.emplace(p, pinned[i]);
         }
     }
     // the batch is cut into chunks, each on its own stream: H2D(c+1) overlaps solve(c) overlaps D2H(c-1), and the
@@ -826,8 +837,10 @@ int mpcq_solve_host(mpcq_handle* h, int32_t B, const void* x0, const void* yaw, 
     // workspace cannot run twice concurrently, so such handles use one chunk.
     bool any_global = false;
     for (int ci = 0; ci < h->ncls; ++ci) any_global = any_global || h->lglobal[ci];
-    // measured at B = 4096: 1 / 2 / 3 / 4 chunks = 1.144 / 1.130 / 1.148 / 1.157 ms (smaller chunks hide more of the copies but
-    // give the expected-work-first schedule less to work with); large batches take all four streams
+    // measured at B = 4096 (v13): 1 / 2 / 3 / 4 chunks = 0.80-0.82 / 0.81 / 0.81-0.84 / 0.83 ms (smaller chunks hide more of the copies
+    // but give the expected-work-first schedule less to work with); large batches take all four streams.  Reading page-locked
+    // inputs in place (zero copy, one chunk) was tried and is slower (0.85 ms): the kernels read their inputs twice and the
+    // first wave of CTAs queues 2.8 MB of PCIe reads in front of the hardest environments.
     int nchunk = any_global ? 1 : (B >= 16384 ? kHostStreams : (B >= 1024 ? 2 : 1));
     if (const char* ov = getenv("MPCQ_HOST_CHUNKS")) {          // experiments only
         const int v = atoi(ov);
@@ -855,7 +868,7 @@ int mpcq_solve_host(mpcq_handle* h, int32_t B, const void* x0, const void* yaw, 
         auto dp = [&](int i) -> char* { return width[i] ? d + off[i] + lo * width[i] : nullptr; };
         const int rc = solve_impl(h, (int32_t)nb, dp(0), dp(1), dp(2), reinterpret_cast<float*>(dp(3)), dp(4), dp(5), dp(6),
                                   reinterpret_cast<int32_t*>(dp(7)), reinterpret_cast<double*>(dp(8)),
-                                  reinterpret_cast<int32_t*>(dp(9)), reinterpret_cast<uint8_t*>(dp(10)), 1, lo, st);
+                                  reinterpret_cast<int32_t*>(dp(9)), reinterpret_cast<uint8_t*>(dp(10)), 1, lo, st, c % kHostStreams);
         if (rc != MPCQ_OK) return rc;
         launches += h->last_launches;
         for (int i = 5; i < 11; ++i) {

@@ -189,7 +189,7 @@ def test_host_entry_point_chunked_pinned_and_pageable():
         assert np.array_equal(r["u"], res.u.cpu().numpy())
         assert np.array_equal(r["status"], res.status.cpu().numpy())
     assert np.array_equal(host["iters"], res.iters.cpu().numpy())
-    assert eng.last_launch_count == 3 * 2                       # (schedule + 2 size classes) x 2 chunks
+    assert eng.last_launch_count == 4 * 2                       # (2 schedule launches + 2 size classes) x 2 chunks
 
 
 def test_edge_cases_empty_batch_all_swing_and_errors():
