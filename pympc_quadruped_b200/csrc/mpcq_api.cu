@@ -509,6 +509,13 @@ cudaError_t configure(mpcq_handle* h) {
             need = (need + 31) / 32 * 32;
             if (need > gws_elems) gws_elems = need;
         }
+        if (const char* ov = getenv("MPCQ_CTAS_PER_SM")) {       // experiments only: fewer resident teams per SM (class 0)
+            const int k = atoi(ov);
+            if (ci == 0 && k >= 1 && k <= 12 && !h->lglobal[ci]) {
+                const size_t want = ((size_t)233472 / k - 1024) / 128 * 128;
+                if (want > s && want <= kMaxSmem) s = want;
+            }
+        }
         h->smem[ci] = s;
     }
     cudaError_t e = cudaSuccess;

@@ -61,7 +61,10 @@ MPCQ_UNROLL
     a.active[idx] = ss >= 1.0 ? 0 : 1;                             // :125-126 swing finished -> next swing starts afresh
     a.remaining[idx] = rem;
 MPCQ_UNROLL
-    for (int i = 0; i < 3; ++i) { a.foot_init[o + i] = ini[i]; a.foot_final[o + i] = fin[i]; }
+    for (int i = 0; i < 3; ++i) {
+        if (!started) a.foot_init[o + i] = ini[i];                 // unchanged during a swing: not written back (96 B per robot)
+        a.foot_final[o + i] = fin[i];
+    }
     // three-point zero-velocity cubic Hermite (:38-63; Drake PiecewisePolynomial.CubicHermite, float32 break points)
     const double t1 = (double)(float)(Tsw / 2.0), t2 = (double)(float)Tsw;
     double t = Tsw - rem;

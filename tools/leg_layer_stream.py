@@ -1,9 +1,11 @@
 """HBM-stream rate of the two leg-layer kernels at a batch large enough to leave launch latency behind:
 `mpcq_swing_targets` and `mpcq_leg_torques` over B robots (default 2^20), CUDA events, 20 launches after 3 warm-ups, inputs far
-larger than L2.  Algorithmic bytes per robot (every array read or written once; of the 3x18 Jacobian only the leg's own 3x3
-block counts; DRAM sectors actually touched in the 18-column layout are reported beside it):
-  swing  : 392 B in + 360 B state in/out + 192 B out = 944 B   (all four legs swinging; stance legs write 48 B only)
-  torque : 4 x 72 B Jacobian blocks + 72 R + 96 + 96 + 48 forces + 32 + 96 + 96 in + 48 out = 872 B   (1 632 B of sectors, ncol = 18)
+larger than L2.  Algorithmic bytes per robot (every array read or written once, steady state = mid-swing; checked against the
+ncu capture profiles/r01_ncu_legs_v14.txt: 799 B per robot measured when the kernel still re-wrote footpos_init, 96 B more than this):
+  swing  : 168 B per robot (pos, vel, R, commands, times; once if any leg swings) + per swinging leg 146 B (thigh 24, phase 8,
+           state in/out 42, final 24, targets 48) + per stance leg 56 B (phase 8, zero targets 48) = 752 B with all four legs swinging
+  torque : 4 x 72 B Jacobian blocks + 72 R + 96 + 96 + 48 forces + 32 + 96 + 96 in + 48 out = 872 B (ncol = 3); in the reference's
+           18-column layout the DRAM reads nearly the whole 1 728 B Jacobian (ncu: 2.19 GB per 2^20 robots = 6.9 TB/s, the HBM peak)
 Usage: python tools/leg_layer_stream.py [B]"""
 import json, os, sys
 sys.path.insert(0, os.path.join(os.path.dirname(__file__), ".."))
@@ -44,7 +46,7 @@ for label, frac_swing in (("all legs swinging", 1.0), ("trot (half the legs swin
             torch.cuda.synchronize()
             if it >= 3:
                 ms_s += e[0].elapsed_time(e[1]) / 20; ms_t += e[1].elapsed_time(e[2]) / 20
-        sw_bytes = B * (4 * (8 + 48) + frac_swing * (944 - 4 * 8 - 192) + (1 - frac_swing) * 0)
+        sw_bytes = B * (168 * (1 - (1 - frac_swing) ** 4) + 4 * (frac_swing * 146 + (1 - frac_swing) * 56))
         tq_alg = B * (4 * 8 + 48 + 4 * (72 + frac_swing * (72 / 4 + 24 * 4) + (1 - frac_swing) * 12))
         out[f"{label}, ncol={ncol}"] = {
             "swing_ms": ms_s, "swing_gbs": sw_bytes / ms_s / 1e6, "swing_frac_hbm": sw_bytes / ms_s / 1e6 / peak,
