@@ -271,8 +271,13 @@ struct AssembleArgs {
 template <class T>
 __global__ void __launch_bounds__(128)
 mpcq_assemble_kernel(const __grid_constant__ AssembleArgs a, T* x0, T* yaw_out, T* x_ref) {
-    const int b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= a.B) return;
+    // x_ref rows are staged per horizon step in shared memory and written by the whole block in runs of 13 consecutive values
+    // per robot (one thread per robot writing its own 13H values touches 32 cache lines per store instruction)
+    __shared__ T stage[128 * 13];
+    const int b0 = blockIdx.x * blockDim.x;
+    const bool valid = b0 + (int)threadIdx.x < a.B;
+    const int b = valid ? b0 + (int)threadIdx.x : a.B - 1;         // idle threads shadow the last robot, their stores are masked
+    const int nvalid = a.B - b0 < (int)blockDim.x ? a.B - b0 : (int)blockDim.x;
     const double qw = a.quat[4 * b], qx = a.quat[4 * b + 1], qy = a.quat[4 * b + 2], qz = a.quat[4 * b + 3];
     // quat2ZYXangle (utils/kinematics.py:40-49), float64
     const double roll = atan2(2 * (qw * qx + qy * qz), 1 - 2 * (qx * qx + qy * qy));
@@ -287,8 +292,11 @@ mpcq_assemble_kernel(const __grid_constant__ AssembleArgs a, T* x0, T* yaw_out, 
         st[9 + i] = (float)a.vel[3 * b + i];
     }
     st[12] = (float)(-a.gravity);
-    for (int i = 0; i < 13; ++i) x0[(size_t)b * 13 + i] = (T)st[i];
-    yaw_out[b] = (T)yaw;
+    for (int i = 0; i < 13; ++i) stage[threadIdx.x * 13 + i] = (T)st[i];
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < nvalid * 13; idx += blockDim.x) x0[(size_t)b0 * 13 + idx] = stage[idx];   // contiguous
+    __syncthreads();
+    if (valid) yaw_out[b] = (T)yaw;
     // vel_base_des = R_base @ base_vel_base_des (mpc.py:83)
     double R[9];
     if (a.R) {
@@ -320,23 +328,28 @@ mpcq_assemble_kernel(const __grid_constant__ AssembleArgs a, T* x0, T* yaw_out, 
         if (fabs((double)st[10]) > 0.1) roll_init += a.dt * (0.0 - (double)st[0]) / (double)st[10];
         roll_init = fmin(fmax(roll_init, -0.25), 0.25);
         pitch_init = fmin(fmax(pitch_init, -0.25), 0.25);
-        a.rp_init[2 * b] = roll_init; a.rp_init[2 * b + 1] = pitch_init;
+        if (valid) { a.rp_init[2 * b] = roll_init; a.rp_init[2 * b + 1] = pitch_init; }
         const float rc = (float)((double)st[10] * roll_init), pc = (float)((double)st[9] * pitch_init);
         float ry = (float)yawd, rx = (float)xd, rY = (float)yd;
-        T* X = x_ref + (size_t)b * 13 * a.H;
         for (int i = 0; i < a.H; ++i) {
             if (i > 0) {                                        // float32 storage, float64 increments (mpc.py:163-166)
                 ry = (float)((double)ry + a.dt * rate);
                 rx = (float)((double)rx + a.dt * vx);
                 rY = (float)((double)rY + a.dt * vy);
             }
-            T* r = X + 13 * i;
+            T* r = stage + threadIdx.x * 13;
             r[0] = (T)rc; r[1] = (T)pc; r[2] = (T)ry; r[3] = (T)rx; r[4] = (T)rY; r[5] = (T)(float)a.com_height;
             r[6] = (T)0; r[7] = (T)0; r[8] = (T)(float)rate; r[9] = (T)(float)vx; r[10] = (T)(float)vy; r[11] = (T)0;
             r[12] = (T)(float)(-a.gravity);
+            __syncthreads();
+            for (int idx = threadIdx.x; idx < nvalid * 13; idx += blockDim.x) {
+                const int rb = idx / 13, c = idx - 13 * rb;
+                x_ref[((size_t)(b0 + rb) * a.H + i) * 13 + c] = stage[idx];
+            }
+            __syncthreads();
         }
     }
-    a.xy_des[2 * b] = xd; a.xy_des[2 * b + 1] = yd; a.yaw_des[b] = yawd;
+    if (valid) { a.xy_des[2 * b] = xd; a.xy_des[2 * b + 1] = yd; a.yaw_des[b] = yawd; }
 }
 
 }  // namespace
