@@ -574,7 +574,7 @@ def run_ours(a):
             "gpu_launches": launches_per_step * a.steps,
             "kernel_ms": {"per_class_mean": [float(v) for v in kmean], "dominant_class": dom,
                           "share_of_step": float(kmean[dom] / (total_ms / a.steps)),
-                          "note": "solve kernels by size class; the schedule pre-pass (one small launch) is not in this list"},
+                          "note": "solve kernels by size class; the schedule pre-pass (two small launches: score + scatter) is not in this list; the classes run side by side"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                          "traffic": traffic, "traffic_source": traffic_src, "algorithmic_bytes_per_launch": ALGO_BYTES(H) * (rs // 4) * B,
                          "peak_source": peak_src,
