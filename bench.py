@@ -431,7 +431,7 @@ def run_ours(a):
     LEG_BYTES = 944 + 872
     robot_tick = {"value": world * B / (tick_ms * 1e-3), "unit": "robot control ticks/s (each with an MPC update)", "ms_per_step": tick_ms,
                   "api": "BatchedGaitSchedule.set_iteration + update_robot_state + update_mpc_if_needed + "
-                         "BatchedSwingFootTrajectoryGenerator.update + BatchedLegController.update on device tensors (7 kernel launches)",
+                         "BatchedSwingFootTrajectoryGenerator.update + BatchedLegController.update on device tensors (9 kernel launches)",
                   "leg_layer_ms": leg_ms, "leg_layer_launches": 3,
                   "leg_layer_hbm_gbs": B * LEG_BYTES / (leg_ms * 1e-3) / 1e9,
                   "note": "leg layer = gait kernel + mpcq_swing_targets + mpcq_leg_torques, launch-latency bound at this batch "
@@ -569,7 +569,7 @@ def run_ours(a):
                     "ms_per_step": 1e3 * float(te.item()) / a.steps, "launches_per_step": e2e_launches},
             "controller_api": {"value": world * B / (ctrl_ms * 1e-3), "unit": UNIT, "ms_per_step": ctrl_ms,
                                "api": "BatchedModelPredictiveController.update_robot_state + update_mpc_if_needed on device tensors "
-                                      "(mpcq_gait_tables + mpcq_assemble + mpcq_solve: 4 kernel launches)"},
+                                      "(mpcq_gait_tables + mpcq_assemble + mpcq_solve: 6 kernel launches, the two size classes side by side)"},
             "robot_tick": robot_tick,
             "gpu_launches": launches_per_step * a.steps,
             "kernel_ms": {"per_class_mean": [float(v) for v in kmean], "dominant_class": dom,
