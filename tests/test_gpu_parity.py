@@ -548,3 +548,42 @@ def test_warm_start_on_a_model_consistent_rollout():
         xref[:, -1, 2:5] += xref[:, -1, 2:5] - xref[:, -3, 2:5] if H > 2 else 0.0
     print(f"model-consistent rollout: factorisations per update cold {np.mean(nf_cold[1:]):.2f}, warm {np.mean(nf_warm[1:]):.2f}")
     assert np.mean(nf_warm[1:]) < 0.75 * np.mean(nf_cold[1:]), (nf_cold, nf_warm)
+
+
+def test_solve_is_graph_capturable():
+    """include/mpcq.h promises that mpcq_solve stays ONE ordered, capturable operation on the caller's stream although it forks
+    its size classes onto private streams: capture it in a CUDA graph, replay on new inputs, compare bit for bit with eager calls."""
+    B = 1024
+    sets = [make_batch(A1Config, 10, B, "mixed", (Gait.TROTTING10, Gait.STANDING), 41 + i, solve=False) for i in range(2)]
+    eng = _engine(sets[0], A1Config, torch.float32)
+    dev = [_to_dev(b, torch.float32) for b in sets]
+    eager = []
+    for x0, feet, gait, xref, yaw in dev:
+        r = eng.solve(x0, feet, gait, xref, yaw=yaw, want=("u", "status"))
+        eager.append((r.forces.clone(), r.u.clone(), r.status.clone()))
+    static = [t.clone() for t in dev[0]]
+    out = eng.solve(*static[:4], yaw=static[4], want=("u", "status"))          # warm-up: buffers of the handle are allocated
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        eng.solve(*static[:4], yaw=static[4], want=("u", "status"), out=out)
+    for k in (1, 0, 1):
+        for dst, src in zip(static, dev[k]):
+            dst.copy_(src)
+        out.forces.zero_(); out.u.zero_(); out.status.zero_()
+        g.replay()
+        torch.cuda.synchronize()
+        assert torch.equal(out.forces, eager[k][0]) and torch.equal(out.u, eager[k][1]) and torch.equal(out.status, eager[k][2]), k
+    # replay timing next to eager launches (information only)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    res = {}
+    for name, fn in (("eager", lambda: eng.solve(*static[:4], yaw=static[4], want=("u", "status"), out=out)), ("graph", g.replay)):
+        for _ in range(5):
+            fn()
+        e0.record()
+        for _ in range(50):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        res[name] = e0.elapsed_time(e1) / 50
+    print("mpcq_solve, 1024 robots, ms per call:", res)
