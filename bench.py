@@ -592,7 +592,7 @@ def run_ours(a):
                        "precision": "Cholesky/triangular solves in " + a.dtype + ", residuals + KKT tests in f64"},
             "latency_ms": {"p50": lat[len(lat) // 2], "p90": lat[int(len(lat) * 0.9)], "max": lat[-1]},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "api": "mpcq_solve_host (C ABI, pinned host buffers in and out, chunks pipelined on separate streams)",
+                    "api": "mpcq_solve_host (C ABI, pinned host buffers in and out: DMA of the inputs, results written in place by the kernels; batches of 8192+ robots are cut into chunks pipelined on separate streams)",
                     "ms_per_step": 1e3 * float(te.item()) / a.steps, "launches_per_step": e2e_launches},
             "controller_api": {"value": world * B / (ctrl_ms * 1e-3), "unit": UNIT, "ms_per_step": ctrl_ms,
                                "api": "BatchedModelPredictiveController.update_robot_state + update_mpc_if_needed on device tensors "

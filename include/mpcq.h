@@ -215,7 +215,8 @@ int mpcq_leg_torques(mpcq_handle* h, int32_t B, const mpcq_leg_params* lp, const
 /*
  * Same call with HOST buffers (what a CPU-side simulator loop such as scripts/isaacgym_a1.py:119-164
  * would hand over): inputs are staged through pinned memory, copied to the device, solved and the
- * requested outputs copied back; returns after the results are in the caller's buffers.
+ * requested outputs copied back (page-locked result buffers are written in place by the kernels, without a copy);
+ * returns after the results are in the caller's buffers.
  */
 int mpcq_solve_host(mpcq_handle* h, int32_t B,
                     const void* x0, const void* yaw, const void* r_feet, const float* gait, const void* x_ref,

@@ -381,6 +381,7 @@ struct mpcq_handle {
     uint8_t* bucket[2] = {nullptr, nullptr};
     size_t perm_cap[2] = {0, 0};
     bool schedule = true;
+    bool direct_results = true;           // mpcq_solve_host: kernels write into page-locked result buffers (MPCQ_HOST_DIRECT=0 turns it off)
     int* cta_hist = nullptr;              // per-CTA histograms of the two-launch schedule: [1 + kHostStreams][kSchedMaxCtas][64]
     // warm start of the next mpcq_solve calls (mpcq_set_warm_start)
     const uint8_t* face_in = nullptr;
@@ -599,6 +600,7 @@ int mpcq_create(const mpcq_config* cfg, mpcq_handle** out) {
     if (!mpcq::consts_from_config(*cfg, h->cs, err)) { g_create_err = err; delete h; return MPCQ_ERR_INVALID; }
     h->real_size = cfg->dtype == MPCQ_F64 ? 8 : 4;
     h->schedule = cfg->schedule >= 0;
+    if (const char* ov = getenv("MPCQ_HOST_DIRECT")) h->direct_results = atoi(ov) != 0;
     DeviceGuard guard(cfg->device);
     cudaError_t e = cfg->dtype == MPCQ_F64 ? configure<double>(h) : configure<float>(h);
     if (e == cudaErrorInvalidValue && !h->smem[0]) { g_create_err = "horizon needs more shared memory than one SM has"; delete h; return MPCQ_ERR_UNSUPPORTED; }
@@ -862,7 +864,8 @@ int mpcq_solve_host(mpcq_handle* h, int32_t B, const void* x0, const void* yaw, 
     // but give the expected-work-first schedule less to work with); large batches take all four streams.  Reading page-locked
     // inputs in place (zero copy, one chunk) was tried and is slower (0.85 ms): the kernels read their inputs twice and the
     // first wave of CTAs queues 2.8 MB of PCIe reads in front of the hardest environments.
-    int nchunk = any_global ? 1 : (B >= 16384 ? kHostStreams : (B >= 1024 ? 2 : 1));
+    // v15: with the results written in place one chunk wins at 4 096 (0.78-0.79 vs 0.79-0.81 ms): the launch order sees the whole batch
+    int nchunk = any_global ? 1 : (B >= 16384 ? kHostStreams : (B >= 8192 ? 2 : 1));
     if (const char* ov = getenv("MPCQ_HOST_CHUNKS")) {          // experiments only
         const int v = atoi(ov);
         if (v >= 1 && v <= kHostStreams && !any_global) nchunk = v;
@@ -873,6 +876,15 @@ int mpcq_solve_host(mpcq_handle* h, int32_t B, const void* x0, const void* yaw, 
     }
     char* d = h->dev;
     int launches = 0;
+    // Results that go to page-locked caller buffers are written there by the kernels themselves (mapped host memory: a few
+    // posted PCIe writes per environment when it finishes) instead of being staged on the device and copied behind the kernel.
+    char* zdst[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    for (int i = 5; i < 11; ++i) {
+        if (!width[i] || !pinned[i] || !h->direct_results) continue;
+        void* dptr = nullptr;
+        if (cudaHostGetDevicePointer(&dptr, dst[i - 5], 0) == cudaSuccess) zdst[i - 5] = static_cast<char*>(dptr);
+        else cudaGetLastError();
+    }
     for (int c = 0; c < nchunk; ++c) {
         const size_t lo = b * c / nchunk, hi = b * (c + 1) / nchunk, nb = hi - lo;
         if (nb == 0) continue;
@@ -886,14 +898,17 @@ int mpcq_solve_host(mpcq_handle* h, int32_t B, const void* x0, const void* yaw, 
             }
             if (!cuda_ok(h, cudaMemcpyAsync(d + off[i] + lo * width[i], from, nb * width[i], cudaMemcpyHostToDevice, st), "H2D")) return MPCQ_ERR_CUDA;
         }
-        auto dp = [&](int i) -> char* { return width[i] ? d + off[i] + lo * width[i] : nullptr; };
+        auto dp = [&](int i) -> char* {
+            if (!width[i]) return nullptr;
+            return (i >= 5 && zdst[i - 5]) ? zdst[i - 5] + lo * width[i] : d + off[i] + lo * width[i];
+        };
         const int rc = solve_impl(h, (int32_t)nb, dp(0), dp(1), dp(2), reinterpret_cast<float*>(dp(3)), dp(4), dp(5), dp(6),
                                   reinterpret_cast<int32_t*>(dp(7)), reinterpret_cast<double*>(dp(8)),
                                   reinterpret_cast<int32_t*>(dp(9)), reinterpret_cast<uint8_t*>(dp(10)), 1, lo, st, c % kHostStreams);
         if (rc != MPCQ_OK) return rc;
         launches += h->last_launches;
         for (int i = 5; i < 11; ++i) {
-            if (!width[i]) continue;
+            if (!width[i] || zdst[i - 5]) continue;
             char* to = pinned[i] ? static_cast<char*>(dst[i - 5]) + lo * width[i] : h->pin + off[i] + lo * width[i];
             if (!cuda_ok(h, cudaMemcpyAsync(to, d + off[i] + lo * width[i], nb * width[i], cudaMemcpyDeviceToHost, st), "D2H")) return MPCQ_ERR_CUDA;
         }

@@ -169,11 +169,12 @@ def test_host_entry_point_equals_device_entry_point():
     assert np.array_equal(host["iters"], res.iters.cpu().numpy())
 
 
-def test_host_entry_point_chunked_pinned_and_pageable():
+def test_host_entry_point_chunked_pinned_and_pageable(monkeypatch):
     """B large enough for the chunked multi-stream pipeline of mpcq_solve_host; pinned buffers are used for DMA
     directly, pageable ones are staged - all three routes must agree bit for bit."""
     B = 2500
     batch = make_batch(A1Config, 10, B, "mixed", (Gait.TROTTING10, Gait.STANDING), 32, solve=False)
+    monkeypatch.setenv("MPCQ_HOST_CHUNKS", "2")                 # batches below 8 192 robots take one chunk by default
     eng = _engine(batch, A1Config, torch.float32)
     x0, feet, gait, xref, yaw = _to_dev(batch, torch.float32)
     res = eng.solve(x0, feet, gait, xref, yaw=yaw)
