@@ -28,22 +28,35 @@ constexpr int kGlobalCtas = 148 * 2;       // resident CTAs of a class whose fac
 // warps of the team that owns one environment, per slot capacity (must match mpcq::kClasses)
 template <int NCAP> struct TeamWarps { static constexpr int value = NCAP <= 64 ? MPCQ_NW0 : (NCAP <= 128 ? MPCQ_NW1 : (NCAP <= 192 ? MPCQ_NW2 : MPCQ_NW3)); };
 
-template <class T, int NCAP, bool LGLOBAL>
-// small class: shared memory allows 12 one-warp teams per SM (fp32, 18 432 B each), so cap the registers at
-// 65536 / (12 * 32) -> 168
-// (with 2-warp teams: 12 teams = 24 warps per SM)
-#ifndef MPCQ_MINB0
-#define MPCQ_MINB0 (MPCQ_NW0 > 1 ? 12 : (sizeof(T) == 4 ? 12 : 1))
+// One-warp teams (the small class) are launched several to a CTA, each warp with its own robot and its own slice of the
+// CTA's shared memory: the warps of a CTA start together and run the same instruction stream through the uniform part of the
+// path (model, factorisation, inversion - no data-dependent control flow there), so the SM's instruction caches serve one
+// copy of it instead of one per resident warp (measured: the kernel stalls on instruction fetch, profiles/r02_*).
+#ifndef MPCQ_EPC0
+#define MPCQ_EPC0 4
 #endif
-__global__ void __launch_bounds__(32 * TeamWarps<NCAP>::value, NCAP <= 64 ? MPCQ_MINB0 : 1)
+template <int NCAP> struct EnvsPerCta { static constexpr int value = TeamWarps<NCAP>::value == 1 ? MPCQ_EPC0 : 1; };
+
+template <class T, int NCAP, bool LGLOBAL>
+__global__ void __launch_bounds__(32 * TeamWarps<NCAP>::value * EnvsPerCta<NCAP>::value, NCAP <= 64 ? (sizeof(T) == 4 ? 8 / EnvsPerCta<NCAP>::value : 1) : 1)
 mpcq_solve_kernel(const __grid_constant__ Consts cs, const __grid_constant__ IO<T> io, T* gws, size_t gws_stride,
-                  int ns_lo, int ns_hi) {
+                  int ns_lo, int ns_hi, unsigned env_bytes) {
     extern __shared__ __align__(32) char smem[];
-    T* lg = LGLOBAL ? gws + (size_t)blockIdx.x * gws_stride : nullptr;
-    for (int i = blockIdx.x; i < io.B; i += gridDim.x) {
-        const int b = io.perm ? io.perm[i] : i;
-        mpcq::solve_env<T, NCAP, TeamWarps<NCAP>::value>(cs, io, b, smem, lg, ns_lo, ns_hi);
-        __syncthreads();
+    constexpr int EPC = EnvsPerCta<NCAP>::value;
+    if constexpr (EPC > 1) {
+        const int wq = threadIdx.x >> 5;
+        const int i = blockIdx.x * (blockDim.x >> 5) + wq;      // fewer warps than EPC when the workspace is large (long horizons)
+        if (i < io.B) {
+            const int b = io.perm ? io.perm[i] : i;
+            mpcq::solve_env<T, NCAP, 1>(cs, io, b, smem + (size_t)wq * env_bytes, nullptr, ns_lo, ns_hi);
+        }
+    } else {
+        T* lg = LGLOBAL ? gws + (size_t)blockIdx.x * gws_stride : nullptr;
+        for (int i = blockIdx.x; i < io.B; i += gridDim.x) {
+            const int b = io.perm ? io.perm[i] : i;
+            mpcq::solve_env<T, NCAP, TeamWarps<NCAP>::value>(cs, io, b, smem, lg, ns_lo, ns_hi);
+            __syncthreads();
+        }
     }
 }
 
@@ -157,7 +170,7 @@ mpcq_build_qp_kernel(const __grid_constant__ Consts cs, const __grid_constant__ 
     mpcq::Work<T> w;
     mpcq::carve<T>(w, smem, reinterpret_cast<T*>(smem), H, 384, true);   // no factor needed: vectors only
     // every foot-step counts as stance here so that g comes out in the full [H][12] layout
-    for (int k = lane; k < 4 * H; k += 32) { w.fk[k] = (uint8_t)k; w.fo[k] = (uint8_t)k; w.cidx[k] = (uint8_t)k; }
+    for (int k = lane; k < 4 * H; k += 32) { w.fk[k] = (uint8_t)k; w.cidx[k] = (uint8_t)k; }
     w.ns = 4 * H;
     w.nv = 12 * H;
     w.n = 12 * H;
@@ -419,8 +432,11 @@ template <class T, int NCAP, bool LG>
 cudaError_t launch_class(mpcq_handle* h, const IO<T>& io, int ci, cudaStream_t st) {
     auto kern = mpcq_solve_kernel<T, NCAP, LG>;
     const mpcq::SizeClass& sc = mpcq::kClasses[ci];
-    const int grid = LG ? (io.B < kGlobalCtas ? io.B : kGlobalCtas) : io.B;
-    kern<<<grid, 32 * TeamWarps<NCAP>::value, h->smem[ci], st>>>(h->cs, io, static_cast<T*>(h->gws), h->gws_stride, sc.ns_lo, sc.ns_hi);
+    int epc = EnvsPerCta<NCAP>::value;
+    while (epc > 1 && h->smem[ci] * epc > kMaxSmem) --epc;
+    const int grid = LG ? (io.B < kGlobalCtas ? io.B : kGlobalCtas) : (io.B + epc - 1) / epc;
+    kern<<<grid, 32 * TeamWarps<NCAP>::value * epc, h->smem[ci] * epc, st>>>(h->cs, io, static_cast<T*>(h->gws), h->gws_stride, sc.ns_lo,
+                                                                          sc.ns_hi, (unsigned)h->smem[ci]);
     return cudaGetLastError();
 }
 
@@ -492,18 +508,20 @@ cudaError_t launch_all(mpcq_handle* h, IO<T> io, int32_t* perm, uint8_t* bucket,
     return e;
 }
 
+// The dynamic shared-memory limit of a kernel is per-device state shared by every handle of the process (a handle for a
+// short horizon must not lower what a long-horizon handle needs), so it is always raised to the hardware maximum.
 template <class T, int NCAP>
 cudaError_t set_attr(mpcq_handle* h, int ci) {
     if constexpr (NCAP <= 128) {
         if (h->lglobal[ci]) return cudaErrorInvalidValue;
-        return cudaFuncSetAttribute(mpcq_solve_kernel<T, NCAP, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem[ci]);
+        return cudaFuncSetAttribute(mpcq_solve_kernel<T, NCAP, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem);
     } else if constexpr (NCAP >= 384) {
         if (!h->lglobal[ci]) return cudaErrorInvalidValue;
-        return cudaFuncSetAttribute(mpcq_solve_kernel<T, NCAP, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem[ci]);
+        return cudaFuncSetAttribute(mpcq_solve_kernel<T, NCAP, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem);
     } else {
         if (h->lglobal[ci])
-            return cudaFuncSetAttribute(mpcq_solve_kernel<T, NCAP, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem[ci]);
-        return cudaFuncSetAttribute(mpcq_solve_kernel<T, NCAP, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem[ci]);
+            return cudaFuncSetAttribute(mpcq_solve_kernel<T, NCAP, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem);
+        return cudaFuncSetAttribute(mpcq_solve_kernel<T, NCAP, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem);
     }
 }
 
@@ -520,7 +538,7 @@ cudaError_t configure(mpcq_handle* h) {
         if (h->lglobal[ci]) {
             s = mpcq::work_bytes<T>(H, ncap, false, false, nmax, mpcq::kClasses[ci].nw);
             if (s > kMaxSmem) return cudaErrorInvalidValue;
-            size_t need = (size_t)mpcq::l_elems(ncap);
+            size_t need = (size_t)mpcq::ps_elems(nmax);
             need = (need + 31) / 32 * 32;
             if (need > gws_elems) gws_elems = need;
         }
@@ -531,7 +549,7 @@ cudaError_t configure(mpcq_handle* h) {
                 if (want > s && want <= kMaxSmem) s = want;
             }
         }
-        h->smem[ci] = s;
+        h->smem[ci] = (s + 127) / 128 * 128;
     }
     cudaError_t e = cudaSuccess;
     for (int ci = 0; ci < h->ncls && e == cudaSuccess; ++ci) {
@@ -543,8 +561,8 @@ cudaError_t configure(mpcq_handle* h) {
         }
     }
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(mpcq_build_qp_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)mpcq::work_bytes<T>(H, 384, false, true));
+    if (mpcq::work_bytes<T>(H, 384, false, true) > kMaxSmem) return cudaErrorInvalidValue;
+    e = cudaFuncSetAttribute(mpcq_build_qp_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem);
     if (e != cudaSuccess) return e;
     if (gws_elems) {
         h->gws_stride = gws_elems;

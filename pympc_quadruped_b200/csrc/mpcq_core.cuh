@@ -23,8 +23,9 @@
 #pragma once
 
 #include "mpcq_warp.cuh"
-#if defined(MPCQ_HOST_EMU) && defined(MPCQ_TRACE)
+#if defined(MPCQ_HOST_EMU)
 #include <stdio.h>
+#include <stdlib.h>
 #endif
 
 namespace mpcq {
@@ -67,6 +68,7 @@ struct Consts {
     double q[13];
     double r[12];
     double tol_p, tol_d;   // relative primal / dual tolerances of the face tests
+    double tol_pc, tol_dc; // the same for the precision-T ("cheap") rounds: decisions only, the fp64 tests have the last word
     double tol_r_loose, tol_r_tight;   // reduced-gradient tolerances (relative to 1 + |g|_inf)
     double tol_active;     // slack tolerance of the reported constraint activity
     double tol_r_abs;      // absolute cap of the tight reduced-gradient tolerance: 2 min(R) * (force accuracy in N)
@@ -101,6 +103,14 @@ enum : int { ST_VERIFIED = 1, ST_FALLBACK = 2, ST_MAXITER = 4, ST_NUMERIC = 8, S
 // per-warp workspace
 MPCQ_HD constexpr size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 MPCQ_HD constexpr int l_elems(int n) { return n * n / 2 + 2 * n + 32; }   // +32: unpredicated row sweeps may overrun
+// The factor region is reused for P = H^-1 (full symmetric storage, leading dimension n + 1) and, above P's diagonal
+// and in one extra column, the Schur complement of the active rows: (n + 1)^2 elements.
+// size classes by slot capacity: most stance foot-steps of the class, rows of its largest system, leading dimension of P
+// (compile-time, so that every address in the O(n^3) loops is a base register plus an immediate)
+MPCQ_HD constexpr int class_ns_hi(int ncap) { return ncap <= 64 ? 20 : (ncap <= 128 ? 42 : (ncap <= 192 ? 64 : 128)); }
+MPCQ_HD constexpr int class_rows(int ncap) { return (3 * class_ns_hi(ncap) + 3) & ~3; }
+MPCQ_HD constexpr int class_ld(int ncap) { return class_rows(ncap) + 1; }
+MPCQ_HD constexpr int ps_elems(int n) { return (((n + 1) * (n + 1) > l_elems(n) ? (n + 1) * (n + 1) : l_elems(n)) + 3) & ~3; }
 
 template <class T> struct Work {
     // fp64
@@ -109,22 +119,29 @@ template <class T> struct Work {
     // precision T
     T *L, *dblk, *vec, *cw, *zt, *Mf, *r2;   // r2 = 2 * diag(R) in precision T
     T *NS2;                // [H][H][2]: (2 N_ij, 2 S_ij) pairs for the Hessian assembly
+    T *stage;              // [4 n] column block of L, transposed, while P = H^-1 is formed
+    T *u0f;                // unconstrained minimiser -H^-1 g (precision T)
+    T *tv;                 // scratch vector of dual_apply
+    T *lam;                // right-hand side / multipliers of the active rows
+    T *sinv;               // inverse pivots of the Schur factor
+    T *rcf;                // active row i:  u[rc1[i]] + rcf[i] * u[rc2[i]] = b_i
+    uint16_t *rc1, *rc2;
+    uint16_t *rbase;       // first active row of stance foot-step p
     int32_t* sinf;         // per slot: step | leg << 8 | foot << 16 | dead << 30
     // bytes
     uint8_t *fk;           // stance list: full foot-step index k = 4*step + leg
-    uint8_t *fo;           // stance index (position in the ORIGINAL stance list) of the foot now at position p;
-                           // the fp64 vectors g, u, gam, ucur, utrial are stored in that fixed compact order
+    uint8_t *fo;           // stance index of the foot at position p (identity; the fp64 vectors g, u, gam, ucur, utrial
+                           // are stored in that compact order)
     uint8_t *cidx;         // full foot-step k -> stance index, 255 = swing
     int8_t* face;          // 3 per stance foot-step
-    int8_t* face2;         // trial faces of the fallback
-    int8_t* facef;         // faces the current factor was built for
+    int8_t* face2;         // trial faces
     int n, ns, H, nv;      // nv = 3 * ns: live length of the compact vectors
+    int q;                 // number of active rows
     team::Ctx t;             // the team of warps that owns this environment
 };
 
 // Shared-memory layout of one team's workspace.  nvc = capacity of everything indexed by slot (the largest system of the
-// size class, `nmax`, or `ncap` when not given); cw is double-buffered only for multi-warp teams.  The small class must
-// stay within 18 432 B (fp32) so that 12 one-warp teams fit in the 228 KB of an SM (12 x (18 432 + 1 024 reserved)).
+// size class, `nmax`, or `ncap` when not given); cw is double-buffered only for multi-warp teams.
 struct Layout { size_t nd, nt, nb; int nvc, cw; };
 MPCQ_HD constexpr Layout layout(int H, int ncap, bool l_in_smem, bool with_md, int nmax, int nw) {
     Layout l{};
@@ -132,8 +149,9 @@ MPCQ_HD constexpr Layout layout(int H, int ncap, bool l_in_smem, bool with_md, i
     l.cw = nw > 1 ? 256 : 128;
     const size_t nv = (size_t)l.nvc;
     l.nd = (with_md ? 288 : 0) + 72 + 9 * (size_t)H + 12 * (size_t)H + 6 * nv + nv / 3 + 1 + 12 + 40;
-    l.nt = (l_in_smem ? (size_t)l_elems(l.nvc) : 0) + 3 * nv + nv + (size_t)l.cw + 3 * nv + 288 + 12 + 2 * (size_t)H * H;
-    l.nb = (nv / 3 + 1) * 11 + 4 * (size_t)H + 16 + 4 * nv;
+    l.nt = (l_in_smem ? (size_t)ps_elems(l.nvc) : 0) + 3 * nv + nv + (size_t)l.cw + 3 * nv + 288 + 12 + ((2 * (size_t)H * H + 3) & ~(size_t)3) +
+           4 * nv + 2 * nv + 3 * (nv + 4);
+    l.nb = (nv / 3 + 1) * 8 + 4 * (size_t)H + 16 + 4 * nv + 2 * 2 * (nv + 4) + 2 * (nv / 3 + 2) + 16;
     return l;
 }
 
@@ -169,7 +187,7 @@ MPCQ_DEV void carve(Work<T>& w, char* base, T* l_global, int H, int ncap, bool w
     if (l_global) {
         w.L = l_global;
     } else {
-        w.L = t; t += l_elems(nv);
+        w.L = t; t += ps_elems(nv);
     }
     w.dblk = t; t += 3 * nv;     // 12 values per block of 4 columns
     w.vec = t; t += nv;
@@ -177,14 +195,23 @@ MPCQ_DEV void carve(Work<T>& w, char* base, T* l_global, int H, int ncap, bool w
     w.zt = t; t += 3 * nv;
     w.Mf = t; t += 288;
     w.r2 = t; t += 12;
-    w.NS2 = t; t += 2 * H * H;
+    w.NS2 = t; t += (2 * H * H + 3) & ~3;
+    w.stage = t; t += 4 * nv;
+    w.u0f = t; t += nv;
+    w.tv = t; t += nv;
+    w.lam = t; t += nv + 4;
+    w.sinv = t; t += nv + 4;
+    w.rcf = t; t += nv + 4;
     uint8_t* b = reinterpret_cast<uint8_t*>(base + align_up(l.nd * 8, 16) + align_up(l.nt * sizeof(T), 16));
     w.fk = b; b += nv / 3 + 1;
     w.fo = b; b += nv / 3 + 1;
     w.cidx = b; b += 4 * H;
     w.face = reinterpret_cast<int8_t*>(b); b += 3 * (nv / 3 + 1);
     w.face2 = reinterpret_cast<int8_t*>(b); b += 3 * (nv / 3 + 1);
-    w.facef = reinterpret_cast<int8_t*>(b); b += 3 * (nv / 3 + 1);
+    b = reinterpret_cast<uint8_t*>(reinterpret_cast<uintptr_t>(b + 1) & ~uintptr_t(1));
+    w.rc1 = reinterpret_cast<uint16_t*>(b); b += 2 * (nv + 4);
+    w.rc2 = reinterpret_cast<uint16_t*>(b); b += 2 * (nv + 4);
+    w.rbase = reinterpret_cast<uint16_t*>(b); b += 2 * (nv / 3 + 2);
     w.sinf = reinterpret_cast<int32_t*>(reinterpret_cast<uintptr_t>(b + 15) & ~uintptr_t(15));
     w.H = H;
 }
@@ -198,8 +225,15 @@ MPCQ_DEV int colbase(int j, int n) {
     return 4 * g * n - 8 * g * (g - 1) + t * (n - 4 * g) - 4 * g;
 }
 
+#ifdef MPCQ_HOST_EMU
+// the emulation checks what the vector loads of the device require
+inline void emu_check_align(const void* p, size_t a) {
+    if (reinterpret_cast<uintptr_t>(p) % a) { fprintf(stderr, "mpcq_emu: MISALIGNED %zu-byte vector load at %p\n", a, p); abort(); }
+}
+#endif
 MPCQ_DEV void load4(const float* p, float& a, float& b, float& c, float& d) {
 #ifdef MPCQ_HOST_EMU
+    emu_check_align(p, 16);
     a = p[0]; b = p[1]; c = p[2]; d = p[3];
 #else
     float4 v = *reinterpret_cast<const float4*>(p);
@@ -208,6 +242,7 @@ MPCQ_DEV void load4(const float* p, float& a, float& b, float& c, float& d) {
 }
 MPCQ_DEV void load4(const double* p, double& a, double& b, double& c, double& d) {
 #ifdef MPCQ_HOST_EMU
+    emu_check_align(p, 16);
     a = p[0]; b = p[1]; c = p[2]; d = p[3];
 #else
     double2 v0 = *reinterpret_cast<const double2*>(p);
@@ -218,6 +253,7 @@ MPCQ_DEV void load4(const double* p, double& a, double& b, double& c, double& d)
 
 MPCQ_DEV void load2(const float* p, float& a, float& b) {
 #ifdef MPCQ_HOST_EMU
+    emu_check_align(p, 8);
     a = p[0]; b = p[1];
 #else
     float2 v = *reinterpret_cast<const float2*>(p);
@@ -226,6 +262,7 @@ MPCQ_DEV void load2(const float* p, float& a, float& b) {
 }
 MPCQ_DEV void load2(const double* p, double& a, double& b) {
 #ifdef MPCQ_HOST_EMU
+    emu_check_align(p, 16);
     a = p[0]; b = p[1];
 #else
     double2 v = *reinterpret_cast<const double2*>(p);
@@ -343,7 +380,7 @@ MPCQ_DEV void setup_model(const Consts& cs, Work<T>& w, const T* x0p, double yaw
         if (x == y) { m0 += cs.q[9 + x] * im2; m1 += cs.q[3 + x] * im2; }
         m0 *= dt2; m1 *= dt4;
         if (w.Md) { w.Md[idx] = m0; w.Md[144 + idx] = m1; }
-        w.Mf[idx] = (T)m0; w.Mf[144 + idx] = (T)m1;
+        w.Mf[2 * idx] = (T)m0; w.Mf[2 * idx + 1] = (T)m1;       // (M00, M11) pairs, row-major 12 x 12
     }
     // --- suffix sums E0, E1 of Q e_k (free response minus reference), one lane per state component
     if (lane < 12) {
@@ -379,7 +416,7 @@ MPCQ_DEV void setup_model(const Consts& cs, Work<T>& w, const T* x0p, double yaw
             t0 += w.GW[18 * a + 3 * k + y] * E0[6 + k];
             t1 += w.GW[18 * a + 9 + 3 * k + y] * E1[k];
         }
-        w.g[3 * w.fo[p] + y] = 2.0 * (dt * t0 + dt2 * t1);
+        w.g[3 * p + y] = 2.0 * (dt * t0 + dt2 * t1);
     }
     team::sync(w.t);
 }
@@ -430,7 +467,7 @@ MPCQ_DEV void hess_apply(const Consts& cs, Work<T>& w, const double* uin, double
     const double dt2 = cs.dt * cs.dt, dt4 = dt2 * dt2;
     for (int v = lane; v < w.nv; v += w.t.nt) {
         const int p = v / 3, y = v - 3 * p, j = w.fk[p] >> 2, a = w.fk[p] & 3;
-        const int o = 3 * w.fo[p] + y;
+        const int o = 3 * p + y;
         const double* Y = w.P1 + 12 * j;
         const double* gw = w.GW + 18 * a + y;
         const double t0 = cs.inv_mass * Y[3 + y] + gw[0] * Y[0] + gw[3] * Y[1] + gw[6] * Y[2];
@@ -444,56 +481,16 @@ template <class T>
 MPCQ_DEV void hess_apply(const Consts& cs, Work<T>& w) { hess_apply(cs, w, w.u, w.gam, true); }
 
 // ---------------------------------------------------------------------------------------------
-// K3: faces -> slot vectors z (precision T) and the face constants c written into u.
-// slot v = 3p + comp of stance foot-step p; dead slots (z = 0) become identity rows.
-template <class T>
-MPCQ_DEV bool build_slots(const Consts& cs, Work<T>& w) {
-    MPCQ_PHASE(2);
-    const int lane = w.t.tid;
-    const T mu = (T)cs.mu;
-    bool nonzero_c = false;
-    for (int idx = lane; idx < w.nv; idx += w.t.nt) w.u[idx] = 0.0;
-    team::sync(w.t);
-    for (int p = lane; p < w.n / 3 + 1; p += w.t.nt) {
-        T z[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-        if (p < w.ns) {
-            const int sx = w.face[3 * p], sy = w.face[3 * p + 1], sz = w.face[3 * p + 2];
-            if (sz >= 0) {
-                if (sx == 0) z[0] = 1;
-                if (sy == 0) z[4] = 1;
-                if (sz == 0) { z[6] = sx * mu; z[7] = sy * mu; z[8] = 1; }
-                else {
-                    const double fm = w.fmax[p];
-                    double* up = w.u + 3 * w.fo[p];
-                    up[0] = sx * cs.mu * fm; up[1] = sy * cs.mu * fm; up[2] = fm;
-                    nonzero_c = true;
-                }
-            }
-        }
-        MPCQ_UNROLL
-        for (int c = 0; c < 9; ++c)
-            if (3 * p + c / 3 < w.n) w.zt[9 * p + c] = z[c];
-        MPCQ_UNROLL
-        for (int c = 0; c < 3; ++c)
-            if (3 * p + c < w.n) {
-                const bool dead = z[3 * c] == 0 && z[3 * c + 1] == 0 && z[3 * c + 2] == 0;
-                const int k = p < w.ns ? w.fk[p] : 0;
-                w.sinf[3 * p + c] = (k >> 2) | ((k & 3) << 8) | (p << 16) | (dead ? (1 << 30) : 0);
-            }
-    }
-    team::sync(w.t);
-    return team::any(w.t, nonzero_c);
-}
-
-// ---------------------------------------------------------------------------------------------
-// K2 + K4a: assemble K = Z'HZ column panel by column panel (never materialised) and factor it.
+// K2 + K4a: assemble H (stance slots only) column panel by column panel - never materialised - and factor it.
 // Left-looking, 4-column panels, executed by the whole team (NW warps).  Rows are dealt to threads in blocks of
 // 4, round-robin over the warps:   row = 4 * (NW * (8 * slot + lane / 4) + warp) + lane % 4,
 // so that every warp keeps a share of the rows that are still active as the panel index grows (for NW = 1 this
 // is row = lane + 32 * slot).  Returns false on a bad pivot.  The inner sweeps are unpredicated: rows above the
-// panel / beyond n compute garbage that is never stored.
+// panel / beyond n compute garbage that is never stored.  Slot v = 3 p + comp of stance foot-step p; the slots beyond
+// 3 ns (padding of n to a multiple of 4) are identity rows.
+// An entry is  2 N_ij M00[ra][cb] + 2 S_ij M11[ra][cb] (+ 2 R on the diagonal):  one (2N, 2S) pair and one (M00, M11) pair.
 template <class T, int NCAP, int NW>
-MPCQ_DEV bool chol_factor(const Consts& cs, Work<T>& w, int k_start) {
+MPCQ_DEV bool chol_factor(const Consts& cs, Work<T>& w) {
     MPCQ_PHASE(3);
     constexpr int NSLOT = NCAP / (32 * NW);
     constexpr int RSTEP = 32 * NW;                 // rows between two slots of a thread
@@ -501,93 +498,63 @@ MPCQ_DEV bool chol_factor(const Consts& cs, Work<T>& w, int k_start) {
     const int n = w.n, H = cs.horizon;
     T* L = w.L;
     bool ok = true;
+    // per slot: horizon step | (3 leg + comp) << 8 | dead << 30
+    for (int v = w.t.tid; v < n; v += w.t.nt) {
+        const int p = v / 3, c = v - 3 * p;
+        const int k = p < w.ns ? w.fk[p] : 0;
+        w.sinf[v] = (k >> 2) | ((3 * (k & 3) + c) << 8) | (p < w.ns ? 0 : (1 << 30));
+    }
+    team::sync(w.t);
     const int row0 = 4 * (NW * (lane >> 2) + wid) + (lane & 3);
     // row data of this thread, fixed for the whole factorisation
-    T zr[NSLOT][3], zq[NSLOT][3];                  // z of the row and 2 R z (the R term of a same-foot entry)
-    int ri[NSLOT];
+    const T* nsr[NSLOT];                           // row of the (2N, 2S) table of the slot's horizon step
+    const T* mr[NSLOT];                            // row of the (M00, M11) table of the slot's force component
+    T rdiag[NSLOT];                                // 2 R of the slot (1 for a padding row)
+    bool dead[NSLOT];
     MPCQ_UNROLL
     for (int m = 0; m < NSLOT; ++m) {
         const int v = row0 + RSTEP * m;
-        const bool in = v < n;
-        ri[m] = in ? w.sinf[v] : (1 << 30);
-        zr[m][0] = in ? w.zt[3 * v] : (T)0;
-        zr[m][1] = in ? w.zt[3 * v + 1] : (T)0;
-        zr[m][2] = in ? w.zt[3 * v + 2] : (T)0;
-        const T* r2 = w.r2 + 3 * ((ri[m] >> 8) & 3);
-        zq[m][0] = zr[m][0] * r2[0]; zq[m][1] = zr[m][1] * r2[1]; zq[m][2] = zr[m][2] * r2[2];
+        const int info = v < n ? w.sinf[v] : (1 << 30);
+        const int ra = (info >> 8) & 15;
+        dead[m] = (info >> 30) != 0;
+        nsr[m] = w.NS2 + 2 * (info & 0xff) * H;
+        mr[m] = w.Mf + 24 * ra;
+        rdiag[m] = dead[m] ? (T)1 : w.r2[ra];
     }
-    // cw[c][mat][leg][x] = sum_y M_mat[3 leg + x][3 b_c + y] z_c[y] for the 4 panel columns: one (c,mat,leg) per lane of
-    // warp 0, double-buffered so the next panel's table can be written while other warps still read this one
-    auto write_cw = [&](int k0, T* dstbuf) {
-        const int c = lane >> 3, mat = (lane >> 2) & 1, leg = lane & 3;
-        const int info = w.sinf[k0 + c];
-        const int b = (info >> 8) & 3;
-        const T* z = w.zt + 3 * (k0 + c);
-        const T z0 = z[0], z1 = z[1], z2 = z[2];
-        const T* mrow = w.Mf + mat * 144 + (3 * leg) * 12 + 3 * b;
-        T* dst = dstbuf + 4 * lane;
-        dst[0] = mrow[0] * z0 + mrow[1] * z1 + mrow[2] * z2;
-        dst[1] = mrow[12] * z0 + mrow[13] * z1 + mrow[14] * z2;
-        dst[2] = mrow[24] * z0 + mrow[25] * z1 + mrow[26] * z2;
-        dst[3] = 0;
-    };
-    if (wid == 0) write_cw(0, w.cw);
-    team::sync(w.t);
-    // Rows < k_start keep their factor (leading block unchanged since the previous factorisation, see
-    // reorder_feet): for panels k0 < k_start only the rows >= k_start are recomputed (L21 = K21 L11^-T, using the
-    // stored diagonal blocks); from k_start on it is the plain left-looking factorisation.
     // One panel.  M0 >= 0 fixes the first live row slot at compile time (slots below it hold only rows above the panel):
     // with predication instead, a one-warp team would still ISSUE the dead slot's multiply-adds - half of all
     // instructions of the later panels, and the kernel is issue-bound under load.  M0 = -1: decided at run time.
     auto panel = [&](int k0, auto m0c) {
         constexpr int M0 = decltype(m0c)::value;
-        const bool keep_diag = k0 < k_start;
-        const int row_lo = keep_diag ? k_start : k0;
-        const T* cw = w.cw + (NW > 1 ? 128 * ((k0 >> 2) & 1) : 0);   // double-buffered for multi-warp teams only
-        int ci[4];
+        const int row_lo = k0;
+        int cj[4], cb[4];
+        bool cdead[4];
         MPCQ_UNROLL
-        for (int c = 0; c < 4; ++c) ci[c] = w.sinf[k0 + c];
+        for (int c = 0; c < 4; ++c) {
+            const int info = w.sinf[k0 + c];
+            cj[c] = 2 * (info & 0xff); cb[c] = 2 * ((info >> 8) & 15); cdead[c] = (info >> 30) != 0;
+        }
         // ---- initial entries of the panel
         T acc[NSLOT][4];
         const int m0 = M0 >= 0 ? M0 : row_lo / RSTEP;   // first live row slot (compile-time in the specialised bodies)
-        {
-        MPCQ_PHASE(10);
         MPCQ_UNROLL
         for (int m = 0; m < NSLOT; ++m) {
             if (m < m0) continue;
-            const int iv = ri[m] & 0xff, av = (ri[m] >> 8) & 3;
-            const bool dead = (ri[m] >> 30) != 0;
             const int v = row0 + RSTEP * m;
             MPCQ_UNROLL
             for (int c = 0; c < 4; ++c) {
-                const int jw = ci[c] & 0xff;
-                T q0, q1, q2, q3, s0, s1, s2, s3;
-                load4(cw + 4 * (8 * c + av), q0, q1, q2, q3);
-                load4(cw + 4 * (8 * c + 4 + av), s0, s1, s2, s3);
-                const T t0 = zr[m][0] * q0 + zr[m][1] * q1 + zr[m][2] * q2;
-                const T t1 = zr[m][0] * s0 + zr[m][1] * s1 + zr[m][2] * s2;
-                T n2w, s2w;
-                load2(w.NS2 + 2 * (iv * H + jw), n2w, s2w);        // 2 N_ij, 2 S_ij
+                T n2w, s2w, t0, t1;
+                load2(nsr[m] + cj[c], n2w, s2w);                   // 2 N_ij, 2 S_ij
+                load2(mr[m] + cb[c], t0, t1);                      // M00, M11 entry of the two force components
                 T e = n2w * t0 + s2w * t1;
-                // same foot-step (and same dead flag): R term / unit diagonal - branch-free (every lane executes a
-                // divergent branch body anyway as soon as one lane takes it)
-                const bool same = ((ri[m] ^ ci[c]) >> 16) == 0;
-                const T* zw = w.zt + 3 * (k0 + c);
-                const T rterm = zq[m][0] * zw[0] + zq[m][1] * zw[1] + zq[m][2] * zw[2];
-                e += wp::sel(same, rterm, (T)0);
-                e = wp::sel(same && dead && v == k0 + c, (T)1, e);
+                e = wp::sel(dead[m] || cdead[c], (T)0, e);         // padding rows / columns: identity
+                e += wp::sel(v == k0 + c, rdiag[m], (T)0);
                 acc[m][c] = e;
             }
-        }
-        }
-        if (NW == 1) {                                          // one-warp team: the table of the NEXT panel is written now, off
-            wp::sync();                                         // the serial end of this panel (every lane is done reading cw)
-            if (k0 + 4 < n) write_cw(k0 + 4, w.cw);
         }
         // ---- left-looking update with all previous columns
         const T* colg;
         {
-            MPCQ_PHASE(11);
             const T* col = L;
             int stride = n;
             // software-pipelined over groups of 4 columns: the loads of group g + 1 are issued before the multiply-adds
@@ -650,8 +617,7 @@ MPCQ_DEV bool chol_factor(const Consts& cs, Work<T>& w, int k_start) {
         }
         // ---- 4x4 diagonal block: kept, or factored by the warp that owns its rows and published through dblk
         T m10 = 0, m20 = 0, m21 = 0, m30 = 0, m31 = 0, m32 = 0, m00 = 0, m11 = 0, m22 = 0, m33 = 0;
-        if (!keep_diag) {
-            MPCQ_PHASE(12);
+        {
             const int kb = k0 >> 2, q = kb / NW;
             if (wid == kb - q * NW) {
                 const int ld = 4 * (q & 7), md = q >> 3;
@@ -695,8 +661,7 @@ MPCQ_DEV bool chol_factor(const Consts& cs, Work<T>& w, int k_start) {
             }
             if (NW > 1) team::sync(w.t);                        // dblk visible to the team
         }
-        MPCQ_PHASE(13);
-        if (NW > 1 || keep_diag) {
+        if (NW > 1) {
             T pad0, pad1;
             const T* db = w.dblk + 3 * k0;
             load4(db, m10, m20, m21, m30);
@@ -724,13 +689,11 @@ MPCQ_DEV bool chol_factor(const Consts& cs, Work<T>& w, int k_start) {
                 }
             }
         }
-        if (NW > 1 && wid == 0 && k0 + 4 < n) write_cw(k0 + 4, w.cw + 128 * (((k0 >> 2) + 1) & 1));
         team::sync(w.t);                                        // panel columns + next cw visible
     };
     for (int k0 = 0; k0 < n; k0 += 4) {
-        const int row_lo = k0 < k_start ? k_start : k0;
         if constexpr (NSLOT == 2) {
-            if (row_lo >= RSTEP) panel(k0, IntC<1>{}); else panel(k0, IntC<0>{});
+            if (k0 >= RSTEP) panel(k0, IntC<1>{}); else panel(k0, IntC<0>{});
         } else {
             panel(k0, IntC<-1>{});
         }
@@ -738,95 +701,474 @@ MPCQ_DEV bool chol_factor(const Consts& cs, Work<T>& w, int k_start) {
     return team::any(w.t, !ok) == false;
 }
 
-// K4b: solve L L' x = vec in place (vec in shared memory, precision T).  One warp; lane owns rows lane + 32 m.
-// The row updates are written branch-free (selects and zero-masked loads): per-lane if/else chains cost a divergent
-// branch region per slot and block (measured 400 cycles per 4-column block before, see profiles/r01_phase_cycles_*).
-template <class T, int NSLOT>
-MPCQ_DEV void tri_solve(Work<T>& w) {
+// ---------------------------------------------------------------------------------------------
+// K4b: P = H^-1 from the Cholesky factor, written over it.
+//
+// The factor is used exactly once per environment: every later linear solve of the active-set rounds goes through P
+// (a Schur complement on the active rows, see schur_factor), so a round costs O(q^3/6 + n q) instead of a new O(n^3/3)
+// factorisation.  P is formed by the backward block recurrence of L'P = L^-1 (4 columns J at a time, trailing block
+// "2" = rows/columns beyond J):
+//     T   = P22 L21                       (the O(n^3/3) part: one symmetric block-matvec per column block)
+//     P21 = -T M,   M = L11^-1           (the stored inverse diagonal block of the factor)
+//     P11 = M'(I + L21'T) M
+// Storage: full symmetric, element (i, k) at P[k * ld + i] with ld = n + 1 (odd: a lane-per-row sweep down a column
+// and the transposed store along a row are both conflict-free).  P is written over the packed factor in place:
+// column block J of P lands at addresses >= j0 * ld + j0, above every factor column < j0 that is still to be read.
+template <class T, int NCAP, int NW>
+MPCQ_DEV void invert_factor(Work<T>& w) {
     MPCQ_PHASE(4);
+    constexpr int NT = 32 * NW;
+    constexpr int NSLOT = NCAP / NT;
+    constexpr int ld = class_ld(NCAP);
+    const int tid = w.t.tid, n = w.n;
+    T* P = w.L;
+    T* stage = w.stage;
+    for (int j0 = n - 4; j0 >= 0; j0 -= 4) {
+        // ---- stage the column block of L (rows below the diagonal block), row-major, and fetch M
+        {
+            const T* c0 = w.L + colbase(j0, n);
+            const int stride = n - j0;
+            MPCQ_UNROLL
+            for (int m = 0; m < NSLOT; ++m) {
+                const int r = tid + NT * m;
+                if (r >= j0 + 4 && r < n) {
+                    T* d = stage + 4 * r;
+                    d[0] = c0[r]; d[1] = c0[stride + r]; d[2] = c0[2 * stride + r]; d[3] = c0[3 * stride + r];
+                }
+            }
+        }
+        T m10, m20, m21, m30, m31, m32, m00, m11, m22, m33, pad0, pad1;
+        {
+            const T* db = w.dblk + 3 * j0;
+            load4(db, m10, m20, m21, m30);
+            load4(db + 4, m31, m32, m00, m11);
+            load4(db + 8, m22, m33, pad0, pad1);
+        }
+        team::sync(w.t);
+        // ---- acc = -T = -(P22 L21) for the rows of this thread (rows above the trailing block compute garbage, never stored)
+        T acc[NSLOT][4];
+        MPCQ_UNROLL
+        for (int m = 0; m < NSLOT; ++m) { acc[m][0] = acc[m][1] = acc[m][2] = acc[m][3] = (T)0; }
+        const int m0 = (j0 + 4) / NT;                          // slots below hold no row of the trailing block
+        {
+            const T* pc = P + (size_t)(j0 + 4) * ld + tid;
+            const T* sg = stage + 4 * (j0 + 4);
+            for (int k = j0 + 4; k < n; k += 4) {
+                MPCQ_UNROLL
+                for (int t = 0; t < 4; ++t) {
+                    T l[4];
+                    load4(sg + 4 * t, l[0], l[1], l[2], l[3]);
+                    MPCQ_UNROLL
+                    for (int m = 0; m < NSLOT; ++m) {
+                        if (m < m0) continue;
+                        wp::fma4_sub(acc[m], pc[t * ld + NT * m], l);
+                    }
+                }
+                pc += 4 * ld;
+                sg += 16;
+            }
+        }
+        // ---- G = L21'(-T): 10 sums over the trailing rows (every thread adds its rows, then the team reduces)
+        T gp[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+        MPCQ_UNROLL
+        for (int m = 0; m < NSLOT; ++m) {
+            const int r = tid + NT * m;
+            if (r >= j0 + 4 && r < n) {
+                T l0, l1, l2, l3;
+                load4(stage + 4 * r, l0, l1, l2, l3);
+                gp[0] += l0 * acc[m][0];
+                gp[1] += l1 * acc[m][0]; gp[2] += l1 * acc[m][1];
+                gp[3] += l2 * acc[m][0]; gp[4] += l2 * acc[m][1]; gp[5] += l2 * acc[m][2];
+                gp[6] += l3 * acc[m][0]; gp[7] += l3 * acc[m][1]; gp[8] += l3 * acc[m][2]; gp[9] += l3 * acc[m][3];
+            }
+        }
+        MPCQ_UNROLL
+        for (int e = 0; e < 10; ++e) {
+            MPCQ_UNROLL
+            for (int sft = 16; sft > 0; sft >>= 1) gp[e] += wp::shfl_xor(gp[e], sft);
+        }
+        if (NW > 1) {
+            T* red = w.cw;                                       // free while P is formed
+            if (wp::lane() == 0) {
+                MPCQ_UNROLL
+                for (int e = 0; e < 10; ++e) red[10 * w.t.wid + e] = gp[e];
+            }
+            team::sync(w.t);
+            MPCQ_UNROLL
+            for (int e = 0; e < 10; ++e) {
+                T sacc = red[e];
+                for (int ww = 1; ww < NW; ++ww) sacc += red[10 * ww + e];
+                gp[e] = sacc;
+            }
+        }
+        // ---- P21 rows: x = (-T) M, stored down the columns of J and along its rows
+        MPCQ_UNROLL
+        for (int m = 0; m < NSLOT; ++m) {
+            const int r = tid + NT * m;
+            if (r >= j0 + 4 && r < n) {
+                const T x0 = (acc[m][0] * m00 + acc[m][1] * m10) + (acc[m][2] * m20 + acc[m][3] * m30);
+                const T x1 = acc[m][1] * m11 + acc[m][2] * m21 + acc[m][3] * m31;
+                const T x2 = acc[m][2] * m22 + acc[m][3] * m32;
+                const T x3 = acc[m][3] * m33;
+                T* pc = P + (size_t)j0 * ld + r;
+                pc[0] = x0; pc[ld] = x1; pc[2 * ld] = x2; pc[3 * ld] = x3;
+                T* pr = P + (size_t)r * ld + j0;
+                pr[0] = x0; pr[1] = x1; pr[2] = x2; pr[3] = x3;
+            }
+        }
+        // ---- P11 = M'(I - G)M   (G symmetric: gp = g00 | g10 g11 | g20 g21 g22 | g30 g31 g32 g33), one thread stores it
+        if (tid == 0) {
+            const T a00 = (T)1 - gp[0], a10 = -gp[1], a11 = (T)1 - gp[2], a20 = -gp[3], a21 = -gp[4], a22 = (T)1 - gp[5];
+            const T a30 = -gp[6], a31 = -gp[7], a32 = -gp[8], a33 = (T)1 - gp[9];
+            // B = A M  (M lower triangular: B[e][d] = sum_{f >= d} A[e][f] M[f][d])
+            const T b00 = a00 * m00 + a10 * m10 + a20 * m20 + a30 * m30, b01 = a10 * m11 + a20 * m21 + a30 * m31,
+                    b02 = a20 * m22 + a30 * m32, b03 = a30 * m33;
+            const T b10 = a10 * m00 + a11 * m10 + a21 * m20 + a31 * m30, b11 = a11 * m11 + a21 * m21 + a31 * m31,
+                    b12 = a21 * m22 + a31 * m32, b13 = a31 * m33;
+            const T b20 = a20 * m00 + a21 * m10 + a22 * m20 + a32 * m30, b21 = a21 * m11 + a22 * m21 + a32 * m31,
+                    b22 = a22 * m22 + a32 * m32, b23 = a32 * m33;
+            const T b30 = a30 * m00 + a31 * m10 + a32 * m20 + a33 * m30, b31 = a31 * m11 + a32 * m21 + a33 * m31,
+                    b32 = a32 * m22 + a33 * m32, b33 = a33 * m33;
+            // P11[c][d] = sum_{e >= c} M[e][c] B[e][d]
+            const T p00 = m00 * b00 + m10 * b10 + m20 * b20 + m30 * b30;
+            const T p10 = m11 * b10 + m21 * b20 + m31 * b30, p11 = m11 * b11 + m21 * b21 + m31 * b31;
+            const T p20 = m22 * b20 + m32 * b30, p21 = m22 * b21 + m32 * b31, p22 = m22 * b22 + m32 * b32;
+            const T p30 = m33 * b30, p31 = m33 * b31, p32 = m33 * b32, p33 = m33 * b33;
+            (void)b01; (void)b02; (void)b03; (void)b12; (void)b13; (void)b23;
+            T* pd = P + (size_t)j0 * ld + j0;
+            pd[0] = p00; pd[1] = p10; pd[2] = p20; pd[3] = p30;
+            pd[ld] = p10; pd[ld + 1] = p11; pd[ld + 2] = p21; pd[ld + 3] = p31;
+            pd[2 * ld] = p20; pd[2 * ld + 1] = p21; pd[2 * ld + 2] = p22; pd[2 * ld + 3] = p32;
+            pd[3 * ld] = p30; pd[3 * ld + 1] = p31; pd[3 * ld + 2] = p32; pd[3 * ld + 3] = p33;
+        }
+        team::sync(w.t);
+    }
+}
+
+// element (i, k) of the symmetric P, read from its lower triangle (the upper one is given to the Schur complement)
+template <class T> MPCQ_DEV T psym(const T* P, int ld, int i, int k) {
+    const int lo = i < k ? i : k, hi = i < k ? k : i;
+    return P[lo * ld + hi];
+}
+
+// ---------------------------------------------------------------------------------------------
+// K3b: the active rows of the current faces.  Row i reads  u[rc1] + rcf u[rc2] = b:
+//   fx = sx mu fz -> (x, z, -sx mu, 0);  fy likewise;  fz = fmax -> (z, z, 0, fmax);  apex -> x, y, z = 0 (three rows).
+// Rows are numbered foot by foot (rbase[p] = first row of foot p); lam receives rho = A u0 - b.  One warp.
+template <class T, int NFS>
+MPCQ_DEV int dual_rows(const Consts& cs, Work<T>& w) {
     const int lane = wp::lane();
-    const int n = w.n;
-    const T* L = w.L;
+    const T mu = (T)cs.mu;
+    int base = 0;
+    MPCQ_UNROLL
+    for (int t = 0; t < NFS; ++t) {
+        const int p = lane + 32 * t;
+        const bool valid = p < w.ns;
+        const int sx = valid ? w.face[3 * p] : 0, sy = valid ? w.face[3 * p + 1] : 0, sz = valid ? w.face[3 * p + 2] : 0;
+        const int cnt = !valid ? 0 : (sz < 0 ? 3 : (sx != 0) + (sy != 0) + (sz > 0));
+        int incl = cnt;                                          // inclusive scan over the lanes
+        MPCQ_UNROLL
+        for (int d = 1; d < 32; d <<= 1) {
+            const int o = wp::shfl(incl, (lane - d) & 31);
+            incl += lane >= d ? o : 0;
+        }
+        int r = base + incl - cnt;
+        if (valid) {
+            w.rbase[p] = (uint16_t)r;
+            const int vx = 3 * p, vy = 3 * p + 1, vz = 3 * p + 2;
+            const T ux = w.u0f[vx], uy = w.u0f[vy], uz = w.u0f[vz];
+            if (sz < 0) {
+                w.rc1[r] = (uint16_t)vx; w.rc2[r] = (uint16_t)vx; w.rcf[r] = (T)0; w.lam[r] = ux; ++r;
+                w.rc1[r] = (uint16_t)vy; w.rc2[r] = (uint16_t)vy; w.rcf[r] = (T)0; w.lam[r] = uy; ++r;
+                w.rc1[r] = (uint16_t)vz; w.rc2[r] = (uint16_t)vz; w.rcf[r] = (T)0; w.lam[r] = uz;
+            } else {
+                if (sx != 0) { w.rc1[r] = (uint16_t)vx; w.rc2[r] = (uint16_t)vz; w.rcf[r] = -(T)sx * mu; w.lam[r] = ux - (T)sx * mu * uz; ++r; }
+                if (sy != 0) { w.rc1[r] = (uint16_t)vy; w.rc2[r] = (uint16_t)vz; w.rcf[r] = -(T)sy * mu; w.lam[r] = uy - (T)sy * mu * uz; ++r; }
+                if (sz > 0) { w.rc1[r] = (uint16_t)vz; w.rc2[r] = (uint16_t)vz; w.rcf[r] = (T)0; w.lam[r] = uz - (T)w.fmax[p]; }
+            }
+        }
+        base += wp::shfl(incl, 31);
+    }
+    return base;
+}
+
+// element (i, j), j <= i, of the Schur complement / its Cholesky factor: kept above P's diagonal, at P[(i + 1) * ld + j]
+// (column i + 1 <= n exists because the region has n + 1 columns), so it costs no shared memory of its own
+#define MPCQ_SA(i, j) P[((i) + 1) * ld + (j)]
+
+// K4c: S = A P A' on the q active rows (padded with identity rows to a multiple of 4) and its Cholesky factor.
+// The entries are written first (every thread its rows: no dependencies), then the factor is formed column by column,
+// left-looking, one row per thread and slot.  Every thread accumulates the pivot of column j itself (it reads row j of
+// the factor anyway), so a column needs no exchange - only the barrier that publishes it.  The inverse 4x4 diagonal
+// blocks go to dblk (free once P is formed) for the blocked substitutions of schur_solve.  Returns false on a bad pivot.
+template <class T, int NCAP, int NW>
+MPCQ_DEV bool schur_factor(Work<T>& w) {
+    MPCQ_PHASE(10);
+    constexpr int NT = 32 * NW;
+    constexpr int NSLOT = NCAP / NT;
+    constexpr int ld = class_ld(NCAP);
+    const int tid = w.t.tid, q = w.q, q4 = (q + 3) & ~3;
+    T* P = w.L;
+    const int nsl = (q4 + NT - 1) / NT;                          // live row slots
+    bool ok = true;
+    T* rp[NSLOT];
+    MPCQ_UNROLL
+    for (int m = 0; m < NSLOT; ++m) {
+        if (m >= nsl) continue;
+        const int i = tid + NT * m;
+        const int ie = i < q4 ? i : q4 - 1;                      // rows beyond the system read (and discard) the last row
+        rp[m] = &MPCQ_SA(ie, 0);
+        if (i < q) {
+            const int c1 = w.rc1[i], c2 = w.rc2[i];
+            const T cf = w.rcf[i];
+            for (int j = 0; j <= i; ++j) {
+                const int c1j = w.rc1[j], c2j = w.rc2[j];
+                const T cfj = w.rcf[j];
+                rp[m][j] = (psym(P, ld, c1, c1j) + cfj * psym(P, ld, c1, c2j)) + cf * (psym(P, ld, c2, c1j) + cfj * psym(P, ld, c2, c2j));
+            }
+        } else if (i < q4) {
+            for (int j = 0; j < i; ++j) rp[m][j] = (T)0;
+            rp[m][i] = (T)1;
+        }
+    }
+    team::sync(w.t);
+    // ---- left-looking factorisation in panels of 4 columns
+    for (int k0 = 0; k0 < q4; k0 += 4) {
+        // rows k0 .. k0+3 of the factor so far, transposed: stage[k] = L[k0 .. k0+3, k]  (one 4-vector per earlier column)
+        for (int k = tid; k < k0; k += NT) {
+            const T* c = &MPCQ_SA(k0, k);
+            T* d = w.stage + 4 * k;
+            d[0] = c[0]; d[1] = c[ld]; d[2] = c[2 * ld]; d[3] = c[3 * ld];
+        }
+        team::sync(w.t);
+        T acc[NSLOT][4];
+        MPCQ_UNROLL
+        for (int m = 0; m < NSLOT; ++m) {
+            if (m >= nsl) continue;
+            const T* r = rp[m] + k0;
+            acc[m][0] = r[0]; acc[m][1] = r[1]; acc[m][2] = r[2]; acc[m][3] = r[3];
+        }
+        for (int k = 0; k < k0; k += 4) {
+            MPCQ_UNROLL
+            for (int t = 0; t < 4; ++t) {
+                T l[4];
+                load4(w.stage + 4 * (k + t), l[0], l[1], l[2], l[3]);
+                MPCQ_UNROLL
+                for (int m = 0; m < NSLOT; ++m) {
+                    if (m >= nsl) continue;
+                    wp::fma4_sub(acc[m], rp[m][k + t], l);
+                }
+            }
+        }
+        // the 4x4 diagonal block: its owners publish it, every thread factors it (inverse M of its Cholesky factor)
+        T* dg = w.cw;
+        MPCQ_UNROLL
+        for (int m = 0; m < NSLOT; ++m) {
+            if (m >= nsl) continue;
+            const int dv = tid + NT * m - k0;
+            if ((unsigned)dv < 4u) { T* d = dg + 4 * dv; d[0] = acc[m][0]; d[1] = acc[m][1]; d[2] = acc[m][2]; d[3] = acc[m][3]; }
+        }
+        team::sync(w.t);
+        T d00, d10, d11, d20, d21, d22, d30, d31, d32, d33, pad0, pad1, pad2, pad3, pad4, pad5;
+        load4(dg, d00, pad0, pad1, pad2);
+        load4(dg + 4, d10, d11, pad3, pad4);
+        load4(dg + 8, d20, d21, d22, pad5);
+        load4(dg + 12, d30, d31, d32, d33);
+        T piv = d00;
+        ok = ok && (piv > (T)0);
+        const T i0 = wp::rsqrt_(piv > (T)0 ? piv : (T)1);
+        const T l10 = d10 * i0, l20 = d20 * i0, l30 = d30 * i0;
+        piv = d11 - l10 * l10;
+        ok = ok && (piv > (T)0);
+        const T i1 = wp::rsqrt_(piv > (T)0 ? piv : (T)1);
+        const T l21 = (d21 - l20 * l10) * i1, l31 = (d31 - l30 * l10) * i1;
+        piv = d22 - l20 * l20 - l21 * l21;
+        ok = ok && (piv > (T)0);
+        const T i2 = wp::rsqrt_(piv > (T)0 ? piv : (T)1);
+        const T l32 = (d32 - l30 * l20 - l31 * l21) * i2;
+        piv = d33 - l30 * l30 - l31 * l31 - l32 * l32;
+        ok = ok && (piv > (T)0);
+        const T i3 = wp::rsqrt_(piv > (T)0 ? piv : (T)1);
+        const T m10 = -(l10 * i0) * i1, m21 = -(l21 * i1) * i2, m32 = -(l32 * i2) * i3;
+        const T m20 = -(l20 * i0 + l21 * m10) * i2, m31 = -(l31 * i1 + l32 * m21) * i3;
+        const T m30 = -(l30 * i0 + l31 * m10 + l32 * m20) * i3;
+        if (tid == 0) {
+            T* db = w.dblk + 3 * k0;
+            db[0] = m10; db[1] = m20; db[2] = m21; db[3] = m30;
+            db[4] = m31; db[5] = m32; db[6] = i0; db[7] = i1;
+            db[8] = i2; db[9] = i3; db[10] = 0; db[11] = 0;
+        }
+        // panel rows: x = acc inv(Ld)'
+        MPCQ_UNROLL
+        for (int m = 0; m < NSLOT; ++m) {
+            if (m >= nsl) continue;
+            const int i = tid + NT * m, dv = i - k0;
+            if (dv >= 0 && i < q4) {
+                T* r = rp[m] + k0;
+                r[0] = i0 * acc[m][0];
+                if (dv >= 1) r[1] = m10 * acc[m][0] + i1 * acc[m][1];
+                if (dv >= 2) r[2] = (m20 * acc[m][0] + m21 * acc[m][1]) + i2 * acc[m][2];
+                if (dv >= 3) r[3] = (m30 * acc[m][0] + m31 * acc[m][1]) + (m32 * acc[m][2] + i3 * acc[m][3]);
+            }
+        }
+        team::sync(w.t);
+    }
+    return ok;
+}
+
+// lam <- S^-1 lam through the factor: forward and backward substitution in blocks of 4 columns (inverse diagonal blocks
+// from dblk: 4 independent dot products per block instead of a 4-deep chain).  One warp; lane owns rows lane + 32 m.
+// Branch-free row updates (selects and masked loads), as the per-lane if/else chains cost a divergent region each.
+template <class T, int NSLOT, int ld>
+MPCQ_DEV void schur_solve(Work<T>& w) {
+    MPCQ_PHASE(13);
+    const int lane = wp::lane(), q = w.q, q4 = (q + 3) & ~3;
+    const T* P = w.L;
     T bv[NSLOT];
-    int cbv[NSLOT];
+    const T* rp[NSLOT];
     MPCQ_UNROLL
     for (int m = 0; m < NSLOT; ++m) {
         const int v = lane + 32 * m;
-        bv[m] = v < n ? w.vec[v] : (T)0;
-        cbv[m] = v < n ? colbase(v, n) : 0;
+        bv[m] = v < q ? w.lam[v] : (T)0;
+        rp[m] = &MPCQ_SA(v < q4 ? v : q4 - 1, 0);
     }
-    // One 4-column block of the forward / backward sweep.  MD = the slot that holds the block's rows when known at compile
-    // time (NSLOT == 2: slots below MD in the forward sweep / above MD in the backward sweep hold no row that still
-    // changes, and are not even issued); MD = -1: generic.
-    auto fwd = [&](int k0, auto mdc) {
-        constexpr int MD = decltype(mdc)::value;
-        const int md = MD >= 0 ? MD : (k0 >> 5), ld = k0 & 31;
-        const T mine = MD >= 0 ? bv[MD >= 0 ? MD : 0] : pick<T, NSLOT>(bv, md);
-        const T b0 = wp::shfl(mine, ld), b1 = wp::shfl(mine, ld + 1), b2 = wp::shfl(mine, ld + 2), b3 = wp::shfl(mine, ld + 3);
+    const int nsl = (q4 + 31) >> 5;
+    for (int k0 = 0; k0 < q4; k0 += 4) {                        // L y = rho
+        const T mine = pick<T, NSLOT>(bv, k0 >> 5);
+        const int l0 = k0 & 31;
+        const T b0 = wp::shfl(mine, l0), b1 = wp::shfl(mine, l0 + 1), b2 = wp::shfl(mine, l0 + 2), b3 = wp::shfl(mine, l0 + 3);
         T m10, m20, m21, m30, m31, m32, m00, m11, m22, m33, pad0, pad1;
         const T* db = w.dblk + 3 * k0;
         load4(db, m10, m20, m21, m30);
         load4(db + 4, m31, m32, m00, m11);
         load4(db + 8, m22, m33, pad0, pad1);
-        const T y0 = m00 * b0;                                  // y = M b (M = inverse of the diagonal block)
+        const T y0 = m00 * b0;
         const T y1 = m10 * b0 + m11 * b1;
         const T y2 = (m20 * b0 + m21 * b1) + m22 * b2;
         const T y3 = (m30 * b0 + m31 * b1) + (m32 * b2 + m33 * b3);
-        const int stride = n - k0;
-        const T* c0 = L + colbase(k0, n);
         MPCQ_UNROLL
-        for (int m = (MD >= 0 ? MD : 0); m < NSLOT; ++m) {
-            const int v = lane + 32 * m;
-            const int dv = v - k0;
-            const bool upd = dv >= 4 && v < n;
-            const T l0 = upd ? c0[v] : (T)0, l1 = upd ? c0[stride + v] : (T)0;
-            const T l2 = upd ? c0[2 * stride + v] : (T)0, l3 = upd ? c0[3 * stride + v] : (T)0;
-            const T contrib = (l0 * y0 + l1 * y1) + (l2 * y2 + l3 * y3);
+        for (int m = 0; m < NSLOT; ++m) {
+            if (m >= nsl) continue;
+            const int dv = lane + 32 * m - k0;
+            const T* r = rp[m] + k0;
+            const T contrib = (r[0] * y0 + r[1] * y1) + (r[2] * y2 + r[3] * y3);
             const T yv = wp::sel(dv < 2, wp::sel(dv == 0, y0, y1), wp::sel(dv == 2, y2, y3));
-            bv[m] = wp::sel((unsigned)dv < 4u, yv, bv[m] - contrib);
+            bv[m] = wp::sel((unsigned)dv < 4u, yv, wp::sel(dv >= 4, bv[m] - contrib, bv[m]));
         }
-    };
-    auto bwd = [&](int k0, auto mdc) {
-        constexpr int MD = decltype(mdc)::value;
-        const int md = MD >= 0 ? MD : (k0 >> 5), ld = k0 & 31;
-        const T mine = MD >= 0 ? bv[MD >= 0 ? MD : 0] : pick<T, NSLOT>(bv, md);
-        const T b0 = wp::shfl(mine, ld), b1 = wp::shfl(mine, ld + 1), b2 = wp::shfl(mine, ld + 2), b3 = wp::shfl(mine, ld + 3);
+    }
+    for (int k0 = q4 - 4; k0 >= 0; k0 -= 4) {                   // L' lam = y
+        const T mine = pick<T, NSLOT>(bv, k0 >> 5);
+        const int l0 = k0 & 31;
+        const T b0 = wp::shfl(mine, l0), b1 = wp::shfl(mine, l0 + 1), b2 = wp::shfl(mine, l0 + 2), b3 = wp::shfl(mine, l0 + 3);
         T m10, m20, m21, m30, m31, m32, m00, m11, m22, m33, pad0, pad1;
         const T* db = w.dblk + 3 * k0;
         load4(db, m10, m20, m21, m30);
         load4(db + 4, m31, m32, m00, m11);
         load4(db + 8, m22, m33, pad0, pad1);
-        const T x3 = m33 * b3;                                  // x = M' b
+        const T x3 = m33 * b3;
         const T x2 = m22 * b2 + m32 * b3;
         const T x1 = (m11 * b1 + m21 * b2) + m31 * b3;
         const T x0 = (m00 * b0 + m10 * b1) + (m20 * b2 + m30 * b3);
+        const T* c0 = &MPCQ_SA(k0, 0);                           // rows k0 .. k0+3 of the factor, read along the row
         MPCQ_UNROLL
-        for (int m = 0; m < (MD >= 0 ? MD + 1 : NSLOT); ++m) {
+        for (int m = 0; m < NSLOT; ++m) {
+            if (m >= nsl) continue;
             const int v = lane + 32 * m;
             const int dv = v - k0;
-            T a0, a1, a2, a3;
-            load4(L + cbv[m] + k0, a0, a1, a2, a3);              // L[k0..k0+3, v]; any row >= k0 reads in-bounds garbage, masked below
-            const T contrib = (a0 * x0 + a1 * x1) + (a2 * x2 + a3 * x3);
+            const int ve = dv < 0 ? v : 0;                       // rows at or beyond the block read column 0 (masked below)
+            const T contrib = (c0[ve] * x0 + c0[ld + ve] * x1) + (c0[2 * ld + ve] * x2 + c0[3 * ld + ve] * x3);
             const T xv = wp::sel(dv < 2, wp::sel(dv == 0, x0, x1), wp::sel(dv == 2, x2, x3));
             bv[m] = wp::sel(dv < 0, bv[m] - contrib, wp::sel(dv < 4, xv, bv[m]));
         }
-    };
-    if constexpr (NSLOT == 2) {
-        const int nlo = n < 32 ? n : 32;
-        for (int k0 = 0; k0 < nlo; k0 += 4) fwd(k0, IntC<0>{});
-        for (int k0 = 32; k0 < n; k0 += 4) fwd(k0, IntC<1>{});
-        for (int k0 = n - 4; k0 >= 32; k0 -= 4) bwd(k0, IntC<1>{});
-        for (int k0 = nlo - 4; k0 >= 0; k0 -= 4) bwd(k0, IntC<0>{});
-    } else {
-        for (int k0 = 0; k0 < n; k0 += 4) fwd(k0, IntC<-1>{});
-        for (int k0 = n - 4; k0 >= 0; k0 -= 4) bwd(k0, IntC<-1>{});
     }
     MPCQ_UNROLL
     for (int m = 0; m < NSLOT; ++m) {
-        const int v = lane + 32 * m;
-        if (v < n) w.vec[v] = bv[m];
+        const int i = lane + 32 * m;
+        if (i < q) w.lam[i] = bv[m];
     }
     wp::sync();
+}
+
+// The two uses of the Schur complement, one body (the kernel stalls on instruction fetch: every large piece exists once):
+//   round   the minimiser on the current faces, precision T: rows, S and its factor, multipliers lam = S^-1 (A u0 - b),
+//           u = u0 - P A' lam (made exact on the faces, stored as fp64) and gam = -A' lam.
+//   !round  vec <- (P - P A' S^-1 A P) vec: the inverse of H restricted to the null space of the active rows, applied to
+//           the slot-form reduced gradient (the right-hand side of the reduced system, lifted to the full space).
+// Returns false on a bad pivot.
+template <class T, int NCAP, int NW>
+MPCQ_DEV bool dual_op(const Consts& cs, Work<T>& w, bool round) {
+    MPCQ_PHASE(11);
+    constexpr int NFS = (NCAP / 3 + 31) / 32;
+    constexpr int ld = class_ld(NCAP);
+    const int n = w.n;
+    const T* P = w.L;
+    bool ok = true;
+    const T* base = w.u0f;
+    if (round) {
+        int q = 0;
+        if (w.t.wid == 0) q = dual_rows<T, NFS>(cs, w);
+        w.q = team::bcast(w.t, q);
+        if (w.q > 0) ok = schur_factor<T, NCAP, NW>(w);
+    } else {
+        for (int v = w.t.tid; v < w.nv; v += w.t.nt) {
+            T a0 = 0, a1 = 0;
+            for (int k = 0; k < n; k += 4) {
+                T r0, r1, r2, r3;
+                load4(w.vec + k, r0, r1, r2, r3);
+                a0 += psym(P, ld, v, k) * r0 + psym(P, ld, v, k + 2) * r2;
+                a1 += psym(P, ld, v, k + 1) * r1 + psym(P, ld, v, k + 3) * r3;
+            }
+            w.tv[v] = a0 + a1;
+        }
+        team::sync(w.t);
+        for (int i = w.t.tid; i < w.q; i += w.t.nt) w.lam[i] = w.tv[w.rc1[i]] + w.rcf[i] * w.tv[w.rc2[i]];
+        team::sync(w.t);
+        base = w.tv;
+    }
+    if (w.q > 0) {
+        if (w.t.wid == 0) schur_solve<T, NCAP / 32, class_ld(NCAP)>(w);
+        team::sync(w.t);
+    }
+    // vec = base - P A' lam
+    {
+        MPCQ_PHASE(14);
+        const int q = w.q;
+        for (int v = w.t.tid; v < w.nv; v += w.t.nt) {
+            T a = base[v];
+            for (int i = 0; i < q; ++i) {
+                const T li = w.lam[i], cfi = w.rcf[i];
+                const int c1i = w.rc1[i], c2i = w.rc2[i];
+                a -= li * (psym(P, ld, v, c1i) + cfi * psym(P, ld, v, c2i));
+            }
+            w.vec[v] = a;
+        }
+        team::sync(w.t);
+    }
+    if (round) {
+        const double mu = cs.mu;
+        for (int p = w.t.tid; p < w.ns; p += w.t.nt) {
+            const int sx = w.face[3 * p], sy = w.face[3 * p + 1], sz = w.face[3 * p + 2];
+            double* up = w.u + 3 * p;
+            double* gp = w.gam + 3 * p;
+            int r = w.rbase[p];
+            if (sz < 0) {
+                up[0] = up[1] = up[2] = 0.0;
+                gp[0] = -(double)w.lam[r]; gp[1] = -(double)w.lam[r + 1]; gp[2] = -(double)w.lam[r + 2];
+            } else {
+                double lx = 0.0, ly = 0.0, lz = 0.0;
+                if (sx != 0) lx = (double)w.lam[r++];
+                if (sy != 0) ly = (double)w.lam[r++];
+                if (sz > 0) lz = (double)w.lam[r];
+                const double fz = sz > 0 ? w.fmax[p] : (double)w.vec[3 * p + 2];
+                up[2] = fz;
+                up[0] = sx != 0 ? sx * mu * fz : (double)w.vec[3 * p];
+                up[1] = sy != 0 ? sy * mu * fz : (double)w.vec[3 * p + 1];
+                gp[0] = -lx; gp[1] = -ly; gp[2] = mu * (sx * lx + sy * ly) - lz;
+            }
+        }
+        team::sync(w.t);
+    }
+    return ok;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -855,7 +1197,7 @@ MPCQ_DEV double reduced_gradient(const Consts& cs, Work<T>& w) {
     double rmax = 0;
     for (int p = lane; p < w.n / 3 + 1; p += w.t.nt) {
         double r0 = 0.0, r1 = 0.0, r2 = 0.0;
-        if (p < w.ns) foot_residual(w.face[3 * p], w.face[3 * p + 1], w.face[3 * p + 2], w.gam + 3 * w.fo[p], cs.mu, r0, r1, r2);
+        if (p < w.ns) foot_residual(w.face[3 * p], w.face[3 * p + 1], w.face[3 * p + 2], w.gam + 3 * p, cs.mu, r0, r1, r2);
         if (3 * p < w.n) w.vec[3 * p] = (T)r0;                   // the slots beyond 3 ns (padding of n to a multiple of 4) get 0
         if (3 * p + 1 < w.n) w.vec[3 * p + 1] = (T)r1;
         if (3 * p + 2 < w.n) w.vec[3 * p + 2] = (T)r2;
@@ -875,7 +1217,7 @@ MPCQ_DEV void apply_step(const Consts& cs, Work<T>& w) {
     for (int p = lane; p < w.ns; p += w.t.nt) {
         const int sx = w.face[3 * p], sy = w.face[3 * p + 1], sz = w.face[3 * p + 2];
         if (sz < 0) continue;
-        double* up = w.u + 3 * w.fo[p];
+        double* up = w.u + 3 * p;
         const double w0 = (double)w.vec[3 * p], w1 = (double)w.vec[3 * p + 1], w2 = (double)w.vec[3 * p + 2];
         if (sz == 0) {
             up[2] += w2;
@@ -889,103 +1231,6 @@ MPCQ_DEV void apply_step(const Consts& cs, Work<T>& w) {
     team::sync(w.t);
 }
 
-// Improve u on the current faces until the reduced gradient is below tol; leaves gam = Hu+g.
-// Conjugate gradients on the reduced system Z'HZ w = -Z'(Hu+g), preconditioned by the (precision-T) Cholesky
-// factor, with every residual and the operator in fp64.  With an accurate factor this is one step of
-// iterative refinement per iteration; with a factor that is only a rough inverse (fp32, n = 180, cond 1e6)
-// plain refinement stagnates while CG still converges in a few steps.  The search direction lives in the
-// full space (d = Z p, kept in utrial), so no reduced-space fp64 vectors are needed.
-template <class T, int NSLOT>
-MPCQ_DEV double refine(const Consts& cs, Work<T>& w, double tol_abs, bool u_is_zero, bool use_cg) {
-    const int lane = w.t.tid;
-    // ONE loop (one call site each for tri_solve and reduced_gradient - the kernel stalls on instruction fetch, code size
-    // matters) with two phases:
-    //  plain  u += Z M^-1 r, gam recomputed: with an accurate factor it gains 2-3 digits per step and is the cheapest.
-    //         Intermediate active-set rounds (use_cg = false) stop there - they only need the faces right.
-    //  cg     entered when the plain steps converge too slowly or run out: preconditioned CG, gam updated incrementally.
-    double rmax = 0.0, prev = 0.0, rz = 0.0;
-    double* d = w.utrial;
-    const int cap = use_cg ? cs.refine_max : 3;
-    bool cg = false;
-    int it = 0, itcg = 0;
-    for (;;) {
-        if (!cg) {
-            if (it == 0 && u_is_zero) {
-                for (int idx = lane; idx < w.nv; idx += w.t.nt) w.gam[idx] = w.g[idx];
-                team::sync(w.t);
-            } else {
-                hess_apply(cs, w);
-            }
-        }
-        rmax = reduced_gradient(cs, w);                              // r = -Z' gam -> vec
-        if (!cg) {
-            const bool stop = !(rmax > tol_abs && it < cap);
-            if (stop || (it > 0 && rmax > 0.2 * prev)) {         // done, out of steps, or converging too slowly: hand over to CG
-                if (!use_cg || rmax <= tol_abs) return rmax;
-                cg = true;
-            } else {
-                prev = rmax;
-            }
-        }
-        if (cg && !(rmax > tol_abs && itcg < cs.refine_max)) break;
-        if (w.t.wid == 0) tri_solve<T, NSLOT>(w);               // z = M^-1 r; the serial chain runs on one warp
-        team::sync(w.t);
-        if (!cg) {
-            apply_step(cs, w);
-            ++it;
-            continue;
-        }
-        // rz = r'z (r recomputed from gam in fp64), beta, d = Z z + beta d
-        double part = 0.0;
-        for (int v = lane; v < w.n; v += w.t.nt) {
-            const int p = v / 3;
-            if (p < w.ns)
-                part += slot_residual(w.face[3 * p], w.face[3 * p + 1], w.face[3 * p + 2], v - 3 * p, w.gam + 3 * w.fo[p], cs.mu) *
-                        (double)w.vec[v];
-        }
-        const double rz_new = team::reduce_sum(w.t, part);
-        const double beta = itcg == 0 ? 0.0 : rz_new / rz;
-        rz = rz_new;
-        if (!(rz > 0.0)) break;                                  // converged to rounding (or a broken factor)
-        for (int p = lane; p < w.ns; p += w.t.nt) {
-            const int sx = w.face[3 * p], sy = w.face[3 * p + 1], sz = w.face[3 * p + 2];
-            double* dp = d + 3 * w.fo[p];
-            double z0 = 0.0, z1 = 0.0, z2 = 0.0;
-            if (sz >= 0) {
-                const double w0 = (double)w.vec[3 * p], w1 = (double)w.vec[3 * p + 1], w2 = (double)w.vec[3 * p + 2];
-                if (sz == 0) { z2 = w2; z0 = sx != 0 ? sx * cs.mu * w2 : w0; z1 = sy != 0 ? sy * cs.mu * w2 : w1; }
-                else { z0 = sx == 0 ? w0 : 0.0; z1 = sy == 0 ? w1 : 0.0; }
-            }
-            if (itcg == 0) { dp[0] = z0; dp[1] = z1; dp[2] = z2; }
-            else { dp[0] = z0 + beta * dp[0]; dp[1] = z1 + beta * dp[1]; dp[2] = z2 + beta * dp[2]; }
-        }
-        team::sync(w.t);
-        hess_apply(cs, w, d, w.hd, false);                       // hd = H d
-        part = 0.0;
-        for (int idx = lane; idx < w.nv; idx += w.t.nt) part += d[idx] * w.hd[idx];
-        const double dHd = team::reduce_sum(w.t, part);
-        if (!(dHd > 0.0)) break;
-        const double alpha = rz / dHd;
-        for (int idx = lane; idx < w.nv; idx += w.t.nt) {
-            w.u[idx] += alpha * d[idx];
-            w.gam[idx] += alpha * w.hd[idx];
-        }
-        team::sync(w.t);
-        ++itcg;
-    }
-    // the face equalities hold to rounding after the updates; make them exact again (changes u by ~1 ulp)
-    for (int p = lane; p < w.ns; p += w.t.nt) {
-        const int sx = w.face[3 * p], sy = w.face[3 * p + 1], sz = w.face[3 * p + 2];
-        double* up = w.u + 3 * w.fo[p];
-        if (sz < 0) { up[0] = up[1] = up[2] = 0.0; continue; }
-        if (sz > 0) up[2] = w.fmax[p];
-        if (sx != 0) up[0] = sx * cs.mu * up[2];
-        if (sy != 0) up[1] = sy * cs.mu * up[2];
-    }
-    team::sync(w.t);
-    return rmax;
-}
-
 // ---------------------------------------------------------------------------------------------
 // face tests of a primal-dual round: the faces every offending foot should move to are written to face2 (all feet, so
 // that commit_faces() can adopt them without evaluating the tests a second time); returns the violation counts.
@@ -997,20 +1242,22 @@ MPCQ_DEV void commit_faces(Work<T>& w) {
     team::sync(w.t);
 }
 
+// tol_p, tol_d: relative tolerances; tol_d_abs caps the multiplier threshold (a wrong-signed multiplier eps hides a force
+// error of eps / (2 min R): the final test must not accept more than the force accuracy allows)
 template <class T>
-MPCQ_DEV FaceCheck pdas_update(const Consts& cs, Work<T>& w) {
+MPCQ_DEV FaceCheck pdas_update(const Consts& cs, Work<T>& w, double tol_p, double tol_d, double tol_d_abs) {
     MPCQ_PHASE(7);
     const int lane = w.t.tid;
     const double mu = cs.mu;
     int npv = 0, ndv = 0;
     for (int p = lane; p < w.ns; p += w.t.nt) {
-        const double* f = w.u + 3 * w.fo[p];
-        const double* ga = w.gam + 3 * w.fo[p];
+        const double* f = w.u + 3 * p;
+        const double* ga = w.gam + 3 * p;
         const double fm = w.fmax[p];
         int sx = w.face[3 * p], sy = w.face[3 * p + 1], sz = w.face[3 * p + 2];
-        const double gs = 1.0 + dmax(dabs(ga[0]), dmax(dabs(ga[1]), dabs(ga[2])));
+        const double td = dmin(tol_d * (1.0 + dmax(dabs(ga[0]), dmax(dabs(ga[1]), dabs(ga[2])))), tol_d_abs);
         if (sz < 0) {
-            if (ga[2] - mu * (dabs(ga[0]) + dabs(ga[1])) < -cs.tol_d * gs) {
+            if (ga[2] - mu * (dabs(ga[0]) + dabs(ga[1])) < -td) {
                 ++ndv;
                 sx = ga[0] > 0 ? -1 : (ga[0] < 0 ? 1 : 0);
                 sy = ga[1] > 0 ? -1 : (ga[1] < 0 ? 1 : 0);
@@ -1018,7 +1265,7 @@ MPCQ_DEV FaceCheck pdas_update(const Consts& cs, Work<T>& w) {
             }
         } else {
             const double sc = 1.0 + dmax(dabs(f[0]), dmax(dabs(f[1]), dabs(f[2])));
-            const double tp = cs.tol_p * sc;
+            const double tp = tol_p * sc;
             bool pv = false;
             int nsx = sx, nsy = sy, nsz = sz;
             if (f[2] < -tp) { nsz = -1; pv = true; }
@@ -1037,9 +1284,9 @@ MPCQ_DEV FaceCheck pdas_update(const Consts& cs, Work<T>& w) {
                 const double lx = sx != 0 ? -sx * ga[0] : 0.0;
                 const double ly = sy != 0 ? -sy * ga[1] : 0.0;
                 bool dv = false;
-                if (sx != 0 && lx < -cs.tol_d * gs) { nsx = 0; dv = true; }
-                if (sy != 0 && ly < -cs.tol_d * gs) { nsy = 0; dv = true; }
-                if (sz > 0 && (-ga[2] + mu * (lx + ly)) < -cs.tol_d * gs) { nsz = 0; dv = true; }
+                if (sx != 0 && lx < -td) { nsx = 0; dv = true; }
+                if (sy != 0 && ly < -td) { nsy = 0; dv = true; }
+                if (sz > 0 && (-ga[2] + mu * (lx + ly)) < -td) { nsz = 0; dv = true; }
                 if (dv) ++ndv;
             }
             sx = nsx; sy = nsy; sz = nsz;
@@ -1053,82 +1300,6 @@ MPCQ_DEV FaceCheck pdas_update(const Consts& cs, Work<T>& w) {
     return fc;
 }
 
-// Stable partition of the stance list: foot-steps whose face is the one the current factor was built for
-// stay in front (same relative order), the changed ones move to the back.  The leading principal block of
-// K = Z'HZ - and therefore the leading columns of its Cholesky factor - is then unchanged, so the
-// factorisation restarts at the first changed column instead of column 0.  Returns that column (multiple of 4).
-template <class T, int NFS>
-MPCQ_DEV int reorder_feet(Work<T>& w) {
-    MPCQ_PHASE(8);
-    const int lane = wp::lane();
-    const int ns = w.ns;
-    unsigned balc[NFS];
-    int fc[NFS], ff[NFS], fkv[NFS], fov[NFS];
-    double fm[NFS];
-    int n_changed = 0, first_changed = ns;
-    MPCQ_UNROLL
-    for (int t = 0; t < NFS; ++t) {
-        const int p = lane + 32 * t;
-        const bool valid = p < ns;
-        fc[t] = valid ? ((w.face[3 * p] & 0xff) | ((w.face[3 * p + 1] & 0xff) << 8) | ((w.face[3 * p + 2] & 0xff) << 16)) : 0;
-        ff[t] = valid ? ((w.facef[3 * p] & 0xff) | ((w.facef[3 * p + 1] & 0xff) << 8) | ((w.facef[3 * p + 2] & 0xff) << 16)) : 0;
-        fkv[t] = valid ? w.fk[p] : 0;
-        fov[t] = valid ? w.fo[p] : 0;
-        fm[t] = valid ? w.fmax[p] : 0.0;
-        balc[t] = wp::ballot(valid && fc[t] != ff[t]);
-        if (balc[t] != 0u && first_changed == ns) {
-            int b = 0;
-            while (!((balc[t] >> b) & 1u)) ++b;
-            first_changed = 32 * t + b;
-        }
-        n_changed += wp::popc(balc[t]);
-    }
-#if defined(MPCQ_HOST_EMU) && defined(MPCQ_TRACE)
-    if (lane == 0) { printf("   changed steps:"); for (int t = 0; t < NFS; ++t) for (int bb = 0; bb < 32; ++bb) if ((balc[t] >> bb) & 1u) printf(" %d", w.fk[32 * t + bb] >> 2); printf("\n"); }
-#endif
-    if (n_changed == 0) return w.n;
-    const int n_unchanged = ns - n_changed;
-    wp::sync();
-    int cb_base = 0;
-    MPCQ_UNROLL
-    for (int t = 0; t < NFS; ++t) {
-        const int p = lane + 32 * t;
-        if (p < ns) {
-            const int cb = cb_base + wp::popc(balc[t] & ((1u << lane) - 1u));
-            const bool changed = (balc[t] >> lane) & 1u;
-            const int q = changed ? n_unchanged + cb : p - cb;
-            w.fk[q] = (uint8_t)fkv[t];
-            w.fo[q] = (uint8_t)fov[t];
-            w.fmax[q] = fm[t];
-            w.face[3 * q] = (int8_t)(fc[t] & 0xff); w.face[3 * q + 1] = (int8_t)((fc[t] >> 8) & 0xff); w.face[3 * q + 2] = (int8_t)((fc[t] >> 16) & 0xff);
-            w.facef[3 * q] = (int8_t)(fc[t] & 0xff); w.facef[3 * q + 1] = (int8_t)((fc[t] >> 8) & 0xff); w.facef[3 * q + 2] = (int8_t)((fc[t] >> 16) & 0xff);
-        }
-        cb_base += wp::popc(balc[t]);
-    }
-    wp::sync();
-    return (3 * first_changed) & ~3;
-}
-
-// one factor-and-solve on the current faces: u = argmin on the faces (to tol), gam = Hu+g
-template <class T, int NCAP, int NW>
-MPCQ_DEV bool face_solve(const Consts& cs, Work<T>& w, double tol_abs, double& rmax, bool use_cg, bool same_factor) {
-    constexpr int NFS = (NCAP / 3 + 31) / 32;
-    bool ok = true, cnz = true;
-    if (!same_factor) {
-    int k_start = 0;
-    if (w.t.wid == 0) k_start = reorder_feet<T, NFS>(w);        // one warp permutes the stance list ...
-    k_start = team::bcast(w.t, k_start);                           // ... and the team learns the restart column
-#if defined(MPCQ_HOST_EMU) && defined(MPCQ_TRACE)
-    if (w.t.tid == 0) printf("   face_solve: k_start %d of n %d\n", k_start, w.n);
-#endif
-    cnz = build_slots(cs, w);
-    ok = k_start < w.n ? chol_factor<T, NCAP, NW>(cs, w, k_start) : true;
-    }
-    // same_factor: faces and factor are those of the previous call and u is its solution - only improve it (to a tighter tol)
-    rmax = refine<T, NCAP / 32>(cs, w, tol_abs, !cnz, use_cg);
-    return ok;
-}
-
 // ---------------------------------------------------------------------------------------------
 // fallback: feasible primal active-set method started from the clamped last iterate.
 // The start point and its faces are derived from the point alone: every foot is moved into K and
@@ -1140,8 +1311,8 @@ MPCQ_DEV void clamp_into(const Consts& cs, Work<T>& w, const double* src, double
     for (int idx = lane; idx < w.nv; idx += w.t.nt) dst[idx] = 0.0;
     team::sync(w.t);
     for (int p = lane; p < w.ns; p += w.t.nt) {
-        const double* f = src + 3 * w.fo[p];
-        double* o = dst + 3 * w.fo[p];
+        const double* f = src + 3 * p;
+        double* o = dst + 3 * p;
         const double fm = w.fmax[p];
         const double tp = cs.tol_p * (1.0 + dmax(dabs(f[0]), dmax(dabs(f[1]), dabs(f[2]))));
         int sx = 0, sy = 0, sz = 0;
@@ -1161,23 +1332,6 @@ MPCQ_DEV void clamp_into(const Consts& cs, Work<T>& w, const double* src, double
     team::sync(w.t);
 }
 
-// phi(v) = 1/2 v'Hv + g'v = 1/2 v'(gam + g) for the vector v currently in w.u with w.gam = Hv + g
-template <class T>
-MPCQ_DEV double objective(const Consts& cs, Work<T>& w) {
-    double s = 0.0;
-    for (int idx = w.t.tid; idx < w.nv; idx += w.t.nt) s += w.u[idx] * (w.gam[idx] + w.g[idx]);
-    return 0.5 * team::reduce_sum(w.t, s);
-}
-
-// objective of an arbitrary vector v: 1/2 v'(Hv + g + g); uses hd as scratch
-template <class T>
-MPCQ_DEV double objective_of(const Consts& cs, Work<T>& w, const double* v) {
-    hess_apply(cs, w, v, w.hd, true);
-    double s = 0.0;
-    for (int idx = w.t.tid; idx < w.nv; idx += w.t.nt) s += v[idx] * (w.hd[idx] + w.g[idx]);
-    return 0.5 * team::reduce_sum(w.t, s);
-}
-
 MPCQ_DEV void row_slacks(const double* f, double mu, double fm, double (&s)[6]) {
     s[0] = f[0] + mu * f[2]; s[1] = -f[0] + mu * f[2];
     s[2] = f[1] + mu * f[2]; s[3] = -f[1] + mu * f[2];
@@ -1195,8 +1349,8 @@ MPCQ_DEV void ratio_test(const Consts& cs, Work<T>& w, double& alpha, int& tag) 
     for (int p = lane; p < w.ns; p += w.t.nt) {
         const int sx = w.face[3 * p], sy = w.face[3 * p + 1], sz = w.face[3 * p + 2];
         if (sz < 0) continue;
-        const double* f0 = w.ucur + 3 * w.fo[p];
-        const double* f1 = w.u + 3 * w.fo[p];
+        const double* f0 = w.ucur + 3 * p;
+        const double* f1 = w.u + 3 * p;
         double s0[6], s1[6];
         row_slacks(f0, mu, w.fmax[p], s0);
         row_slacks(f1, mu, w.fmax[p], s1);
@@ -1225,8 +1379,8 @@ MPCQ_DEV void block_all_at_zero(const Consts& cs, Work<T>& w) {
     for (int p = lane; p < w.ns; p += w.t.nt) {
         int sx = w.face[3 * p], sy = w.face[3 * p + 1], sz = w.face[3 * p + 2];
         if (sz < 0) continue;
-        double* f0 = w.ucur + 3 * w.fo[p];
-        const double* f1 = w.u + 3 * w.fo[p];
+        double* f0 = w.ucur + 3 * p;
+        const double* f1 = w.u + 3 * p;
         double s0[6], s1[6];
         row_slacks(f0, mu, w.fmax[p], s0);
         row_slacks(f1, mu, w.fmax[p], s1);
@@ -1268,7 +1422,7 @@ MPCQ_DEV void blocked_step(const Consts& cs, Work<T>& w, double alpha, int tag) 
         int sx = w.face[3 * p], sy = w.face[3 * p + 1], sz = w.face[3 * p + 2];
         const bool apex = (r == 4) || (r == 0 && sx == 1) || (r == 1 && sx == -1) || (r == 2 && sy == 1) || (r == 3 && sy == -1);
         if (r == 0) sx = -1; else if (r == 1) sx = 1; else if (r == 2) sy = -1; else if (r == 3) sy = 1; else if (r == 5) sz = 1;
-        double* f = w.ucur + 3 * w.fo[p];
+        double* f = w.ucur + 3 * p;
         if (apex || !(f[2] > 0.0)) { sz = -1; f[0] = f[1] = f[2] = 0.0; }
         else {                                              // put the point exactly on the new face
             if (sz == 1) f[2] = w.fmax[p];
@@ -1293,7 +1447,6 @@ MPCQ_DEV void solve_env(const Consts& cs, const IO<T>& io, int b, char* smem, T*
     w.t.nt = 32 * NW;
     w.t.wid = NW == 1 ? 0 : (w.t.tid >> 5);
     const int lane = w.t.tid;                                   // thread index within the team
-    constexpr int NSLOT = NCAP / 32;                            // rows per lane when ONE warp sweeps (triangular solves)
     // ---- K3a: stance list from the contact table (ub_fz = gait * fz_max > 0); every warp builds it redundantly
     // (identical values, so the concurrent writes are benign) and therefore knows ns without a broadcast
     const float* gait = io.gait + (size_t)b * 4 * H;
@@ -1311,11 +1464,10 @@ MPCQ_DEV void solve_env(const Consts& cs, const IO<T>& io, int b, char* smem, T*
             if (w.t.wid == 0) {
                 if (k >= 0) w.cidx[k] = (uint8_t)((st && pos < NCAP / 3) ? pos : 255);
                 if (st && pos < NCAP / 3) {
-                    w.fk[pos] = (uint8_t)k; w.fo[pos] = (uint8_t)pos; w.fmax[pos] = fm;
+                    w.fk[pos] = (uint8_t)k; w.fmax[pos] = fm;
                     const int code = io.face_in ? io.face_in[(size_t)b * 4 * H + k] : 0;      // 0 = all free (cold start)
                     w.face[3 * pos] = (int8_t)face_decode(code); w.face[3 * pos + 1] = (int8_t)face_decode(code >> 2);
                     w.face[3 * pos + 2] = (int8_t)face_decode(code >> 4);
-                    w.facef[3 * pos] = 99; w.facef[3 * pos + 1] = 99; w.facef[3 * pos + 2] = 99;
                 }
             }
             ns += wp::popc(bal);
@@ -1325,6 +1477,7 @@ MPCQ_DEV void solve_env(const Consts& cs, const IO<T>& io, int b, char* smem, T*
     w.ns = ns;
     w.nv = 3 * ns;
     w.n = (3 * ns + 3) & ~3;
+    w.q = 0;
     team::sync(w.t);
     int status = 0, nfac = 0, nas = 0;
     double rmax = 0.0, pviol = 0.0;
@@ -1356,90 +1509,223 @@ MPCQ_DEV void solve_env(const Consts& cs, const IO<T>& io, int b, char* smem, T*
         gsc = 1.0 + team::reduce_max(w.t, gsc);
         // the weakest curvature of H is 2 min(R): a reduced gradient r can hide a force error of r / (2 min R)
         const double tol_tight = dmin(cs.tol_r_tight * gsc, cs.tol_r_abs);
-        const double tol_loose = dmax(cs.tol_r_loose * gsc, tol_tight);
         bool numeric_ok = (gsc == gsc) && (gsc < 1e300);
         bool done = false;
         if (!numeric_ok) {                                     // nothing was solved: return zeros, flagged
             for (int idx = lane; idx < w.nv; idx += w.t.nt) w.u[idx] = 0.0;
             team::sync(w.t);
         }
-        // ---- ONE loop drives both methods, so that the factor-and-solve code exists once in the kernel (it is the bulk of
-        // the code and the kernel stalls on instruction fetch when warps run different copies of it):
-        //   PDAS   primal-dual active-set rounds: solve on the current faces (loose tolerance), test every foot, move all
-        //          offending feet at once;
-        //   TIGHT  no violation left: refine on the same factor to the tight tolerance, re-test -> verified, or back to PDAS;
-        //   AS     fallback after pdas_cap rounds - monotone projected active-set method.  Keeps a FEASIBLE iterate ucur
-        //          whose objective strictly decreases: from the face minimiser u either (a) u is feasible -> take it and
-        //          release every wrong-signed multiplier, or (b) the clamped point clamp(u) lowers the objective -> take it
-        //          with the faces it lands on (many rows change at once), or (c) step to the first blocking row (ratio test).
-        enum { M_PDAS = 0, M_TIGHT = 1, M_AS = 2 };
-        int mode = M_PDAS, round = 0;
-        double phi_cur = 0.0;
-        bool need_phi = false;
+        if (numeric_ok) {
+            // ---- ONE factorisation per environment: H on the all-free faces, then P = H^-1 over it.  Warm-start faces wait
+            // in face2 meanwhile (the factor is always that of the full Hessian).
+            for (int idx = lane; idx < 3 * w.ns; idx += w.t.nt) { w.face2[idx] = w.face[idx]; w.face[idx] = 0; }
+            team::sync(w.t);
+            numeric_ok = chol_factor<T, NCAP, NW>(cs, w);
+            invert_factor<T, NCAP, NW>(w);
+            // ---- u0 = -H^-1 g, refined in fp64 through the structured operator (q = 0: the preconditioner is P itself)
+            w.q = 0;
+            for (int idx = lane; idx < w.nv; idx += w.t.nt) w.u[idx] = 0.0;
+            team::sync(w.t);
+        }
+        // Rounds.  A round = the minimiser on the current faces through the Schur complement of the active rows (precision T:
+        // "cheap"), the face tests on it, and - once the cheap tests pass (or always, in EXACT mode) - fp64 refinement on
+        // those faces and the face tests at the tight tolerances.  PDAS moves every offending foot at once; after pdas_cap
+        // rounds (the rounds can cycle) the monotone primal active-set method takes over: feasible iterate ucur, step to
+        // the first blocking row (ratio test), release wrong-signed multipliers only at a feasible face minimiser.
+        //
+        // The refinement (plain residual correction u += P_A r while it gains >= 5x per step, preconditioned conjugate
+        // gradients on the reduced system when it stagnates; operator and residuals in fp64) is part of the same flat state
+        // machine, so that dual_op, hess_apply, reduced_gradient and the face tests each exist ONCE in the kernel: it stalls
+        // on instruction fetch as soon as warps run different copies of the same code.
+        enum { M_PDAS = 0, M_AS = 1 };
+        enum { S_DUAL = 0, S_HESS = 1, S_RFDONE = 2, S_TEST = 3, S_RATIO = 4 };
+        int mode = M_PDAS, round = 0, st = S_HESS;
+        bool exact = false, first = true, ratio_done = false, tight = true, dual_round = false;
+        // refinement state
+        int rf_it = 0, rf_itcg = 0;
+        bool rf_cg = false, rf_skip = true, rf_half = false;     // rf_skip: u = 0, so gam = g; rf_half: the operator was applied to the CG direction
+        double rf_prev = 0.0, rf_rz = 0.0;
+        // u0 is only refined to the loose tolerance: it is exact enough to decide the first faces, and in nine cases out of ten
+        // it is infeasible anyway; a clean first test tightens it before it is accepted
+        double rf_tol = dmax(tol_tight, cs.tol_r_loose * gsc);
+        double* const dcg = w.utrial;
+        const double* hin = w.u;
+        double* hout = w.gam;
         while (numeric_ok && !done) {
-            if (mode == M_AS && need_phi) { phi_cur = objective_of(cs, w, w.ucur); need_phi = false; }
-            const bool tight = mode != M_PDAS;
-            numeric_ok = face_solve<T, NCAP, NW>(cs, w, tight ? tol_tight : tol_loose, rmax, tight, mode == M_TIGHT) && numeric_ok;
-            if (mode != M_TIGHT) ++nfac;
-            if (mode != M_AS) {
-                const FaceCheck fc = pdas_update(cs, w);
-                const bool clean = fc.n_primal == 0 && fc.n_dual == 0;
-                if (clean && mode == M_PDAS) { mode = M_TIGHT; continue; }          // tighten on the same factor (CG), re-test
-                if (clean) {
-                    // verified only with the stationarity residual actually at tolerance (a NaN fails this test)
-                    if (rmax <= 10.0 * tol_tight) done = true; else numeric_ok = false;
-                    break;
-                }
+            if (st == S_DUAL) {
+                numeric_ok = dual_op<T, NCAP, NW>(cs, w, dual_round) && numeric_ok;
+                if (dual_round) {
+                    ++nfac;
 #if defined(MPCQ_HOST_EMU) && defined(MPCQ_TRACE)
-                if (lane == 0) printf(" PDAS round %d: primal %d dual %d rmax %.2e\n", round, fc.n_primal, fc.n_dual, rmax);
+                    if (lane == 0) printf(" round %d mode %d exact %d: q %d ok %d\n", round, mode, (int)exact, w.q, (int)numeric_ok);
 #endif
-                mode = M_PDAS;
-                if (!numeric_ok) break;
-                if (round++ < cs.pdas_cap) { commit_faces(w); continue; }
-                // the rounds cycle: hand over to the monotone method, started from the clamped last iterate (clamp_into
-                // derives the faces from the point)
-                status |= ST_FALLBACK;
-                clamp_into(cs, w, w.u, w.ucur, w.face);
-                mode = M_AS; need_phi = true; nas = 1;
+                    if (!numeric_ok) break;
+                    if (exact) { rf_it = rf_itcg = 0; rf_cg = rf_skip = rf_half = false; rf_prev = rf_rz = 0.0; rf_tol = tol_tight; hin = w.u; hout = w.gam; st = S_HESS; }
+                    else if (mode == M_AS) st = S_RATIO;
+                    else { tight = false; st = S_TEST; }
+                    continue;
+                }
+                // ---- inside the refinement: vec = z = P_A r
+                if (!rf_cg) {
+                    apply_step(cs, w);
+                    ++rf_it;
+                    hin = w.u; hout = w.gam; rf_half = false;
+                    st = S_HESS;
+                    continue;
+                }
+                // rz = r'z (r recomputed from gam in fp64), beta, d = Z z + beta d
+                double part = 0.0;
+                for (int v = lane; v < w.n; v += w.t.nt) {
+                    const int p = v / 3;
+                    if (p < w.ns)
+                        part += slot_residual(w.face[3 * p], w.face[3 * p + 1], w.face[3 * p + 2], v - 3 * p, w.gam + 3 * p, cs.mu) *
+                                (double)w.vec[v];
+                }
+                const double rz_new = team::reduce_sum(w.t, part);
+                const double beta = rf_itcg == 0 ? 0.0 : rz_new / rf_rz;
+                rf_rz = rz_new;
+                if (!(rf_rz > 0.0)) { st = S_RFDONE; continue; }    // converged to rounding (or a broken preconditioner)
+                for (int p = lane; p < w.ns; p += w.t.nt) {
+                    const int sx = w.face[3 * p], sy = w.face[3 * p + 1], sz = w.face[3 * p + 2];
+                    double* dp = dcg + 3 * p;
+                    double z0 = 0.0, z1 = 0.0, z2 = 0.0;
+                    if (sz >= 0) {
+                        const double w0 = (double)w.vec[3 * p], w1 = (double)w.vec[3 * p + 1], w2 = (double)w.vec[3 * p + 2];
+                        if (sz == 0) { z2 = w2; z0 = sx != 0 ? sx * cs.mu * w2 : w0; z1 = sy != 0 ? sy * cs.mu * w2 : w1; }
+                        else { z0 = sx == 0 ? w0 : 0.0; z1 = sy == 0 ? w1 : 0.0; }
+                    }
+                    if (rf_itcg == 0) { dp[0] = z0; dp[1] = z1; dp[2] = z2; }
+                    else { dp[0] = z0 + beta * dp[0]; dp[1] = z1 + beta * dp[1]; dp[2] = z2 + beta * dp[2]; }
+                }
+                team::sync(w.t);
+                hin = dcg; hout = w.hd; rf_half = true;
+                st = S_HESS;
                 continue;
             }
-            // ---- AS iteration nas
-            if (!numeric_ok) break;
-            double alpha;
-            int tag;
-            ratio_test(cs, w, alpha, tag);
-#if defined(MPCQ_HOST_EMU) && defined(MPCQ_TRACE)
-            if (lane == 0) printf("  AS it %d: alpha %.3e tag %d phi_cur %.10e rmax %.2e\n", nas, alpha, tag, phi_cur, rmax);
-#endif
-            if (tag == 0x7fffffff) {                    // (a)
-                for (int idx = lane; idx < w.nv; idx += w.t.nt) w.ucur[idx] = w.u[idx];
-                phi_cur = objective(cs, w);
-                if (!(rmax <= 10.0 * tol_tight)) { numeric_ok = false; break; }   // the factor cannot deliver the residual
-                const FaceCheck fc = pdas_update(cs, w);
-                commit_faces(w);
-#if defined(MPCQ_HOST_EMU) && defined(MPCQ_TRACE)
-                if (lane == 0) printf("     feasible minimiser: primal %d dual %d\n", fc.n_primal, fc.n_dual);
-#endif
-                if (fc.n_primal == 0 && fc.n_dual == 0) { done = true; break; }
-            } else {
-                clamp_into(cs, w, w.u, w.utrial, w.face2);
-                const double phi_t = objective_of(cs, w, w.utrial);
-#if defined(MPCQ_HOST_EMU) && defined(MPCQ_TRACE)
-                if (lane == 0) printf("     trial phi %.10e -> %s\n", phi_t, phi_t < phi_cur - 1e-12 * dabs(phi_cur) ? "accept" : "ratio step");
-#endif
-                if (phi_t < phi_cur - 1e-12 * dabs(phi_cur)) {   // (b)
-                    for (int idx = lane; idx < w.nv; idx += w.t.nt) w.ucur[idx] = w.utrial[idx];
-                    for (int idx = lane; idx < 3 * w.ns; idx += w.t.nt) w.face[idx] = w.face2[idx];
+            if (st == S_HESS) {
+                if (rf_skip) {
+                    for (int idx = lane; idx < w.nv; idx += w.t.nt) w.gam[idx] = w.g[idx];
                     team::sync(w.t);
-                    phi_cur = phi_t;
-                } else if (alpha <= 1e-13) {                // (c0) degenerate: no move possible, fix every such row
-                    block_all_at_zero(cs, w);
-                } else {                                    // (c)
-                    blocked_step(cs, w, alpha, tag);
-                    need_phi = true;
+                    rf_skip = false;
+                } else {
+                    hess_apply(cs, w, hin, hout, !rf_half);
                 }
+                if (rf_half) {                                   // hd = H d: finish the CG step
+                    double part = 0.0;
+                    for (int idx = lane; idx < w.nv; idx += w.t.nt) part += dcg[idx] * w.hd[idx];
+                    const double dHd = team::reduce_sum(w.t, part);
+                    if (!(dHd > 0.0)) { st = S_RFDONE; continue; }
+                    const double alpha = rf_rz / dHd;
+                    for (int idx = lane; idx < w.nv; idx += w.t.nt) {
+                        w.u[idx] += alpha * dcg[idx];
+                        w.gam[idx] += alpha * w.hd[idx];
+                    }
+                    team::sync(w.t);
+                    ++rf_itcg;
+                }
+                rmax = reduced_gradient(cs, w);                      // r = -Z' gam -> vec
+#if defined(MPCQ_HOST_EMU) && defined(MPCQ_TRACE)
+                if (lane == 0) printf("     refine it %d cg %d(%d) rmax %.3e (tol %.3e) q %d\n", rf_it, (int)rf_cg, rf_itcg, rmax, rf_tol, w.q);
+#endif
+                bool fin = false;
+                if (!rf_cg) {
+                    const bool stop = !(rmax > rf_tol && rf_it < cs.refine_max);
+                    if (stop || (rf_it > 0 && rmax > 0.2 * rf_prev)) {   // done, out of steps, or converging too slowly: hand over to CG
+                        if (rmax <= rf_tol) fin = true; else rf_cg = true;
+                    } else {
+                        rf_prev = rmax;
+                    }
+                }
+                if (rf_cg && !(rmax > rf_tol && rf_itcg < cs.refine_max)) fin = true;
+                if (fin) { st = S_RFDONE; continue; }
+                dual_round = false;
+                st = S_DUAL;
+                continue;
             }
-            if (++nas > cs.as_cap) break;
+            if (st == S_RFDONE) {
+                if (rf_cg) {                                     // the face equalities hold to rounding after CG updates; make them exact again
+                    for (int p = lane; p < w.ns; p += w.t.nt) {
+                        const int sx = w.face[3 * p], sy = w.face[3 * p + 1], sz = w.face[3 * p + 2];
+                        double* up = w.u + 3 * p;
+                        if (sz < 0) { up[0] = up[1] = up[2] = 0.0; continue; }
+                        if (sz > 0) up[2] = w.fmax[p];
+                        if (sx != 0) up[0] = sx * cs.mu * up[2];
+                        if (sy != 0) up[1] = sy * cs.mu * up[2];
+                    }
+                    team::sync(w.t);
+                }
+                if (first) {                                     // this was u0 = -H^-1 g
+                    for (int idx = lane; idx < w.nv; idx += w.t.nt) w.u0f[idx] = (T)w.u[idx];
+                    bool any_warm = false;
+                    for (int idx = lane; idx < 3 * w.ns; idx += w.t.nt) any_warm = any_warm || w.face2[idx] != 0;
+                    if (team::any(w.t, any_warm)) {              // start the rounds from the given faces
+                        commit_faces(w);
+                        first = false;
+                        dual_round = true; st = S_DUAL;
+                        continue;
+                    }
+                    if (nfac == 0) ++nfac;
+                }
+                if (mode == M_AS && !ratio_done) { st = S_RATIO; continue; }
+                tight = true;
+                st = S_TEST;
+                continue;
+            }
+            if (st == S_RATIO) {
+                double alpha;
+                int tag;
+                ratio_test(cs, w, alpha, tag);
+                if (tag != 0x7fffffff) {
+                    if (alpha <= 1e-13) block_all_at_zero(cs, w);      // degenerate: no move possible, fix every such row
+                    else blocked_step(cs, w, alpha, tag);
+                    if (++nas > cs.as_cap) break;
+                    dual_round = true; st = S_DUAL;
+                    continue;
+                }
+                for (int idx = lane; idx < w.nv; idx += w.t.nt) w.ucur[idx] = w.u[idx];   // feasible face minimiser
+                team::sync(w.t);
+                ratio_done = true;
+                tight = exact;
+                st = S_TEST;
+                continue;
+            }
+            // ---- S_TEST
+            const FaceCheck fc = pdas_update(cs, w, tight ? cs.tol_p : cs.tol_pc, tight ? cs.tol_d : cs.tol_dc, tight ? cs.tol_r_abs : 1e300);
+            const bool clean = fc.n_primal == 0 && fc.n_dual == 0;
+#if defined(MPCQ_HOST_EMU) && defined(MPCQ_TRACE)
+            if (lane == 0) printf("   tests: primal %d dual %d tight %d rmax %.2e\n", fc.n_primal, fc.n_dual, (int)tight, rmax);
+#endif
+            if (clean) {
+                if (!tight) {                                   // refine on these faces, then the tight tests
+                    rf_it = rf_itcg = 0; rf_cg = rf_skip = rf_half = false; rf_prev = rf_rz = 0.0; rf_tol = tol_tight; hin = w.u; hout = w.gam;
+                    st = S_HESS;
+                    continue;
+                }
+                // verified only with the stationarity residual actually at tolerance (a NaN fails this test)
+                if (rmax <= 10.0 * tol_tight) { done = true; break; }
+                if (first && rf_tol > tol_tight) {               // the unconstrained minimiser is feasible: tighten it, test again
+                    rf_it = rf_itcg = 0; rf_cg = rf_skip = rf_half = false; rf_prev = rf_rz = 0.0; rf_tol = tol_tight; hin = w.u; hout = w.gam;
+                    st = S_HESS;
+                    continue;
+                }
+                numeric_ok = false;
+                break;
+            }
+            if (tight && !first) exact = true;                  // the cheap tests were too optimistic: decide in fp64 from now on
+            first = false;
+            commit_faces(w);
+            if (mode == M_PDAS) {
+                if (round++ >= cs.pdas_cap) {                   // the rounds cycle: hand over to the monotone method
+                    status |= ST_FALLBACK;
+                    clamp_into(cs, w, w.u, w.ucur, w.face);
+                    mode = M_AS; nas = 1;
+                }
+            } else if (++nas > cs.as_cap) {
+                break;
+            }
+            ratio_done = false;
+            dual_round = true;
+            st = S_DUAL;
         }
         if (mode == M_AS && !done && numeric_ok) {          // iteration cap: return the feasible iterate
             for (int idx = lane; idx < w.nv; idx += w.t.nt) w.u[idx] = w.ucur[idx];

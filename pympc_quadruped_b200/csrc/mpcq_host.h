@@ -27,7 +27,8 @@ struct SizeClass { int ncap, ns_lo, ns_hi, nw; };      // nw = warps of the team
 #ifndef MPCQ_NW3
 #define MPCQ_NW3 2
 #endif
-static const SizeClass kClasses[4] = {{64, 0, 20, MPCQ_NW0}, {128, 21, 42, MPCQ_NW1}, {192, 43, 64, MPCQ_NW2}, {384, 65, 128, MPCQ_NW3}};
+static const SizeClass kClasses[4] = {{64, 0, class_ns_hi(64), MPCQ_NW0}, {128, class_ns_hi(64) + 1, class_ns_hi(128), MPCQ_NW1},
+                                      {192, class_ns_hi(128) + 1, class_ns_hi(192), MPCQ_NW2}, {384, class_ns_hi(192) + 1, class_ns_hi(384), MPCQ_NW3}};
 inline int class_nmax(const SizeClass& c) { return (3 * c.ns_hi + 3) & ~3; }   // rows of the largest system in the class
 
 inline int num_classes(int horizon) {
@@ -46,7 +47,7 @@ inline bool consts_from_config(const mpcq_config& c, Consts& k, std::string& err
         if (!(c.q_diag[i] >= 0)) { err = "q_diag must be >= 0"; return false; }
     const bool f64 = c.dtype == MPCQ_F64;
     k.horizon = c.horizon;
-    k.pdas_cap = c.max_pdas_rounds > 0 ? c.max_pdas_rounds : 8;
+    k.pdas_cap = c.max_pdas_rounds > 0 ? c.max_pdas_rounds : 14;
     k.as_cap = c.max_as_iter > 0 ? c.max_as_iter : 12 * c.horizon + 30;
     k.refine_max = c.max_refine > 0 ? c.max_refine : 20;
     k.dt = c.dt; k.mu = c.mu; k.fz_max = c.fz_max;
@@ -56,6 +57,8 @@ inline bool consts_from_config(const mpcq_config& c, Consts& k, std::string& err
     for (int i = 0; i < 12; ++i) k.r[i] = c.r_diag[i];
     k.tol_p = c.tol_primal > 0 ? c.tol_primal : (f64 ? 1e-9 : 1e-7);
     k.tol_d = c.tol_dual > 0 ? c.tol_dual : (f64 ? 1e-9 : 1e-7);
+    k.tol_pc = f64 ? k.tol_p : (k.tol_p > 1e-5 ? k.tol_p : 1e-5);
+    k.tol_dc = f64 ? k.tol_d : (k.tol_d > 1e-5 ? k.tol_d : 1e-5);
     k.tol_r_tight = c.tol_residual > 0 ? c.tol_residual : (f64 ? 1e-12 : 1e-9);
     k.tol_r_loose = c.tol_residual_loose > 0 ? c.tol_residual_loose : (f64 ? 1e-9 : 1e-6);
     if (k.tol_r_loose < k.tol_r_tight) k.tol_r_loose = k.tol_r_tight;

@@ -5,7 +5,7 @@ from helpers import make_batch
 from pympc_quadruped_b200 import *
 from pympc_quadruped_b200 import _capi
 from pympc_quadruped_b200.engine import MpcqEngine
-names=['setup_model','hess_apply','build_slots','chol_factor','tri_solve','reduced_gradient','apply_step','pdas_update','reorder_feet','solve_env(total)','  chol: assembly','  chol: update loop','  chol: diag block','  chol: panel solve + cw']
+names=['setup_model','hess_apply','build_slots','chol_factor','invert_factor','reduced_gradient','apply_step','pdas_update','refine (incl.)','solve_env(total)','  schur_factor','dual_round (incl.)','dual_apply (incl.)','  schur_solve','  dual_combine']
 bt=make_batch(A1Config,10,4096,'mixed',(Gait.TROTTING10,),9,solve=False)
 eng=MpcqEngine(bt['cfg'],A1Config)
 lib=_capi.load_library()
@@ -18,10 +18,11 @@ def probe(idx,label):
     idx=torch.as_tensor(idx,device='cuda:0'); a=[x[idx].contiguous() for x in X]
     eng.solve(a[0],a[1],a[2],a[3],yaw=a[4]); lib.mpcq_debug_phase_cycles(buf)
     eng.solve(a[0],a[1],a[2],a[3],yaw=a[4]); lib.mpcq_debug_phase_cycles(buf)
-    v=np.array(list(buf)[:14],dtype=float); rounds=it[idx.cpu().numpy()].sum()
+    v=np.array(list(buf)[:15],dtype=float); rounds=it[idx.cpu().numpy()].sum()
     tot=v[9]
-    print(f'--- {label}: envs {len(idx)} rounds {rounds}  total {tot/rounds:.0f} cycles/round')
-    for n,c in zip(names,v): print(f'   {n:18s} {c/rounds:9.0f} cycles/round  {100*c/tot:5.1f}%')
+    ne=len(idx)
+    print(f'--- {label}: envs {ne} rounds {rounds}  total {tot/ne:.0f} cycles/env')
+    for n,c in zip(names,v): print(f'   {n:20s} {c/ne:9.0f} cycles/env  {100*c/tot:5.1f}%')
 sel=np.flatnonzero(it==6)[:1]
 probe(sel,'one env alone (6 rounds)')
 probe(np.arange(4096),'B=4096 under load')
