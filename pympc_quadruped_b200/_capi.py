@@ -120,6 +120,10 @@ def load_library() -> C.CDLL:
     """Load libmpcq.so or fail loudly (the engine has no fallback path)."""
     global _lib
     if _lib is None:
+        path = os.environ.get("MPCQ_LIB_PATH", LIB_PATH)       # development: another build of the same library (A/B experiments)
+        if path != LIB_PATH:
+            _lib = bind(C.CDLL(path))
+            return _lib
         if not os.path.exists(LIB_PATH):
             raise RuntimeError(
                 f"{LIB_PATH} is missing: the CUDA engine is not built (run __graft_entry__.build()). "

@@ -10,7 +10,7 @@ import subprocess
 import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-OUT = os.path.join(HERE, "_build", "libmpcq.so")
+OUT = os.path.join(HERE, "_build", os.environ.get("MPCQ_OUT", "libmpcq.so"))   # MPCQ_OUT: experiment builds beside the product
 SOURCES = ["mpcq_api.cu", "mpcq_probe.cu"]
 DEPS = SOURCES + ["mpcq_core.cuh", "mpcq_legs.cuh", "mpcq_warp.cuh", "mpcq_host.h", os.path.join("..", "..", "include", "mpcq.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

@@ -33,7 +33,7 @@ template <int NCAP> struct TeamWarps { static constexpr int value = NCAP <= 64 ?
 // path (model, factorisation, inversion - no data-dependent control flow there), so the SM's instruction caches serve one
 // copy of it instead of one per resident warp (measured: the kernel stalls on instruction fetch, profiles/r02_*).
 #ifndef MPCQ_EPC0
-#define MPCQ_EPC0 4
+#define MPCQ_EPC0 8
 #endif
 template <int NCAP> struct EnvsPerCta { static constexpr int value = TeamWarps<NCAP>::value == 1 ? MPCQ_EPC0 : 1; };
 

@@ -117,13 +117,12 @@ template <class T> struct Work {
     double *Md, *GW, *g, *u, *gam, *P0, *P1, *ucur, *utrial, *hd, *fmax, *zero3;
     double *hs, *hq, *rd;  // hess_apply tables: stage-1 scales [9], stage-2 scales [12], diag(R) [12]
     // precision T
-    T *L, *dblk, *vec, *cw, *zt, *Mf, *r2;   // r2 = 2 * diag(R) in precision T
+    T *L, *dblk, *vec, *cw, *Mf, *r2;        // Mf = (M00, M11) pairs; r2 = 2 * diag(R) in precision T
     T *NS2;                // [H][H][2]: (2 N_ij, 2 S_ij) pairs for the Hessian assembly
     T *stage;              // [4 n] column block of L, transposed, while P = H^-1 is formed
     T *u0f;                // unconstrained minimiser -H^-1 g (precision T)
     T *tv;                 // scratch vector of dual_apply
     T *lam;                // right-hand side / multipliers of the active rows
-    T *sinv;               // inverse pivots of the Schur factor
     T *rcf;                // active row i:  u[rc1[i]] + rcf[i] * u[rc2[i]] = b_i
     uint16_t *rc1, *rc2;
     uint16_t *rbase;       // first active row of stance foot-step p
@@ -149,8 +148,8 @@ MPCQ_HD constexpr Layout layout(int H, int ncap, bool l_in_smem, bool with_md, i
     l.cw = nw > 1 ? 256 : 128;
     const size_t nv = (size_t)l.nvc;
     l.nd = (with_md ? 288 : 0) + 72 + 9 * (size_t)H + 12 * (size_t)H + 6 * nv + nv / 3 + 1 + 12 + 40;
-    l.nt = (l_in_smem ? (size_t)ps_elems(l.nvc) : 0) + 3 * nv + nv + (size_t)l.cw + 3 * nv + 288 + 12 + ((2 * (size_t)H * H + 3) & ~(size_t)3) +
-           4 * nv + 2 * nv + 3 * (nv + 4);
+    l.nt = (l_in_smem ? (size_t)ps_elems(l.nvc) : 0) + 3 * nv + nv + (size_t)l.cw + 288 + 12 + ((2 * (size_t)H * H + 3) & ~(size_t)3) +
+           4 * nv + 2 * nv + 2 * (nv + 4);
     l.nb = (nv / 3 + 1) * 8 + 4 * (size_t)H + 16 + 4 * nv + 2 * 2 * (nv + 4) + 2 * (nv / 3 + 2) + 16;
     return l;
 }
@@ -192,7 +191,6 @@ MPCQ_DEV void carve(Work<T>& w, char* base, T* l_global, int H, int ncap, bool w
     w.dblk = t; t += 3 * nv;     // 12 values per block of 4 columns
     w.vec = t; t += nv;
     w.cw = t; t += l.cw;
-    w.zt = t; t += 3 * nv;
     w.Mf = t; t += 288;
     w.r2 = t; t += 12;
     w.NS2 = t; t += (2 * H * H + 3) & ~3;
@@ -200,7 +198,6 @@ MPCQ_DEV void carve(Work<T>& w, char* base, T* l_global, int H, int ncap, bool w
     w.u0f = t; t += nv;
     w.tv = t; t += nv;
     w.lam = t; t += nv + 4;
-    w.sinv = t; t += nv + 4;
     w.rcf = t; t += nv + 4;
     uint8_t* b = reinterpret_cast<uint8_t*>(base + align_up(l.nd * 8, 16) + align_up(l.nt * sizeof(T), 16));
     w.fk = b; b += nv / 3 + 1;
@@ -291,7 +288,9 @@ MPCQ_DEV void setup_model(const Consts& cs, Work<T>& w, const T* x0p, double yaw
     const int lane = w.t.tid;
     const int H = cs.horizon;
     // --- Rz (float32-rounded like the reference), world inertia, its inverse: every lane, redundantly
-    const double c = (double)(float)cos(yaw), s = (double)(float)sin(yaw);
+    double sy_, cy_;
+    sincos(yaw, &sy_, &cy_);
+    const double c = (double)(float)cy_, s = (double)(float)sy_;
     const double Rz[9] = {c, -s, 0, s, c, 0, 0, 0, 1};
     double RI[9], WI[9];
     MPCQ_UNROLL
@@ -356,14 +355,18 @@ MPCQ_DEV void setup_model(const Consts& cs, Work<T>& w, const T* x0p, double yaw
         w.hq[lane] = 0.5 * ((lane >= 3 && lane < 6) ? cs.q[6 + lane] : (lane >= 9 ? cs.q[lane - 6] : 1.0));   // 1/2: NS2 holds 2N, 2S
     }
     if (lane < 4) w.zero3[lane] = 0.0;
-    // --- horizon table S
-    for (int idx = lane; idx < H * H; idx += w.t.nt) {
-        const int i = idx / H, j = idx - i * H;
-        const int m = i > j ? i : j;
-        const double a = m - i + 0.5, b = m - j + 0.5, Ln = H - m;
-        const double sv = Ln * a * b + (a + b) * Ln * (Ln - 1) * 0.5 + (Ln - 1) * Ln * (2 * Ln - 1) / 6.0;
-        w.NS2[2 * idx] = (T)(2.0 * Ln);                     // 2 N_ij
-        w.NS2[2 * idx + 1] = (T)(2.0 * sv);                 // 2 S_ij: multiples of 1/2 below 2^18, exact in float
+    // --- horizon table (2 N_ij, 2 S_ij): small integers and halves, exact in float; idx / H by multiply-shift (idx < 1024)
+    {
+        const int rcp = (65536 + H - 1) / H;
+        for (int idx = lane; idx < H * H; idx += w.t.nt) {
+            const int i = (idx * rcp) >> 16, j = idx - i * H;
+            const int m = i > j ? i : j;
+            const float a = (float)(m - i) + 0.5f, b = (float)(m - j) + 0.5f, Ln = (float)(H - m);
+            // sum_{k=0}^{Ln-1} (a + k)(b + k) = Ln a b + (a + b) Ln (Ln - 1) / 2 + (Ln - 1) Ln (2 Ln - 1) / 6
+            const float sv = Ln * a * b + (a + b) * (Ln * (Ln - 1.0f) * 0.5f) + (float)(((H - m - 1) * (H - m) * (2 * (H - m) - 1)) / 6);
+            w.NS2[2 * idx] = (T)(2.0f * Ln);                    // 2 N_ij
+            w.NS2[2 * idx + 1] = (T)(2.0f * sv);                // 2 S_ij: multiples of 1/2 below 2^18, exact in float
+        }
     }
     team::sync(w.t);
     // --- M00 = B0'QB0, M11 = B1'QB1
@@ -753,6 +756,7 @@ MPCQ_DEV void invert_factor(Work<T>& w) {
         {
             const T* pc = P + (size_t)(j0 + 4) * ld + tid;
             const T* sg = stage + 4 * (j0 + 4);
+            MPCQ_UNROLL2                                         // two groups in flight: the loads of one hide behind the other's multiply-adds
             for (int k = j0 + 4; k < n; k += 4) {
                 MPCQ_UNROLL
                 for (int t = 0; t < 4; ++t) {
@@ -921,10 +925,20 @@ MPCQ_DEV bool schur_factor(Work<T>& w) {
         if (i < q) {
             const int c1 = w.rc1[i], c2 = w.rc2[i];
             const T cf = w.rcf[i];
-            for (int j = 0; j <= i; ++j) {
-                const int c1j = w.rc1[j], c2j = w.rc2[j];
-                const T cfj = w.rcf[j];
-                rp[m][j] = (psym(P, ld, c1, c1j) + cfj * psym(P, ld, c1, c2j)) + cf * (psym(P, ld, c2, c1j) + cfj * psym(P, ld, c2, c2j));
+            // 4 entries per pass: all loads first, then the stores (the compiler cannot move a load of P across a store to
+            // the Schur block - same array - so entry by entry every pass would wait out the shared-memory latency)
+            for (int j0 = 0; j0 <= i; j0 += 4) {
+                T e[4];
+                MPCQ_UNROLL
+                for (int t = 0; t < 4; ++t) {
+                    const int j = j0 + t < q ? j0 + t : q - 1;
+                    const int c1j = w.rc1[j], c2j = w.rc2[j];
+                    const T cfj = w.rcf[j];
+                    e[t] = (psym(P, ld, c1, c1j) + cfj * psym(P, ld, c1, c2j)) + cf * (psym(P, ld, c2, c1j) + cfj * psym(P, ld, c2, c2j));
+                }
+                MPCQ_UNROLL
+                for (int t = 0; t < 4; ++t)
+                    if (j0 + t <= i) rp[m][j0 + t] = e[t];
             }
         } else if (i < q4) {
             for (int j = 0; j < i; ++j) rp[m][j] = (T)0;

@@ -16,6 +16,7 @@
 #define MPCQ_DEV inline
 #define MPCQ_HD inline
 #define MPCQ_UNROLL
+#define MPCQ_UNROLL2
 #define MPCQ_NOUNROLL
 namespace mpcq_emu {
 int lane_id();                            // lane within the warp
@@ -28,6 +29,7 @@ void team_barrier();                      // all threads of the team
 #define MPCQ_DEV __device__ __forceinline__
 #define MPCQ_HD __host__ __device__ inline
 #define MPCQ_UNROLL _Pragma("unroll")
+#define MPCQ_UNROLL2 _Pragma("unroll 2")
 #define MPCQ_NOUNROLL _Pragma("unroll 1")
 #endif
 
