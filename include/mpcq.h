@@ -223,6 +223,26 @@ int mpcq_solve_host(mpcq_handle* h, int32_t B,
                     void* f_out, void* u_full, int32_t* iters, double* resid, int32_t* status, uint8_t* active);
 
 /*
+ * One MPC update from HOST state: for B robots, the body of the simulator loop up to the forces -
+ * Gait.set_iteration + get_gait_table (linear_mpc/gait.py:76-100), ModelPredictiveController.update_robot_state
+ * (mpc.py:55-79) and update_mpc_if_needed on an MPC tick (:81-108), i.e. scripts/isaacgym_a1.py:119-144 without the
+ * per-robot Python loop.  Only the RobotData fields cross the bus (272 B per robot instead of the 784 B of assembled
+ * state + reference trajectory + contact table that mpcq_solve_host takes); the gait schedule, state assembly,
+ * reference trajectory and the solve run on the device (mpcq_gait_tables + mpcq_assemble + mpcq_solve kernels).
+ *   state_cmd   [B,29] float64 host: quat (w,x,y,z) 4 | pos_base 3 | ang_vel_base 3 | lin_vel_base 3 (world) |
+ *               pos_base_feet 12 (world-frame base->foot, FL FR RL RR) | v_des_body 3 | yaw_rate_des
+ *   gait_params [B,10] int32 host: stance_offsets 4 | stance_durations 4 | num_segment | cur_iteration (control tick)
+ *   first_run != 0: desired pose initialised from the state as mpc.py:84-88
+ *   f_out [B,12] `real` host, status [B] int32 host or NULL; page-locked buffers are read by DMA / written in place.
+ * The controller state of mpc.py (x/y/yaw desired, roll/pitch compensation integrators) is kept per robot inside the
+ * handle between calls (slot i = robot i; a larger B than before re-allocates and zeroes it; mpcq_tick_reset zeroes it).
+ * Returns after the results are in the caller's buffers.
+ */
+int mpcq_tick_host(mpcq_handle* h, int32_t B, const double* state_cmd, const int32_t* gait_params,
+                   int32_t iterations_between_mpc, int32_t first_run, void* f_out, int32_t* status);
+int mpcq_tick_reset(mpcq_handle* h);
+
+/*
  * Stage entry point for parity tests: the QP data the reference would hand to the solver.
  *   H_out [B,12H,12H] (_generate_QP_cost :232), g_out [B,12H] (:233), ub_out [B,20H] (:248-258;
  *   lb is identically 0 and C = kron(I_4H, pyramid(mu)) is constant).  Always float64; +inf in

@@ -127,6 +127,7 @@ def _polish(H, g, A, b, act):
 
 
 def solve_qp_exact(H, g, mu, ub_fz, kkt_tol=1e-8, feas_tol=1e-9, max_rounds=60) -> QPSolution:
+    mu = float(np.float32(mu))                               # the reference's C is float32 (mpc.py:239-245)
     H = np.asarray(H, dtype=np.float64)
     g = np.asarray(g, dtype=np.float64)
     ub_fz = np.asarray(ub_fz, dtype=np.float64)
@@ -220,6 +221,7 @@ def kkt_report(H, g, mu, ub_fz, u, tol_active=1e-6):
     """Independent KKT check of a candidate u against (H, g, constraints): returns
     (stationarity residual after a per-foot NNLS multiplier fit, primal violation,
     active_lower[20H], active_upper[20H]) with activity decided on primal slack."""
+    mu = float(np.float32(mu))                               # the reference's C is float32 (mpc.py:239-245)
     H = np.asarray(H, dtype=np.float64)
     u = np.asarray(u, dtype=np.float64)
     nfeet = len(ub_fz)

@@ -61,30 +61,12 @@ class BatchedRobotData:
         return cls(quat, pos, rs[:, 10:13].contiguous(), rs[:, 7:10].contiguous(), pos_base_feet.contiguous())
 
 
-def quat_to_matrix(q: torch.Tensor) -> torch.Tensor:
-    """(w,x,y,z) -> R_base, batched (utils/kinematics.py:51-71)."""
-    w, x, y, z = q.unbind(-1)
-    R = torch.stack([
-        w * w + x * x - y * y - z * z, 2 * (x * y - w * z), 2 * (w * y + x * z),
-        2 * (w * z + x * y), w * w - x * x + y * y - z * z, 2 * (y * z - w * x),
-        2 * (x * z - w * y), 2 * (w * x + y * z), w * w - x * x - y * y + z * z], dim=-1)
-    return R.reshape(q.shape[:-1] + (3, 3))
-
-
-def quat_to_zyx(q: torch.Tensor) -> torch.Tensor:
-    """(w,x,y,z) -> [roll, pitch, yaw] float64 (utils/kinematics.py:40-49)."""
-    w, x, y, z = q.unbind(-1)
-    roll = torch.atan2(2 * (w * x + y * z), 1 - 2 * (x * x + y * y))
-    pitch = torch.asin(2 * (w * y - z * x))
-    yaw = torch.atan2(2 * (w * z + x * y), 1 - 2 * (y * y + z * z))
-    return torch.stack([roll, pitch, yaw], dim=-1)
-
-
 class BatchedModelPredictiveController:
     def __init__(self, mpc_config, robot_config, num_envs: int, device="cuda:0", dtype=torch.float32, engine=None,
-                 fused=None, warm_start=False, **solver_knobs):
-        """`engine` is for dependency injection in tests (an object with MpcqEngine.solve's signature);
-        by default the CUDA engine is created and a missing GPU / library raises.
+                 warm_start=False, **solver_knobs):
+        """`engine` is for dependency injection in tests (an object with MpcqEngine's solve / assemble signatures);
+        by default the CUDA engine is created and a missing GPU / library raises.  State assembly, command integration
+        and the reference trajectory always run in the device kernel (`mpcq_assemble`): there is no second backend.
         `warm_start`: start every MPC update from the previous update's active faces shifted by one horizon step
         (`mpcq_set_warm_start`); the optimum is unique, so only the number of active-set rounds changes."""
         c = extract_mpc_constants(mpc_config, robot_config)
@@ -107,16 +89,15 @@ class BatchedModelPredictiveController:
         f64 = dict(dtype=torch.float64, device=dev)
         self.is_initialized = False
         self.is_first_run = True
-        # the fused device path (mpcq_assemble) is used whenever the engine offers it; the torch statement of the same
-        # arithmetic below serves engines without it (the test double) and as the readable specification
-        self._fused = hasattr(self.engine, "assemble") if fused is None else bool(fused)
-        self.current_state = torch.zeros((B, 13), dtype=dtype if self._fused else torch.float32, device=dev)
-        self.yaw = torch.zeros(B, dtype=dtype if self._fused else torch.float64, device=dev)
+        if not hasattr(self.engine, "assemble"):
+            raise TypeError("the engine must provide assemble() (mpcq_assemble): the controller has no host-side fallback")
+        self.current_state = torch.zeros((B, 13), dtype=dtype, device=dev)
+        self.yaw = torch.zeros(B, dtype=dtype, device=dev)
         self._xy_des = torch.zeros((B, 2), **f64)
         self._rp_init = torch.zeros((B, 2), **f64)             # roll_init, pitch_init
         self.yaw_desired = torch.zeros(B, **f64)
         self.contact_forces = torch.zeros((B, 12), dtype=dtype, device=dev)
-        self.ref_traj = torch.zeros((B, 13 * self.horizon), dtype=dtype if self._fused else torch.float32, device=dev)
+        self.ref_traj = torch.zeros((B, 13 * self.horizon), dtype=dtype, device=dev)
         self.last_result = None
         self.warm_start = bool(warm_start)
         self._faces = torch.zeros((B, 4 * self.horizon), dtype=torch.uint8, device=dev) if self.warm_start else None
@@ -144,15 +125,7 @@ class BatchedModelPredictiveController:
         self.pos_base_feet = self._t(robot_data.pos_base_feet, (B, 12))
         R = getattr(robot_data, "R_base", None)
         self._R_given = None if R is None else self._t(R, (B, 3, 3)).contiguous()
-        self.is_initialized = True
-        if self._fused:
-            return                                              # assembled on the device inside update_mpc_if_needed
-        rpy = quat_to_zyx(self._quat)
-        st = torch.cat([rpy, self._pos, self._omega, self._vel,
-                        torch.full((B, 1), -self.gravity, dtype=torch.float64, device=self.device)], dim=1)
-        self.current_state = st.to(torch.float32)
-        self.yaw = rpy[:, 2].clone()
-        self.R_base = quat_to_matrix(self._quat) if self._R_given is None else self._R_given
+        self.is_initialized = True                              # assembled on the device inside update_mpc_if_needed
 
     def update_mpc_if_needed(self, iter_counter: int, base_vel_base_des, yaw_turn_rate_des, gait_table,
                              solver: str = "drake", debug: bool = False, iter_debug=None):
@@ -166,62 +139,13 @@ class BatchedModelPredictiveController:
         v_body = self._t(base_vel_base_des, (-1, 3)).expand(B, 3)
         yaw_rate = self._t(yaw_turn_rate_des, (-1,)).expand(B)
         do_mpc = iter_counter % self.iterations_between_mpc == 0
-        if self._fused:
-            self.engine.assemble(self._quat, self._pos, self._omega, self._vel, v_body.contiguous(), yaw_rate.contiguous(),
-                                 self._xy_des, self.yaw_desired, self._rp_init, self.is_first_run, do_mpc,
-                                 self.current_state, self.yaw, self.ref_traj, R_base=self._R_given)
-            self.is_first_run = False
-            if do_mpc:
-                self.contact_forces = self._solve_mpc(self.ref_traj, gait_table)
-            return self.contact_forces
-        vel_des = torch.einsum("bij,bj->bi", self.R_base, v_body)
-        if self.is_first_run:
-            self._xy_des.zero_()
-            self.yaw_desired = self.yaw.clone()
-            self.is_first_run = False
-        else:
-            self._xy_des[:, 0] += self.dt_control * vel_des[:, 0]
-            self._xy_des[:, 1] += self.dt_control * vel_des[:, 1]
-            self.yaw_desired = self.yaw + self.dt_control * yaw_rate
+        self.engine.assemble(self._quat, self._pos, self._omega, self._vel, v_body.contiguous(), yaw_rate.contiguous(),
+                             self._xy_des, self.yaw_desired, self._rp_init, self.is_first_run, do_mpc,
+                             self.current_state, self.yaw, self.ref_traj, R_base=self._R_given)
+        self.is_first_run = False
         if do_mpc:
-            self.ref_traj = self.generate_reference_trajectory(vel_des, yaw_rate)
             self.contact_forces = self._solve_mpc(self.ref_traj, gait_table)
         return self.contact_forces
-
-    def generate_reference_trajectory(self, vel_des: torch.Tensor, yaw_rate: torch.Tensor) -> torch.Tensor:
-        """mpc.py:110-170 with its float32 storage / float64 scalar arithmetic reproduced."""
-        x = self.current_state.to(torch.float64)            # float32 values (torch path only)
-        H, n, B = self.horizon, 13, self.num_envs
-        lim = 0.1
-        xd, yd = self._xy_des[:, 0].clone(), self._xy_des[:, 1].clone()
-        xd = torch.where(xd - x[:, 3] > lim, x[:, 3] + lim, xd)
-        xd = torch.where(x[:, 3] - xd > lim, x[:, 3] - lim, xd)
-        yd = torch.where(yd - x[:, 4] > lim, x[:, 4] + lim, yd)
-        yd = torch.where(x[:, 4] - yd > lim, x[:, 4] - lim, yd)
-        self._xy_des[:, 0], self._xy_des[:, 1] = xd, yd
-        safe = lambda v: torch.where(v == 0, torch.ones_like(v), v)
-        pitch_init = torch.where(x[:, 9].abs() > 0.2, self._rp_init[:, 1] + self.dt * (0.0 - x[:, 1]) / safe(x[:, 9]),
-                                 self._rp_init[:, 1])
-        roll_init = torch.where(x[:, 10].abs() > 0.1, self._rp_init[:, 0] + self.dt * (0.0 - x[:, 0]) / safe(x[:, 10]),
-                                self._rp_init[:, 0])
-        self._rp_init[:, 0] = roll_init.clamp(-0.25, 0.25)
-        self._rp_init[:, 1] = pitch_init.clamp(-0.25, 0.25)
-        X = torch.zeros((B, H, n), dtype=torch.float32, device=self.device)
-        X[:, :, 0] = (x[:, 10] * self._rp_init[:, 0]).to(torch.float32)[:, None]
-        X[:, :, 1] = (x[:, 9] * self._rp_init[:, 1]).to(torch.float32)[:, None]
-        X[:, :, 5] = self.com_height_des
-        X[:, :, 8] = yaw_rate.to(torch.float32)[:, None]
-        X[:, :, 9] = vel_des[:, 0].to(torch.float32)[:, None]
-        X[:, :, 10] = vel_des[:, 1].to(torch.float32)[:, None]
-        X[:, :, 12] = -self.gravity
-        X[:, 0, 2] = self.yaw_desired.to(torch.float32)
-        X[:, 0, 3] = xd.to(torch.float32)
-        X[:, 0, 4] = yd.to(torch.float32)
-        for i in range(1, H):                                # float32 storage, float64 increments
-            X[:, i, 2] = (X[:, i - 1, 2].to(torch.float64) + self.dt * yaw_rate).to(torch.float32)
-            X[:, i, 3] = (X[:, i - 1, 3].to(torch.float64) + self.dt * vel_des[:, 0]).to(torch.float32)
-            X[:, i, 4] = (X[:, i - 1, 4].to(torch.float64) + self.dt * vel_des[:, 1]).to(torch.float32)
-        return X.reshape(B, n * H)
 
     def _solve_mpc(self, ref_traj: torch.Tensor, gait_table) -> torch.Tensor:
         B, H = self.num_envs, self.horizon

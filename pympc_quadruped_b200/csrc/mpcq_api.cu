@@ -366,6 +366,28 @@ mpcq_assemble_kernel(const __grid_constant__ AssembleArgs a, T* x0, T* yaw_out, 
     if (valid) { a.xy_des[2 * b] = xd; a.xy_des[2 * b + 1] = yd; a.yaw_des[b] = yawd; }
 }
 
+// mpcq_tick_host: the packed per-robot rows a host loop hands over, split into the arrays the gait / assembly / solve kernels
+// take (one thread per robot; 272 B in per robot)
+struct TickArrays {
+    double *quat, *pos, *omega, *vel, *vdes, *yawrate;          // [B,4] [B,3] [B,3] [B,3] [B,3] [B]
+    int32_t *offs, *durs, *seg, *iter;                          // [B,4] [B,4] [B] [B]
+};
+template <typename T>
+__global__ void __launch_bounds__(128)
+mpcq_tick_unpack_kernel(int B, const double* __restrict__ state_cmd, const int32_t* __restrict__ gait_params, TickArrays a, T* feet) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    const double* s = state_cmd + (size_t)b * 29;
+    for (int i = 0; i < 4; ++i) a.quat[4 * b + i] = s[i];
+    for (int i = 0; i < 3; ++i) { a.pos[3 * b + i] = s[4 + i]; a.omega[3 * b + i] = s[7 + i]; a.vel[3 * b + i] = s[10 + i]; a.vdes[3 * b + i] = s[25 + i]; }
+    for (int i = 0; i < 12; ++i) feet[(size_t)12 * b + i] = (T)s[13 + i];
+    a.yawrate[b] = s[28];
+    const int32_t* g = gait_params + (size_t)b * 10;
+    for (int i = 0; i < 4; ++i) { a.offs[4 * b + i] = g[i]; a.durs[4 * b + i] = g[4 + i]; }
+    a.seg[b] = g[8];
+    a.iter[b] = g[9];
+}
+
 }  // namespace
 
 struct mpcq_handle {
@@ -384,7 +406,12 @@ struct mpcq_handle {
     char* dev = nullptr;
     size_t stage_cap = 0;
     cudaStream_t streams[4] = {nullptr, nullptr, nullptr, nullptr};
-    std::unordered_map<const void*, bool> pinned_cache;   // caller buffer -> page-locked?
+    std::unordered_map<const void*, size_t> pinned_cache; // caller buffer -> bytes verified page-locked from that address (0 = pageable)
+    // mpcq_tick_host: device arrays for `tick_cap` robots; the controller state (desired xy / yaw, roll / pitch compensation)
+    // persists between calls
+    char* tick_dev = nullptr;
+    double* tick_state = nullptr;        // [cap,5]: xy_des 2 | yaw_des | rp_init 2
+    size_t tick_cap = 0;
     // measurement hooks
     bool profiling = false;
     cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -659,6 +686,8 @@ void mpcq_destroy(mpcq_handle* h) {
     if (h->cta_hist) cudaFree(h->cta_hist);
     if (h->dev) cudaFree(h->dev);
     if (h->pin) cudaFreeHost(h->pin);
+    if (h->tick_dev) cudaFree(h->tick_dev);
+    if (h->tick_state) cudaFree(h->tick_state);
     delete h;
 }
 
@@ -827,6 +856,22 @@ int mpcq_leg_torques(mpcq_handle* h, int32_t B, const mpcq_leg_params* lp, const
     return cuda_ok(h, cudaGetLastError(), "mpcq_leg_torques launch") ? MPCQ_OK : MPCQ_ERR_CUDA;
 }
 
+// Is [p, p + bytes) page-locked host memory?  The driver query costs 1-2 us per pointer, so the verified extent is remembered
+// per address; first and last byte are both checked (a buffer registered only in part must go through the staging copy:
+// the kernels would otherwise write through a device alias beyond the mapped range).
+static bool host_range_pinned(mpcq_handle* h, const void* p, size_t bytes) {
+    if (!p || !bytes) return false;
+    auto it = h->pinned_cache.find(p);
+    if (it != h->pinned_cache.end() && (it->second == 0 || it->second >= bytes)) return it->second != 0;
+    cudaPointerAttributes a0, a1;
+    bool pin = cudaPointerGetAttributes(&a0, p) == cudaSuccess && a0.type == cudaMemoryTypeHost;
+    if (pin) pin = cudaPointerGetAttributes(&a1, static_cast<const char*>(p) + bytes - 1) == cudaSuccess && a1.type == cudaMemoryTypeHost;
+    cudaGetLastError();
+    if (it != h->pinned_cache.end()) it->second = pin ? bytes : 0;
+    else if (h->pinned_cache.size() < 4096) h->pinned_cache.emplace(p, pin ? bytes : 0);
+    return pin;
+}
+
 int mpcq_solve_host(mpcq_handle* h, int32_t B, const void* x0, const void* yaw, const void* r_feet, const float* gait,
                     const void* x_ref, void* f_out, void* u_full, int32_t* iters, double* resid, int32_t* status,
                     uint8_t* active) {
@@ -860,18 +905,7 @@ int mpcq_solve_host(mpcq_handle* h, int32_t B, const void* x0, const void* yaw, 
     bool pinned[11];
     for (int i = 0; i < 11; ++i) {
         const void* p = i < 5 ? src[i] : dst[i - 5];
-        pinned[i] = false;
-        if (p && width[i]) {
-            // the driver query costs 1-2 us per pointer; remember the answer per address.  A stale answer is harmless: a
-            // pageable buffer taken for page-locked is still copied correctly by cudaMemcpyAsync (synchronously), a page-locked
-            // one taken for pageable merely goes through the staging copy.
-            auto it = h->pinned_cache.find(p);
-            if (it != h->pinned_cache.end()) { pinned[i] = it->second; continue; }
-            cudaPointerAttributes at;
-            if (cudaPointerGetAttributes(&at, p) == cudaSuccess) pinned[i] = at.type == cudaMemoryTypeHost;
-            else cudaGetLastError();
-            if (h->pinned_cache.size() < 4096) h->pinned_cache.emplace(p, pinned[i]);
-        }
+        pinned[i] = (p && width[i]) ? host_range_pinned(h, p, b * width[i]) : false;
     }
     // the batch is cut into chunks, each on its own stream: H2D(c+1) overlaps solve(c) overlaps D2H(c-1), and the
     // kernels of neighbouring chunks fill each other's tails.  A class whose factor lives in the shared global
@@ -894,6 +928,8 @@ int mpcq_solve_host(mpcq_handle* h, int32_t B, const void* x0, const void* yaw, 
     }
     char* d = h->dev;
     int launches = 0;
+    // on a failure in mid-loop the copies and kernels already queued still use the caller's buffers: wait for them before returning
+    auto fail = [&](int code) { for (int i = 0; i < kHostStreams; ++i) cudaStreamSynchronize(h->streams[i]); return code; };
     // Results that go to page-locked caller buffers are written there by the kernels themselves (mapped host memory: a few
     // posted PCIe writes per environment when it finishes) instead of being staged on the device and copied behind the kernel.
     char* zdst[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -914,7 +950,7 @@ int mpcq_solve_host(mpcq_handle* h, int32_t B, const void* x0, const void* yaw, 
                 memcpy(h->pin + off[i] + lo * width[i], from, nb * width[i]);
                 from = h->pin + off[i] + lo * width[i];
             }
-            if (!cuda_ok(h, cudaMemcpyAsync(d + off[i] + lo * width[i], from, nb * width[i], cudaMemcpyHostToDevice, st), "H2D")) return MPCQ_ERR_CUDA;
+            if (!cuda_ok(h, cudaMemcpyAsync(d + off[i] + lo * width[i], from, nb * width[i], cudaMemcpyHostToDevice, st), "H2D")) return fail(MPCQ_ERR_CUDA);
         }
         auto dp = [&](int i) -> char* {
             if (!width[i]) return nullptr;
@@ -923,12 +959,12 @@ int mpcq_solve_host(mpcq_handle* h, int32_t B, const void* x0, const void* yaw, 
         const int rc = solve_impl(h, (int32_t)nb, dp(0), dp(1), dp(2), reinterpret_cast<float*>(dp(3)), dp(4), dp(5), dp(6),
                                   reinterpret_cast<int32_t*>(dp(7)), reinterpret_cast<double*>(dp(8)),
                                   reinterpret_cast<int32_t*>(dp(9)), reinterpret_cast<uint8_t*>(dp(10)), 1, lo, st, c % kHostStreams);
-        if (rc != MPCQ_OK) return rc;
+        if (rc != MPCQ_OK) return fail(rc);
         launches += h->last_launches;
         for (int i = 5; i < 11; ++i) {
             if (!width[i] || zdst[i - 5]) continue;
             char* to = pinned[i] ? static_cast<char*>(dst[i - 5]) + lo * width[i] : h->pin + off[i] + lo * width[i];
-            if (!cuda_ok(h, cudaMemcpyAsync(to, d + off[i] + lo * width[i], nb * width[i], cudaMemcpyDeviceToHost, st), "D2H")) return MPCQ_ERR_CUDA;
+            if (!cuda_ok(h, cudaMemcpyAsync(to, d + off[i] + lo * width[i], nb * width[i], cudaMemcpyDeviceToHost, st), "D2H")) return fail(MPCQ_ERR_CUDA);
         }
     }
     for (int c = 0; c < nchunk && c < kHostStreams; ++c)
@@ -937,6 +973,120 @@ int mpcq_solve_host(mpcq_handle* h, int32_t B, const void* x0, const void* yaw, 
         if (width[i] && !pinned[i]) memcpy(dst[i - 5], h->pin + off[i], b * width[i]);
     h->last_launches = launches;
     return MPCQ_OK;
+}
+
+int mpcq_tick_host(mpcq_handle* h, int32_t B, const double* state_cmd, const int32_t* gait_params, int32_t iterations_between_mpc,
+                   int32_t first_run, void* f_out, int32_t* status) {
+    if (!h) return MPCQ_ERR_INVALID;
+    if (B < 0 || iterations_between_mpc < 1 || (B > 0 && (!state_cmd || !gait_params || !f_out))) {
+        h->err = "mpcq_tick_host: null pointer or iterations_between_mpc < 1";
+        return MPCQ_ERR_INVALID;
+    }
+    h->last_launches = 0;
+    if (B == 0) return MPCQ_OK;
+    DeviceGuard guard(h->cfg.device);
+    const size_t rs = h->real_size, H = (size_t)h->cs.horizon, b = (size_t)B;
+    cudaStream_t st = h->streams[0];
+    // device layout (256-byte aligned sections): packed inputs | unpacked arrays | x0, yaw, x_ref, gait table, feet | results
+    const size_t width[16] = {29 * 8, 10 * 4,                              // state_cmd, gait_params
+                              4 * 8, 3 * 8, 3 * 8, 3 * 8, 3 * 8, 8,        // quat pos omega vel vdes yawrate
+                              16, 16, 4, 4,                                // offs durs seg iter
+                              (13 + 1 + 12 + 13 * H) * rs + 16 * H,        // x0 | yaw | feet | x_ref | table (sub-sections below)
+                              12 * rs, 4, 0};                              // f_out, status
+    size_t off[17], cur = 0;
+    for (int i = 0; i < 16; ++i) { off[i] = cur; cur += (b * width[i] + 255) / 256 * 256 + (i == 12 ? 5 * 256 : 0); }
+    off[16] = cur;
+    if (b > h->tick_cap) {
+        cudaStreamSynchronize(st);
+        if (h->tick_dev) cudaFree(h->tick_dev);
+        if (h->tick_state) cudaFree(h->tick_state);
+        h->tick_dev = nullptr; h->tick_state = nullptr; h->tick_cap = 0;
+        if (!cuda_ok(h, cudaMalloc(&h->tick_dev, cur), "cudaMalloc tick")) return MPCQ_ERR_CUDA;
+        if (!cuda_ok(h, cudaMalloc(&h->tick_state, b * 5 * sizeof(double)), "cudaMalloc tick state")) return MPCQ_ERR_CUDA;
+        if (!cuda_ok(h, cudaMemsetAsync(h->tick_state, 0, b * 5 * sizeof(double), st), "memset tick state")) return MPCQ_ERR_CUDA;
+        h->tick_cap = b;
+    }
+    {
+        const int rcp = ensure_perm(h, 1, b);
+        if (rcp != MPCQ_OK) return rcp;
+    }
+    char* d = h->tick_dev;
+    auto al = [](size_t x) { return (x + 255) / 256 * 256; };
+    // page-locked caller buffers are DMA sources / are written in place by the kernels; pageable ones go through staging
+    const size_t need_pin = al(b * width[0]) + al(b * width[1]) + al(b * width[13]) + al(b * width[14]);
+    if (need_pin > h->stage_cap) {
+        for (int i = 0; i < kHostStreams; ++i) cudaStreamSynchronize(h->streams[i]);
+        if (h->dev) cudaFree(h->dev);
+        if (h->pin) cudaFreeHost(h->pin);
+        h->dev = h->pin = nullptr; h->stage_cap = 0;
+        if (!cuda_ok(h, cudaMalloc(&h->dev, need_pin), "cudaMalloc staging")) return MPCQ_ERR_CUDA;
+        if (!cuda_ok(h, cudaMallocHost(&h->pin, need_pin), "cudaMallocHost staging")) return MPCQ_ERR_CUDA;
+        h->stage_cap = need_pin;
+    }
+    const void* src[2] = {state_cmd, gait_params};
+    size_t poff = 0;
+    for (int i = 0; i < 2; ++i) {
+        const void* from = src[i];
+        if (!host_range_pinned(h, from, b * width[i])) { memcpy(h->pin + poff, from, b * width[i]); from = h->pin + poff; }
+        poff += al(b * width[i]);
+        if (!cuda_ok(h, cudaMemcpyAsync(d + off[i], from, b * width[i], cudaMemcpyHostToDevice, st), "H2D")) return MPCQ_ERR_CUDA;
+    }
+    TickArrays ta{reinterpret_cast<double*>(d + off[2]), reinterpret_cast<double*>(d + off[3]), reinterpret_cast<double*>(d + off[4]),
+                  reinterpret_cast<double*>(d + off[5]), reinterpret_cast<double*>(d + off[6]), reinterpret_cast<double*>(d + off[7]),
+                  reinterpret_cast<int32_t*>(d + off[8]), reinterpret_cast<int32_t*>(d + off[9]), reinterpret_cast<int32_t*>(d + off[10]),
+                  reinterpret_cast<int32_t*>(d + off[11])};
+    char* x0 = d + off[12];
+    char* yaw = x0 + al(b * 13 * rs);
+    char* feet = yaw + al(b * rs);
+    char* xref = feet + al(b * 12 * rs);
+    float* table = reinterpret_cast<float*>(xref + al(b * 13 * H * rs));
+    const int grid = (B + 127) / 128;
+    const double* sc = reinterpret_cast<const double*>(d + off[0]);
+    const int32_t* gp = reinterpret_cast<const int32_t*>(d + off[1]);
+    if (h->cfg.dtype == MPCQ_F64) mpcq_tick_unpack_kernel<double><<<grid, 128, 0, st>>>(B, sc, gp, ta, reinterpret_cast<double*>(feet));
+    else mpcq_tick_unpack_kernel<float><<<grid, 128, 0, st>>>(B, sc, gp, ta, reinterpret_cast<float*>(feet));
+    GaitArgs ga{ta.offs, ta.durs, ta.seg, ta.iter, iterations_between_mpc, B, h->cs.horizon};
+    mpcq_gait_kernel<<<grid, 128, 0, st>>>(ga, table, nullptr, nullptr);
+    double* cst = h->tick_state;
+    AssembleArgs aa{ta.quat, ta.pos, ta.omega, ta.vel, nullptr, ta.vdes, ta.yawrate, cst, cst + 2 * b, cst + 3 * b, first_run, 1, B,
+                    h->cs.horizon, h->cfg.dt_control, h->cfg.dt, h->cfg.com_height_des, h->cfg.gravity};
+    if (h->cfg.dtype == MPCQ_F64)
+        mpcq_assemble_kernel<double><<<grid, 128, 0, st>>>(aa, reinterpret_cast<double*>(x0), reinterpret_cast<double*>(yaw), reinterpret_cast<double*>(xref));
+    else
+        mpcq_assemble_kernel<float><<<grid, 128, 0, st>>>(aa, reinterpret_cast<float*>(x0), reinterpret_cast<float*>(yaw), reinterpret_cast<float*>(xref));
+    if (!cuda_ok(h, cudaGetLastError(), "mpcq_tick_host launch")) return MPCQ_ERR_CUDA;
+    // results: in place into page-locked caller buffers, else staged
+    void* dst[2] = {f_out, status};
+    char* dres[2] = {d + off[13], d + off[14]};
+    bool direct[2] = {false, false};
+    for (int i = 0; i < 2; ++i) {
+        if (!dst[i] || !h->direct_results || !host_range_pinned(h, dst[i], b * width[13 + i])) continue;
+        void* dptr = nullptr;
+        if (cudaHostGetDevicePointer(&dptr, dst[i], 0) == cudaSuccess) { dres[i] = static_cast<char*>(dptr); direct[i] = true; }
+        else cudaGetLastError();
+    }
+    const int rc = solve_impl(h, B, x0, yaw, feet, table, xref, dres[0], nullptr, nullptr, nullptr,
+                              status ? reinterpret_cast<int32_t*>(dres[1]) : nullptr, nullptr, 1, 0, st, 0);
+    if (rc != MPCQ_OK) { cudaStreamSynchronize(st); return rc; }
+    const int launches = h->last_launches + 3;
+    char* pres = h->pin + al(b * width[0]) + al(b * width[1]);
+    for (int i = 0; i < 2; ++i) {
+        if (!dst[i] || direct[i]) continue;
+        char* to = host_range_pinned(h, dst[i], b * width[13 + i]) ? static_cast<char*>(dst[i]) : pres + (i ? al(b * width[13]) : 0);
+        if (!cuda_ok(h, cudaMemcpyAsync(to, dres[i], b * width[13 + i], cudaMemcpyDeviceToHost, st), "D2H")) { cudaStreamSynchronize(st); return MPCQ_ERR_CUDA; }
+    }
+    if (!cuda_ok(h, cudaStreamSynchronize(st), "mpcq_tick_host sync")) return MPCQ_ERR_CUDA;
+    for (int i = 0; i < 2; ++i)
+        if (dst[i] && !direct[i] && !host_range_pinned(h, dst[i], b * width[13 + i])) memcpy(dst[i], pres + (i ? al(b * width[13]) : 0), b * width[13 + i]);
+    h->last_launches = launches;
+    return MPCQ_OK;
+}
+
+int mpcq_tick_reset(mpcq_handle* h) {
+    if (!h) return MPCQ_ERR_INVALID;
+    if (!h->tick_state) return MPCQ_OK;
+    DeviceGuard guard(h->cfg.device);
+    return cuda_ok(h, cudaMemset(h->tick_state, 0, h->tick_cap * 5 * sizeof(double)), "mpcq_tick_reset") ? MPCQ_OK : MPCQ_ERR_CUDA;
 }
 
 int mpcq_last_launch_count(const mpcq_handle* h) { return h ? h->last_launches : 0; }

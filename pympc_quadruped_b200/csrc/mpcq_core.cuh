@@ -1471,7 +1471,7 @@ MPCQ_DEV void solve_env(const Consts& cs, const IO<T>& io, int b, char* smem, T*
         // volatile foot-steps end up at the back of the factor and re-factorisations restart late (reorder_feet).
         for (int k0 = 0; k0 < 4 * H; k0 += 32) {
             const int k = 4 * H - 1 - (k0 + wl);
-            const double fm = k >= 0 ? (double)gait[k] * cs.fz_max : 0.0;
+            const double fm = k >= 0 ? (double)(float)((double)gait[k] * cs.fz_max) : 0.0;   // float32 like the reference's ub (mpc.py:248-258)
             const bool st = fm > 0.0;
             const unsigned bal = wp::ballot(st);
             const int pos = ns + wp::popc(bal & ((1u << wl) - 1u));
@@ -1757,7 +1757,7 @@ MPCQ_DEV void solve_env(const Consts& cs, const IO<T>& io, int b, char* smem, T*
         const int sidx = w.cidx[k];
         double f[3] = {0.0, 0.0, 0.0};
         if (sidx != 255) { f[0] = w.u[3 * sidx]; f[1] = w.u[3 * sidx + 1]; f[2] = w.u[3 * sidx + 2]; }
-        const double fm = dmax((double)gait[k] * cs.fz_max, 0.0);
+        const double fm = dmax((double)(float)((double)gait[k] * cs.fz_max), 0.0);
         const double sc = 1.0 + dmax(dabs(f[0]), dmax(dabs(f[1]), dabs(f[2])));
         double s[6];
         row_slacks(f, mu, fm, s);

@@ -50,7 +50,8 @@ inline bool consts_from_config(const mpcq_config& c, Consts& k, std::string& err
     k.pdas_cap = c.max_pdas_rounds > 0 ? c.max_pdas_rounds : 14;
     k.as_cap = c.max_as_iter > 0 ? c.max_as_iter : 12 * c.horizon + 30;
     k.refine_max = c.max_refine > 0 ? c.max_refine : 20;
-    k.dt = c.dt; k.mu = c.mu; k.fz_max = c.fz_max;
+    // the reference builds the friction pyramid in float32 (mpc.py:239-245): its solver sees float32(mu); fz_max * gait likewise
+    k.dt = c.dt; k.mu = (double)(float)c.mu; k.fz_max = c.fz_max;
     k.inv_mass = (double)(float)(1.0 / c.mass);            // Bc[9:12] = I/m is stored in float32 (mpc.py:190)
     for (int i = 0; i < 9; ++i) k.inertia[i] = c.inertia[i];
     for (int i = 0; i < 13; ++i) k.q[i] = c.q_diag[i];

@@ -213,8 +213,12 @@ MPCQ_DEV void reduce_argmin(const Ctx& c, double& v, int& tag) {
     wp::team_sync();
     double rv = c.red[0];
     int rt = c.redi[0];
-    for (int i = 1; i < (c.nt >> 5); ++i)
-        if (c.red[i] < rv || (c.red[i] == rv && c.redi[i] < rt)) { rv = c.red[i]; rt = c.redi[i]; }
+    for (int i = 1; i < (c.nt >> 5); ++i) {                  // same order as wp::reduce_argmin: a NaN wins (it must be noticed)
+        const double ov = c.red[i];
+        const int ot = c.redi[i];
+        const bool o_nan = ov != ov, v_nan = rv != rv;
+        if ((o_nan && !v_nan) || (o_nan == v_nan && (ov < rv || ((ov == rv || o_nan) && ot < rt)))) { rv = ov; rt = ot; }
+    }
     wp::team_sync();
     v = rv;
     tag = rt;

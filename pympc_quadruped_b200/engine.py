@@ -146,6 +146,40 @@ class MpcqEngine:
         self._err(rc, "mpcq_solve_host")
         return res
 
+    def tick_host(self, state_cmd, gait_params, iterations_between_mpc: int, first_run: bool = False, out=None):
+        """One MPC update of B robots from HOST state through `mpcq_tick_host`: `state_cmd` [B,29] float64
+        (quat 4 | pos 3 | omega 3 | vel 3 | pos_base_feet 12 | v_des_body 3 | yaw_rate), `gait_params` [B,10] int32
+        (stance_offsets 4 | stance_durations 4 | num_segment | cur_iteration).  Gait table, state assembly, reference
+        trajectory and the solve run on the device; the controller's integrator state lives in the handle.
+        Returns dict(forces [B,12], status [B]) as numpy arrays (`out` may hold preallocated, e.g. page-locked, ones)."""
+        rt = np.float64 if self.dtype == torch.float64 else np.float32
+        state_cmd = np.ascontiguousarray(state_cmd, dtype=np.float64)
+        B = state_cmd.shape[0]
+        if state_cmd.shape != (B, 29):
+            raise ValueError(f"state_cmd must be [B,29], got {state_cmd.shape}")
+        gait_params = np.ascontiguousarray(gait_params, dtype=np.int32)
+        if gait_params.shape != (B, 10):
+            raise ValueError(f"gait_params must be [B,10], got {gait_params.shape}")
+        if np.any(gait_params[:, 8] < 1):
+            raise ValueError("num_segment must be >= 1")
+        res = {}
+        for key, shape, dt in (("forces", (B, 12), rt), ("status", (B,), np.int32)):
+            if out is not None and key in out:
+                a = out[key]
+                if a.shape != shape or a.dtype != dt or not a.flags["C_CONTIGUOUS"]:
+                    raise ValueError(f"out[{key!r}] must be a C-contiguous {dt} array of shape {shape}")
+                res[key] = a
+            else:
+                res[key] = np.empty(shape, dt)
+        p = lambda a: a.ctypes.data_as(C.c_void_p)
+        rc = self.lib.mpcq_tick_host(self._h, B, p(state_cmd), p(gait_params), int(iterations_between_mpc), int(bool(first_run)),
+                                     p(res["forces"]), p(res["status"]))
+        self._err(rc, "mpcq_tick_host")
+        return res
+
+    def tick_reset(self):
+        self._err(self.lib.mpcq_tick_reset(self._h), "mpcq_tick_reset")
+
     def build_qp(self, x0, r_feet, gait, x_ref, yaw=None):
         """Dense (H [B,n,n], g [B,n], ub [B,20H]) in float64 - the data the reference hands to its solver."""
         B, H = x0.shape[0], self.horizon

@@ -8,6 +8,7 @@ from oracle import mpc_oracle as mo
 from oracle.qp_exact import solve_qp_exact
 from pympc_quadruped_b200.configs import extract_mpc_constants
 from pympc_quadruped_b200.engine import SolveResult
+from torch_statement import assemble_statement
 
 
 class OracleEngine:
@@ -19,6 +20,9 @@ class OracleEngine:
         self.Qbar = np.kron(np.identity(H), np.diag(self.c["q_diag"]))
         self.Rbar = np.kron(np.identity(H), np.diag(self.c["r_diag"]))
         self.calls = 0
+
+    def assemble(self, *a, **k):
+        assemble_statement(self.c, *a, **k)
 
     def solve(self, x0, r_feet, gait, x_ref, yaw=None, want=(), out=None):
         self.calls += 1

@@ -103,7 +103,7 @@ def test_solve_matches_oracle(name, robot, H, B, regime, gaits, dtype, seed):
         # shows up as a ~1e-5 stationarity residual on ~50 N forces
         Hm, g, ub = batch["qps"][b]
         stat, prim, _, _ = kkt_report(Hm, g, 0.7, ub[4::5], u[b])
-        assert prim <= (1e-9 if dtype == torch.float64 else 1e-5)      # f32: output rounding of ~50 N forces
+        assert prim <= (1e-9 if dtype == torch.float64 else 2e-7 * (1.0 + np.abs(u[b]).max()))   # f32: output rounding (float ulp of the forces)
         assert stat <= 5e-5 * (1.0 + np.abs(g).max())
         if dtype == torch.float64:                                     # KKT <= 1e-6 on the engine's own QP data
             stat, prim, _, _ = kkt_report(Hdev[b], gdev[b], 0.7, ub[4::5], u[b])
@@ -292,9 +292,11 @@ def test_fused_assembly_equals_torch_statement_and_reference_sequence():
     cfg = with_horizon(H)
     st = synth_states(B, A1Config, "mixed", seed=61)
     for dtype in (torch.float32, torch.float64):
+        from torch_statement import StatementEngine
+        from pympc_quadruped_b200.configs import extract_mpc_constants
         fused = BatchedModelPredictiveController(cfg, A1Config, B, dtype=dtype)
-        plain = BatchedModelPredictiveController(cfg, A1Config, B, dtype=dtype, fused=False)
-        assert fused._fused and not plain._fused
+        plain = BatchedModelPredictiveController(cfg, A1Config, B, dtype=dtype,
+                                                 engine=StatementEngine(fused.engine, extract_mpc_constants(cfg, A1Config)))
         for tick in (0, 1, 2, 20, 21, 40):
             s = 1.0 + 0.002 * tick
             rd = BatchedRobotData(st["quat_base"], st["pos_base"] * s, st["ang_vel_base"], st["lin_vel_base"] * s, st["pos_base_feet"],

@@ -1,0 +1,292 @@
+"""GPU parity, second round: activity on the engine's own QP, whole BASELINE batches against the oracle, the host tick entry
+point, the largest size class in fp32, the default horizon through the B = 1 adapter, the 262 144-robot batch, BASELINE
+configs[0] (1 000 consecutive updates of one robot) and the Isaac Gym tensor glue on device tensors."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import make_batch, oracle_pool_solve
+from oracle.qp_exact import solve_qp_exact
+from pympc_quadruped_b200 import A1Config, AliengoConfig, Gait, _capi, with_horizon
+from pympc_quadruped_b200.synth import GAIT_MIX, synth_gait_params, synth_states
+
+pytestmark = pytest.mark.gpu
+
+ABS_TOL, REL_TOL = 1e-3, 1e-4
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def _engine(cfg, robot, dtype, **kw):
+    from pympc_quadruped_b200.engine import MpcqEngine
+    return MpcqEngine(cfg, robot, dtype=dtype, device="cuda:0", **kw)
+
+
+def _to_dev(batch, dtype):
+    t = lambda a, dt: torch.as_tensor(a).to(device="cuda:0", dtype=dt)
+    return (t(batch["x0"], dtype), t(batch["feet"], dtype), t(batch["gait"], torch.float32), t(batch["xref"], dtype), t(batch["yaw"], dtype))
+
+
+def _activity(active_row, H):
+    lo = ((active_row[:, None] >> np.arange(5)[None, :]) & 1).astype(bool).reshape(-1)
+    up = np.zeros(20 * H, dtype=bool)
+    up[4::5] = (active_row >> 5) & 1
+    return lo, up
+
+
+@pytest.mark.parametrize("robot,H,B,regime,gaits,dtype,seed", [
+    (A1Config, 10, 160, "mixed", (Gait.TROTTING10,), torch.float32, 101),
+    (A1Config, 10, 96, "aggressive", (Gait.TROTTING10,), torch.float64, 102),
+    (AliengoConfig, 10, 96, "mixed", GAIT_MIX, torch.float32, 103),
+    (A1Config, 16, 32, "mixed", (Gait.TROTTING16, Gait.STANDING), torch.float32, 104),
+], ids=["a1_trot_f32", "a1_aggr_f64", "aliengo_mix_f32", "a1_h16_f32"])
+def test_activity_identical_on_the_engines_own_qp(robot, H, B, regime, gaits, dtype, seed):
+    """Constraint activity must be IDENTICAL (north_star).  Against the reference-constructed QP a weakly active row can
+    legitimately differ (its Su is float32: the two QPs differ by 5e-7), so the claim is proven where it can be exact: the
+    dense (H, g, ub) the engine itself states (mpcq_build_qp) is solved by the exact fp64 oracle solver and every one of the
+    20 H row flags of every environment has to agree, with the forces within 2e-4 N (f32 mode) / 2e-6 N (f64 mode)."""
+    batch = make_batch(robot, H, B, regime, gaits, seed, solve=False)
+    eng = _engine(batch["cfg"], robot, dtype)
+    a = _to_dev(batch, dtype)
+    res = eng.solve(a[0], a[1], a[2], a[3], yaw=a[4])
+    Hd, gd, ub = eng.build_qp(a[0], a[1], a[2], a[3], yaw=a[4])
+    torch.cuda.synchronize()
+    u = res.u.double().cpu().numpy()
+    active = res.active.cpu().numpy()
+    Hd, gd, ub = Hd.cpu().numpy(), gd.cpu().numpy(), ub.cpu().numpy()
+    assert torch.all(res.status & _capi.ST_VERIFIED)
+    ftol = 2e-6 if dtype == torch.float64 else 2e-4
+    worst = 0.0
+    for b in range(B):
+        sol = solve_qp_exact(Hd[b], gd[b], float(eng.consts["mu"]), ub[b, 4::5])
+        assert sol.verified
+        err = np.abs(u[b] - sol.u).max()
+        worst = max(worst, err)
+        assert err <= ftol + (0 if dtype == torch.float64 else 1e-6 * np.abs(sol.u).max()), f"env {b}: |du| = {err:.3e}"
+        lo, up = _activity(active[b], H)
+        assert np.array_equal(lo, sol.active_lower) and np.array_equal(up, sol.active_upper), \
+            f"env {b}: activity differs on rows {np.flatnonzero((lo != sol.active_lower) | (up != sol.active_upper))}"
+    print(f"activity identical on {B} x {20 * H} rows, worst |du| {worst:.2e} N")
+
+
+WHOLE = [
+    # BASELINE configs[1] in full, >= 1024 robots of configs[2] and [3]: name, robot, H, B, gaits, dtype, seed, oracle envs
+    ("cfg1_a1_trot_4096_f32", "A1Config", 10, 4096, (Gait.TROTTING10,), torch.float32, 21, 4096),
+    ("cfg2_aliengo_mix_16384_f64", "AliengoConfig", 10, 16384, GAIT_MIX, torch.float64, 22, 1536),
+    ("cfg3_a1_h30_4096_f32", "A1Config", 30, 4096, (Gait.TROTTING10,), torch.float32, 23, 1024),
+]
+
+
+@pytest.mark.parametrize("name,robot_name,H,B,gaits,dtype,seed,n_oracle", WHOLE, ids=[c[0] for c in WHOLE])
+def test_whole_batches_against_the_oracle(name, robot_name, H, B, gaits, dtype, seed, n_oracle):
+    """The oracle (reference construction restated + exact solve) on ALL 4 096 robots of BASELINE configs[1] and on >= 1 024
+    robots of configs[2] / [3], spread over the host cores; |du| <= max(1e-3 N, 1e-4 relative) on the whole optimum."""
+    from pympc_quadruped_b200 import configs
+    robot = getattr(configs, robot_name)
+    batch = make_batch(robot, H, B, "mixed", gaits, seed, solve=False)
+    eng = _engine(batch["cfg"], robot, dtype)
+    a = _to_dev(batch, dtype)
+    res = eng.solve(a[0], a[1], a[2], a[3], yaw=a[4], want=("u", "status", "iters"))
+    torch.cuda.synchronize()
+    assert torch.all(res.status & _capi.ST_VERIFIED)
+    u = res.u.double().cpu().numpy()
+    idx = np.arange(B) if n_oracle >= B else np.sort(np.random.default_rng(seed).choice(B, size=n_oracle, replace=False))
+    uo = oracle_pool_solve(batch, robot_name, idx)
+    err = np.abs(u[idx] - uo).max(axis=1)
+    tol = np.maximum(ABS_TOL, REL_TOL * np.abs(uo).max(axis=1))
+    bad = np.flatnonzero(err > tol)
+    assert bad.size == 0, f"{bad.size} envs beyond tolerance, worst {err.max():.3e} at env {idx[np.argmax(err / tol)]}"
+    print(f"{name}: {len(idx)} oracle envs, worst err/tol {np.max(err / tol):.3f} (|du| max {err.max():.2e} N), "
+          f"rounds mean {res.iters[:, 0].float().mean():.2f} max {int(res.iters[:, 0].max())}")
+
+
+def test_handles_of_different_horizons_coexist():
+    """The dynamic shared-memory limit of a kernel is per-device state shared by every handle: a handle created later for
+    a shorter horizon must not lower what an earlier long-horizon handle needs (both dtypes, both orders)."""
+    for dtype in (torch.float32, torch.float64):
+        b30 = make_batch(A1Config, 30, 8, "mixed", (Gait.TROTTING10,), 5, solve=False)
+        b10 = make_batch(A1Config, 10, 8, "mixed", (Gait.TROTTING10, Gait.STANDING), 6, solve=False)
+        e30 = _engine(b30["cfg"], A1Config, dtype)
+        e10 = _engine(b10["cfg"], A1Config, dtype)
+        for eng, bt in ((e30, b30), (e10, b10), (e30, b30)):
+            a = _to_dev(bt, dtype)
+            r = eng.solve(a[0], a[1], a[2], a[3], yaw=a[4])
+            torch.cuda.synchronize()
+            assert torch.all(r.status & _capi.ST_VERIFIED)
+            Hd, gd, ub = eng.build_qp(a[0], a[1], a[2], a[3], yaw=a[4])
+            torch.cuda.synchronize()
+
+
+def _tick_inputs(st, lo, hi):
+    B = hi - lo
+    sc = np.zeros((B, 29))
+    sc[:, 0:4], sc[:, 4:7], sc[:, 7:10], sc[:, 10:13] = st["quat_base"][lo:hi], st["pos_base"][lo:hi], st["ang_vel_base"][lo:hi], st["lin_vel_base"][lo:hi]
+    sc[:, 13:25] = st["pos_base_feet"][lo:hi].reshape(B, 12)
+    sc[:, 25:28], sc[:, 28] = st["vel_cmd_body"][lo:hi], st["yaw_rate_cmd"][lo:hi]
+    return sc
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64], ids=["f32", "f64"])
+def test_tick_host_equals_the_controller_on_device_tensors(dtype):
+    """mpcq_tick_host (272 B per robot over the bus; gait table, state assembly, reference trajectory and solve on the
+    device; controller state inside the handle) against BatchedModelPredictiveController driven with device tensors and the
+    device gait schedule: the same kernels in the same order, so the forces are equal bit for bit - over several MPC
+    updates, first run included, pageable and page-locked buffers."""
+    from pympc_quadruped_b200 import BatchedGaitSchedule
+    from pympc_quadruped_b200.controller import BatchedModelPredictiveController, BatchedRobotData
+    from pympc_quadruped_b200.gait import GaitSchedule
+    B, H, T = 300, 10, 4
+    cfg = with_horizon(H)
+    st = synth_states(B * T, A1Config, "mixed", seed=77)
+    offs, durs, segs, it0 = synth_gait_params(B, GAIT_MIX, seed=78)
+    ctrl = BatchedModelPredictiveController(cfg, A1Config, B, dtype=dtype)
+    eng = _engine(cfg, A1Config, dtype)
+    ibm = int(ctrl.iterations_between_mpc)
+    gs = BatchedGaitSchedule(ctrl.engine, [GaitSchedule("t", int(segs[i]), offs[i], durs[i], horizon=H) for i in range(B)])
+    rt = np.float64 if dtype == torch.float64 else np.float32
+    pinned = dict(forces=torch.empty((B, 12), dtype=dtype, pin_memory=True).numpy(), status=torch.empty((B,), dtype=torch.int32, pin_memory=True).numpy())
+    for t in range(T):
+        lo, hi = t * B, (t + 1) * B
+        cur = (it0 + 3 * t) * ibm
+        rd = BatchedRobotData(st["quat_base"][lo:hi], st["pos_base"][lo:hi], st["ang_vel_base"][lo:hi], st["lin_vel_base"][lo:hi], st["pos_base_feet"][lo:hi])
+        gs.set_iteration(ibm, torch.as_tensor(cur, device="cuda:0"))
+        ctrl.update_robot_state(rd)
+        f_dev = ctrl.update_mpc_if_needed(0, st["vel_cmd_body"][lo:hi], st["yaw_rate_cmd"][lo:hi], gs.get_gait_table())
+        gp = np.concatenate([offs, durs, segs[:, None], cur[:, None]], axis=1).astype(np.int32)
+        r = eng.tick_host(_tick_inputs(st, lo, hi), gp, ibm, first_run=(t == 0), out=pinned if t % 2 else None)
+        torch.cuda.synchronize()
+        assert r["forces"].dtype == rt
+        assert np.array_equal(r["forces"], f_dev.cpu().numpy()), t
+        assert np.all(r["status"] & _capi.ST_VERIFIED)
+    assert eng.last_launch_count >= 4
+    with pytest.raises(ValueError):
+        eng.tick_host(np.zeros((4, 28)), np.ones((4, 10), np.int32), ibm)
+    with pytest.raises(ValueError):
+        eng.tick_host(np.zeros((4, 29)), np.zeros((4, 10), np.int32), ibm)          # num_segment 0
+
+
+def test_largest_class_in_fp32_and_default_horizon_adapter():
+    """Class 384 (A1 standing, H = 30: n = 360, factor and Schur block in the global-memory workspace) in fp32 against the
+    oracle, and the reference's DEFAULT config (horizon 16, TROTTING16 / STANDING) through the B = 1 drop-in class."""
+    batch = make_batch(A1Config, 30, 6, "mixed", (Gait.STANDING,), 19)
+    eng = _engine(batch["cfg"], A1Config, torch.float32)
+    a = _to_dev(batch, torch.float32)
+    res = eng.solve(a[0], a[1], a[2], a[3], yaw=a[4])
+    torch.cuda.synchronize()
+    assert torch.all(res.status & _capi.ST_VERIFIED)
+    u = res.u.double().cpu().numpy()
+    for b in range(batch["B"]):
+        sol = batch["sols"][b]
+        assert np.abs(u[b] - sol.u).max() <= max(ABS_TOL, REL_TOL * np.abs(sol.u).max()), b
+    # default LinearMpcConfig (horizon 16) through ModelPredictiveController, one robot, numpy in / out
+    from oracle.mpc_oracle import OracleMPC, RobotState
+    from pympc_quadruped_b200 import LinearMpcConfig
+    from pympc_quadruped_b200.controller import ModelPredictiveController
+    assert LinearMpcConfig.horizon == 16
+    st = synth_states(6, A1Config, "mixed", seed=33)
+    for b, g in enumerate((Gait.TROTTING16, Gait.STANDING, Gait.TROTTING16, Gait.JUMPING16, Gait.PACING16, Gait.STANDING)):
+        ctrl = ModelPredictiveController(LinearMpcConfig, A1Config, dtype=torch.float32)
+        orc = OracleMPC(LinearMpcConfig, A1Config)
+        rd = RobotState(st["quat_base"][b], st["pos_base"][b], st["ang_vel_base"][b], st["lin_vel_base"][b], st["pos_base_feet"][b])
+        g.set_iteration(20, 20 * b)
+        tab = g.get_gait_table()
+        for tick in (0, 20):
+            ctrl.update_robot_state(rd)
+            orc.update_robot_state(rd)
+            f = ctrl.update_mpc_if_needed(tick, st["vel_cmd_body"][b], float(st["yaw_rate_cmd"][b]), tab)
+            fo = orc.update_mpc_if_needed(tick, st["vel_cmd_body"][b], float(st["yaw_rate_cmd"][b]), tab)
+            assert f.shape == (12,) and f.dtype == np.float64
+            assert np.abs(f - fo).max() <= max(ABS_TOL, REL_TOL * np.abs(fo).max()), (b, tick)
+
+
+def test_262144_robots_properties():
+    """BASELINE configs[4] on one GPU: every one of 262 144 robots verified, forces inside the pyramid, swing forces exactly
+    zero, and the batch split into shards (what the multi-GPU run does per rank) returns the same bits."""
+    B, H = 262144, 10
+    rng = np.random.default_rng(9)
+    base = make_batch(A1Config, H, 8192, "mixed", (Gait.TROTTING10,), 41, solve=False)
+    rep = B // 8192
+    jitter = lambda a, s: np.tile(a, (rep,) + (1,) * (a.ndim - 1)) + rng.normal(0, s, (B,) + a.shape[1:]).astype(a.dtype)
+    x0 = jitter(base["x0"], 1e-3); x0[:, 12] = base["x0"][0, 12]
+    feet, xref = jitter(base["feet"], 1e-3), np.tile(base["xref"], (rep, 1))
+    yaw, gait = x0[:, 2].astype(np.float64), np.tile(base["gait"], (rep, 1))
+    eng = _engine(base["cfg"], A1Config, torch.float32)
+    t = lambda a, dt=torch.float32: torch.as_tensor(a).to(device="cuda:0", dtype=dt)
+    X = (t(x0), t(feet), t(gait), t(xref), t(yaw))
+    res = eng.solve(X[0], X[1], X[2], X[3], yaw=X[4], want=("u", "status"))
+    torch.cuda.synchronize()
+    assert torch.all(res.status & _capi.ST_VERIFIED) and not torch.any(res.status & (_capi.ST_NUMERIC | _capi.ST_MAXITER))
+    f = res.u.reshape(B, 4 * H, 3)
+    stance = X[2].reshape(B, 4 * H) > 0
+    assert torch.all(f[~stance] == 0)
+    mu, fz_max, tol = float(eng.consts["mu"]), float(eng.consts["fz_max"]), 2e-5
+    assert torch.all(f[..., 2] >= -tol) and torch.all(f[..., 2] <= fz_max + tol)
+    assert torch.all(f[..., 0].abs() <= mu * f[..., 2] + tol) and torch.all(f[..., 1].abs() <= mu * f[..., 2] + tol)
+    for lo, hi in ((0, 32768), (32768, 131072), (229376, 262144)):         # shards of an 8-way / 2-way split
+        r2 = eng.solve(X[0][lo:hi], X[1][lo:hi], X[2][lo:hi], X[3][lo:hi], yaw=X[4][lo:hi], want=("u",))
+        assert torch.equal(r2.u, res.u[lo:hi])
+
+
+def test_config0_thousand_updates_of_one_robot():
+    """BASELINE configs[0]: 1 000 consecutive MPC updates of ONE A1 robot through the drop-in class, against the sequence
+    recorded from the unmodified reference class (tests/golden/reference_cfg0_seq.npz, oracle/make_golden_cfg0.py): forces,
+    integrator state and the reference trajectory (checksums) of every update."""
+    from oracle.mpc_oracle import quat_to_matrix
+    from pympc_quadruped_b200.controller import ModelPredictiveController
+    z = np.load(os.path.join(GOLD, "reference_cfg0_seq.npz"))
+    ctrl = ModelPredictiveController(with_horizon(10), A1Config, dtype=torch.float32)
+    gt = Gait.TROTTING10.with_horizon(10)
+
+    class RD:
+        pass
+    worst = 0.0
+    for t in range(z["forces__oracle_solver"].shape[0]):
+        rd = RD()
+        rd.quat_base, rd.pos_base, rd.ang_vel_base, rd.lin_vel_base = z["quat_base"][t], z["pos_base"][t], z["ang_vel_base"][t], z["lin_vel_base"][t]
+        rd.pos_base_feet = [z["pos_base_feet"][t, i] for i in range(4)]
+        rd.R_base = quat_to_matrix(rd.quat_base)
+        gt.set_iteration(20, 20 * t)
+        ctrl.update_robot_state(rd)
+        f = ctrl.update_mpc_if_needed(20 * t, z["vel_cmd_body"][t], float(z["yaw_rate_cmd"][t]), gt.get_gait_table())
+        ref = z["forces__oracle_solver"][t]
+        tol = max(ABS_TOL, REL_TOL * np.abs(ref).max())
+        err = np.abs(f - ref).max()
+        worst = max(worst, err / tol)
+        assert err <= tol, (t, err)
+        des = np.array([float(ctrl.xpos_base_desired[0]), float(ctrl.ypos_base_desired[0]), float(ctrl.yaw_desired[0]),
+                        float(ctrl.roll_init[0]), float(ctrl.pitch_init[0])])
+        # the roll / pitch compensation increments dt (0 - x[0]) / x[10] are float32 under the numpy 2 that generated the fixture
+        # (NEP 50: python float * np.float32 stays float32) and float64 under the reference's pinned numpy 1.24 and on the device
+        # -> the two integrators drift apart by float32 rounding per update (2e-7 after 600 updates); x / y / yaw desired are exact
+        assert np.allclose(des[:3], z["desired"][t][:3], rtol=0, atol=1e-12), (t, des - z["desired"][t])
+        assert np.allclose(des[3:], z["desired"][t][3:], rtol=0, atol=2e-6), (t, des - z["desired"][t])
+        r = ctrl.ref_traj.astype(np.float64)
+        cs = np.array([r.sum(), np.abs(r).sum(), (r * np.arange(1, r.size + 1)).sum()])
+        assert np.allclose(cs, z["ref_traj_checksums"][t], rtol=5e-7, atol=5e-5), (t, cs - z["ref_traj_checksums"][t])
+    print(f"config[0]: 1000 updates, worst err/tol {worst:.3f}")
+
+
+def test_from_isaacgym_on_device_tensors():
+    """BatchedRobotData.from_isaacgym on CUDA tensors (root_state rows pos | quat x,y,z,w | lin vel | ang vel,
+    scripts/isaacgym_a1.py:119-133) feeds the controller the same data as the per-robot reorder of the script."""
+    from pympc_quadruped_b200.controller import BatchedModelPredictiveController, BatchedRobotData
+    B, H = 64, 10
+    st = synth_states(B, A1Config, "mixed", seed=88)
+    q = st["quat_base"]
+    root = np.concatenate([st["pos_base"], q[:, [1, 2, 3, 0]], st["lin_vel_base"], st["ang_vel_base"]], axis=1)   # Isaac Gym layout
+    feet_world = st["pos_base"][:, None, :] + st["pos_base_feet"]
+    dev = "cuda:0"
+    rd_gym = BatchedRobotData.from_isaacgym(torch.as_tensor(root, device=dev), torch.as_tensor(feet_world, device=dev))
+    assert rd_gym.quat_base.is_cuda
+    rd_ref = BatchedRobotData(st["quat_base"], st["pos_base"], st["ang_vel_base"], st["lin_vel_base"], st["pos_base_feet"])
+    g = Gait.TROTTING10.with_horizon(H)
+    g.set_iteration(20, 40)
+    tabs = torch.as_tensor(np.stack([g.get_gait_table()] * B), device=dev)
+    fs = []
+    for rd in (rd_gym, rd_ref):
+        c = BatchedModelPredictiveController(with_horizon(H), A1Config, B)
+        c.update_robot_state(rd)
+        fs.append(c.update_mpc_if_needed(0, st["vel_cmd_body"], st["yaw_rate_cmd"], tabs))
+    assert torch.allclose(fs[0], fs[1], rtol=0, atol=2e-4)
+    assert torch.equal(rd_gym.quat_base.cpu(), torch.as_tensor(st["quat_base"]))

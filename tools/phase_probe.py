@@ -6,7 +6,9 @@ from pympc_quadruped_b200 import *
 from pympc_quadruped_b200 import _capi
 from pympc_quadruped_b200.engine import MpcqEngine
 names=['setup_model','hess_apply','build_slots','chol_factor','invert_factor','reduced_gradient','apply_step','pdas_update','refine (incl.)','solve_env(total)','  schur_factor','dual_round (incl.)','dual_apply (incl.)','  schur_solve','  dual_combine']
-bt=make_batch(A1Config,10,4096,'mixed',(Gait.TROTTING10,),9,solve=False)
+import os
+HH=int(os.environ.get('HH','10')); BB=int(os.environ.get('BB','4096'))
+bt=make_batch(A1Config,HH,BB,'mixed',(Gait.STANDING if os.environ.get('GAIT')=='stand' else Gait.TROTTING10,),9,solve=False)
 eng=MpcqEngine(bt['cfg'],A1Config)
 lib=_capi.load_library()
 t=lambda a,dt=torch.float32: torch.as_tensor(a).to(device='cuda:0',dtype=dt)
@@ -23,6 +25,6 @@ def probe(idx,label):
     ne=len(idx)
     print(f'--- {label}: envs {ne} rounds {rounds}  total {tot/ne:.0f} cycles/env')
     for n,c in zip(names,v): print(f'   {n:20s} {c/ne:9.0f} cycles/env  {100*c/tot:5.1f}%')
-sel=np.flatnonzero(it==6)[:1]
-probe(sel,'one env alone (6 rounds)')
-probe(np.arange(4096),'B=4096 under load')
+sel=np.flatnonzero(it==int(np.median(it)))[:1]
+probe(sel,'one env alone (median rounds)')
+probe(np.arange(BB),'whole batch under load')
