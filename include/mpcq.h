@@ -141,7 +141,9 @@ int mpcq_set_warm_start(mpcq_handle* h, const uint8_t* faces_in, uint8_t* faces_
  *   quat [B,4] (w,x,y,z), pos [B,3], omega [B,3] (world), vel [B,3] (world), R_base [B,9] or NULL (from quat),
  *   v_des_body [B,3], yaw_rate_des [B]
  *   in/out state: xy_des [B,2], yaw_des [B], rp_init [B,2] (roll_init, pitch_init)
- *   first_run != 0: desired pose initialised as mpc.py:84-88;  do_mpc != 0: this tick recomputes X_ref (mpc.py:95-96)
+ *   first_run = 1: desired pose initialised as mpc.py:84-88 (x = y = 0, yaw = current);  first_run = 2 (no reference counterpart: a
+ *   simulator env that was just reset): desired x / y / yaw = the CURRENT pose and the roll / pitch compensation integrators restart
+ *   from 0;  do_mpc != 0: this tick recomputes X_ref (mpc.py:95-96)
  * outputs (`real`): x0 [B,13] and yaw [B] always, x_ref [B,13H] when do_mpc != 0 - exactly the arrays mpcq_solve takes.
  */
 int mpcq_assemble(mpcq_handle* h, int32_t B,
@@ -232,7 +234,7 @@ int mpcq_solve_host(mpcq_handle* h, int32_t B,
  *   state_cmd   [B,29] float64 host: quat (w,x,y,z) 4 | pos_base 3 | ang_vel_base 3 | lin_vel_base 3 (world) |
  *               pos_base_feet 12 (world-frame base->foot, FL FR RL RR) | v_des_body 3 | yaw_rate_des
  *   gait_params [B,10] int32 host: stance_offsets 4 | stance_durations 4 | num_segment | cur_iteration (control tick)
- *   first_run != 0: desired pose initialised from the state as mpc.py:84-88
+ *   first_run: 0 = regular tick, 1 = mpc.py:84-88, 2 = respawn (desired pose = current pose, integrators zeroed); see mpcq_assemble
  *   f_out [B,12] `real` host, status [B] int32 host or NULL; page-locked buffers are read by DMA / written in place.
  * The controller state of mpc.py (x/y/yaw desired, roll/pitch compensation integrators) is kept per robot inside the
  * handle between calls (slot i = robot i; a larger B than before re-allocates and zeroes it; mpcq_tick_reset zeroes it).

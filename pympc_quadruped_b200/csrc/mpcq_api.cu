@@ -324,7 +324,8 @@ mpcq_assemble_kernel(const __grid_constant__ AssembleArgs a, T* x0, T* yaw_out, 
     const double vx = (R[0] * vb0 + R[1] * vb1) + R[2] * vb2, vy = (R[3] * vb0 + R[4] * vb1) + R[5] * vb2;
     const double rate = a.yawrate[b];
     double xd, yd, yawd;
-    if (a.first_run) { xd = 0.0; yd = 0.0; yawd = yaw; }       // mpc.py:84-88
+    if (a.first_run == 2) { xd = (double)st[3]; yd = (double)st[4]; yawd = yaw; }   // respawn: desired pose = current pose
+    else if (a.first_run) { xd = 0.0; yd = 0.0; yawd = yaw; }  // mpc.py:84-88
     else {                                                      // mpc.py:89-92
         xd = a.xy_des[2 * b] + a.dt_control * vx;
         yd = a.xy_des[2 * b + 1] + a.dt_control * vy;
@@ -337,7 +338,7 @@ mpcq_assemble_kernel(const __grid_constant__ AssembleArgs a, T* x0, T* yaw_out, 
         if (x3 - xd > lim) xd = x3 - lim;
         if (yd - x4 > lim) yd = x4 + lim;
         if (x4 - yd > lim) yd = x4 - lim;
-        double roll_init = a.rp_init[2 * b], pitch_init = a.rp_init[2 * b + 1];
+        double roll_init = a.first_run == 2 ? 0.0 : a.rp_init[2 * b], pitch_init = a.first_run == 2 ? 0.0 : a.rp_init[2 * b + 1];
         if (fabs((double)st[9]) > 0.2) pitch_init += a.dt * (0.0 - (double)st[1]) / (double)st[9];
         if (fabs((double)st[10]) > 0.1) roll_init += a.dt * (0.0 - (double)st[0]) / (double)st[10];
         roll_init = fmin(fmax(roll_init, -0.25), 0.25);
@@ -1004,6 +1005,7 @@ int mpcq_tick_host(mpcq_handle* h, int32_t B, const double* state_cmd, const int
         if (!cuda_ok(h, cudaMalloc(&h->tick_dev, cur), "cudaMalloc tick")) return MPCQ_ERR_CUDA;
         if (!cuda_ok(h, cudaMalloc(&h->tick_state, b * 5 * sizeof(double)), "cudaMalloc tick state")) return MPCQ_ERR_CUDA;
         if (!cuda_ok(h, cudaMemsetAsync(h->tick_state, 0, b * 5 * sizeof(double), st), "memset tick state")) return MPCQ_ERR_CUDA;
+        cudaStreamSynchronize(st);                              // the chunks below run on several streams
         h->tick_cap = b;
     }
     {
@@ -1023,14 +1025,33 @@ int mpcq_tick_host(mpcq_handle* h, int32_t B, const double* state_cmd, const int
         if (!cuda_ok(h, cudaMallocHost(&h->pin, need_pin), "cudaMallocHost staging")) return MPCQ_ERR_CUDA;
         h->stage_cap = need_pin;
     }
-    const void* src[2] = {state_cmd, gait_params};
-    size_t poff = 0;
-    for (int i = 0; i < 2; ++i) {
-        const void* from = src[i];
-        if (!host_range_pinned(h, from, b * width[i])) { memcpy(h->pin + poff, from, b * width[i]); from = h->pin + poff; }
-        poff += al(b * width[i]);
-        if (!cuda_ok(h, cudaMemcpyAsync(d + off[i], from, b * width[i], cudaMemcpyHostToDevice, st), "H2D")) return MPCQ_ERR_CUDA;
+    // the batch is cut into chunks on separate streams (like mpcq_solve_host): the copies and the small kernels of one chunk
+    // hide behind the solve of the other, and the solve kernels of neighbouring chunks fill each other's tails
+    bool any_global = false;
+    for (int ci = 0; ci < h->ncls; ++ci) any_global = any_global || h->lglobal[ci];
+    int nchunk = any_global ? 1 : (B >= 16384 ? kHostStreams : (B >= 8192 ? 2 : 1));   // measured at 4 096 robots: 1 / 2 / 3 chunks = 585 / 608 / 642 us
+    if (const char* ov = getenv("MPCQ_HOST_CHUNKS")) {          // experiments only
+        const int v = atoi(ov);
+        if (v >= 1 && v <= kHostStreams && !any_global) nchunk = v;
     }
+    const void* src[2] = {state_cmd, gait_params};
+    bool src_pinned[2];
+    size_t poffs[2] = {0, al(b * width[0])};
+    for (int i = 0; i < 2; ++i) src_pinned[i] = host_range_pinned(h, src[i], b * width[i]);
+    // results: in place into page-locked caller buffers, else staged
+    void* dst[2] = {f_out, status};
+    char* dres[2] = {d + off[13], d + off[14]};
+    bool direct[2] = {false, false}, dst_pinned[2] = {false, false};
+    for (int i = 0; i < 2; ++i) {
+        if (!dst[i]) continue;
+        dst_pinned[i] = host_range_pinned(h, dst[i], b * width[13 + i]);
+        if (!h->direct_results || !dst_pinned[i]) continue;
+        void* dptr = nullptr;
+        if (cudaHostGetDevicePointer(&dptr, dst[i], 0) == cudaSuccess) { dres[i] = static_cast<char*>(dptr); direct[i] = true; }
+        else cudaGetLastError();
+    }
+    char* pres = h->pin + al(b * width[0]) + al(b * width[1]);
+    auto fail = [&](int code) { for (int i = 0; i < kHostStreams; ++i) cudaStreamSynchronize(h->streams[i]); return code; };
     TickArrays ta{reinterpret_cast<double*>(d + off[2]), reinterpret_cast<double*>(d + off[3]), reinterpret_cast<double*>(d + off[4]),
                   reinterpret_cast<double*>(d + off[5]), reinterpret_cast<double*>(d + off[6]), reinterpret_cast<double*>(d + off[7]),
                   reinterpret_cast<int32_t*>(d + off[8]), reinterpret_cast<int32_t*>(d + off[9]), reinterpret_cast<int32_t*>(d + off[10]),
@@ -1039,45 +1060,50 @@ int mpcq_tick_host(mpcq_handle* h, int32_t B, const double* state_cmd, const int
     char* yaw = x0 + al(b * 13 * rs);
     char* feet = yaw + al(b * rs);
     char* xref = feet + al(b * 12 * rs);
-    float* table = reinterpret_cast<float*>(xref + al(b * 13 * H * rs));
-    const int grid = (B + 127) / 128;
-    const double* sc = reinterpret_cast<const double*>(d + off[0]);
-    const int32_t* gp = reinterpret_cast<const int32_t*>(d + off[1]);
-    if (h->cfg.dtype == MPCQ_F64) mpcq_tick_unpack_kernel<double><<<grid, 128, 0, st>>>(B, sc, gp, ta, reinterpret_cast<double*>(feet));
-    else mpcq_tick_unpack_kernel<float><<<grid, 128, 0, st>>>(B, sc, gp, ta, reinterpret_cast<float*>(feet));
-    GaitArgs ga{ta.offs, ta.durs, ta.seg, ta.iter, iterations_between_mpc, B, h->cs.horizon};
-    mpcq_gait_kernel<<<grid, 128, 0, st>>>(ga, table, nullptr, nullptr);
+    char* table = xref + al(b * 13 * H * rs);
     double* cst = h->tick_state;
-    AssembleArgs aa{ta.quat, ta.pos, ta.omega, ta.vel, nullptr, ta.vdes, ta.yawrate, cst, cst + 2 * b, cst + 3 * b, first_run, 1, B,
-                    h->cs.horizon, h->cfg.dt_control, h->cfg.dt, h->cfg.com_height_des, h->cfg.gravity};
-    if (h->cfg.dtype == MPCQ_F64)
-        mpcq_assemble_kernel<double><<<grid, 128, 0, st>>>(aa, reinterpret_cast<double*>(x0), reinterpret_cast<double*>(yaw), reinterpret_cast<double*>(xref));
-    else
-        mpcq_assemble_kernel<float><<<grid, 128, 0, st>>>(aa, reinterpret_cast<float*>(x0), reinterpret_cast<float*>(yaw), reinterpret_cast<float*>(xref));
-    if (!cuda_ok(h, cudaGetLastError(), "mpcq_tick_host launch")) return MPCQ_ERR_CUDA;
-    // results: in place into page-locked caller buffers, else staged
-    void* dst[2] = {f_out, status};
-    char* dres[2] = {d + off[13], d + off[14]};
-    bool direct[2] = {false, false};
-    for (int i = 0; i < 2; ++i) {
-        if (!dst[i] || !h->direct_results || !host_range_pinned(h, dst[i], b * width[13 + i])) continue;
-        void* dptr = nullptr;
-        if (cudaHostGetDevicePointer(&dptr, dst[i], 0) == cudaSuccess) { dres[i] = static_cast<char*>(dptr); direct[i] = true; }
-        else cudaGetLastError();
+    int launches = 0;
+    for (int c = 0; c < nchunk; ++c) {
+        const size_t lo = b * c / nchunk, hi = b * (c + 1) / nchunk, nb = hi - lo;
+        if (nb == 0) continue;
+        cudaStream_t st = h->streams[c % kHostStreams];
+        for (int i = 0; i < 2; ++i) {
+            const char* from = static_cast<const char*>(src[i]) + lo * width[i];
+            if (!src_pinned[i]) { memcpy(h->pin + poffs[i] + lo * width[i], from, nb * width[i]); from = h->pin + poffs[i] + lo * width[i]; }
+            if (!cuda_ok(h, cudaMemcpyAsync(d + off[i] + lo * width[i], from, nb * width[i], cudaMemcpyHostToDevice, st), "H2D")) return fail(MPCQ_ERR_CUDA);
+        }
+        TickArrays tc{ta.quat + 4 * lo, ta.pos + 3 * lo, ta.omega + 3 * lo, ta.vel + 3 * lo, ta.vdes + 3 * lo, ta.yawrate + lo,
+                      ta.offs + 4 * lo, ta.durs + 4 * lo, ta.seg + lo, ta.iter + lo};
+        const int nbi = (int)nb, grid = (nbi + 127) / 128;
+        const double* sc = reinterpret_cast<const double*>(d + off[0]) + 29 * lo;
+        const int32_t* gp = reinterpret_cast<const int32_t*>(d + off[1]) + 10 * lo;
+        char* cx0 = x0 + lo * 13 * rs; char* cyaw = yaw + lo * rs; char* cfeet = feet + lo * 12 * rs; char* cxref = xref + lo * 13 * H * rs;
+        float* ctab = reinterpret_cast<float*>(table) + lo * 4 * H;
+        if (h->cfg.dtype == MPCQ_F64) mpcq_tick_unpack_kernel<double><<<grid, 128, 0, st>>>(nbi, sc, gp, tc, reinterpret_cast<double*>(cfeet));
+        else mpcq_tick_unpack_kernel<float><<<grid, 128, 0, st>>>(nbi, sc, gp, tc, reinterpret_cast<float*>(cfeet));
+        GaitArgs ga{tc.offs, tc.durs, tc.seg, tc.iter, iterations_between_mpc, nbi, h->cs.horizon};
+        mpcq_gait_kernel<<<grid, 128, 0, st>>>(ga, ctab, nullptr, nullptr);
+        AssembleArgs aa{tc.quat, tc.pos, tc.omega, tc.vel, nullptr, tc.vdes, tc.yawrate, cst + 2 * lo, cst + 2 * b + lo, cst + 3 * b + 2 * lo,
+                        first_run, 1, nbi, h->cs.horizon, h->cfg.dt_control, h->cfg.dt, h->cfg.com_height_des, h->cfg.gravity};
+        if (h->cfg.dtype == MPCQ_F64)
+            mpcq_assemble_kernel<double><<<grid, 128, 0, st>>>(aa, reinterpret_cast<double*>(cx0), reinterpret_cast<double*>(cyaw), reinterpret_cast<double*>(cxref));
+        else
+            mpcq_assemble_kernel<float><<<grid, 128, 0, st>>>(aa, reinterpret_cast<float*>(cx0), reinterpret_cast<float*>(cyaw), reinterpret_cast<float*>(cxref));
+        if (!cuda_ok(h, cudaGetLastError(), "mpcq_tick_host launch")) return fail(MPCQ_ERR_CUDA);
+        const int rc = solve_impl(h, nbi, cx0, cyaw, cfeet, ctab, cxref, dres[0] + lo * width[13], nullptr, nullptr, nullptr,
+                                  status ? reinterpret_cast<int32_t*>(dres[1] + lo * width[14]) : nullptr, nullptr, 1, lo, st, c % kHostStreams);
+        if (rc != MPCQ_OK) return fail(rc);
+        launches += h->last_launches + 3;
+        for (int i = 0; i < 2; ++i) {
+            if (!dst[i] || direct[i]) continue;
+            char* to = (dst_pinned[i] ? static_cast<char*>(dst[i]) : pres + (i ? al(b * width[13]) : 0)) + lo * width[13 + i];
+            if (!cuda_ok(h, cudaMemcpyAsync(to, dres[i] + lo * width[13 + i], nb * width[13 + i], cudaMemcpyDeviceToHost, st), "D2H")) return fail(MPCQ_ERR_CUDA);
+        }
     }
-    const int rc = solve_impl(h, B, x0, yaw, feet, table, xref, dres[0], nullptr, nullptr, nullptr,
-                              status ? reinterpret_cast<int32_t*>(dres[1]) : nullptr, nullptr, 1, 0, st, 0);
-    if (rc != MPCQ_OK) { cudaStreamSynchronize(st); return rc; }
-    const int launches = h->last_launches + 3;
-    char* pres = h->pin + al(b * width[0]) + al(b * width[1]);
-    for (int i = 0; i < 2; ++i) {
-        if (!dst[i] || direct[i]) continue;
-        char* to = host_range_pinned(h, dst[i], b * width[13 + i]) ? static_cast<char*>(dst[i]) : pres + (i ? al(b * width[13]) : 0);
-        if (!cuda_ok(h, cudaMemcpyAsync(to, dres[i], b * width[13 + i], cudaMemcpyDeviceToHost, st), "D2H")) { cudaStreamSynchronize(st); return MPCQ_ERR_CUDA; }
-    }
-    if (!cuda_ok(h, cudaStreamSynchronize(st), "mpcq_tick_host sync")) return MPCQ_ERR_CUDA;
+    for (int c = 0; c < nchunk && c < kHostStreams; ++c)
+        if (!cuda_ok(h, cudaStreamSynchronize(h->streams[c]), "mpcq_tick_host sync")) return fail(MPCQ_ERR_CUDA);
     for (int i = 0; i < 2; ++i)
-        if (dst[i] && !direct[i] && !host_range_pinned(h, dst[i], b * width[13 + i])) memcpy(dst[i], pres + (i ? al(b * width[13]) : 0), b * width[13 + i]);
+        if (dst[i] && !direct[i] && !dst_pinned[i]) memcpy(dst[i], pres + (i ? al(b * width[13]) : 0), b * width[13 + i]);
     h->last_launches = launches;
     return MPCQ_OK;
 }
@@ -1086,7 +1112,9 @@ int mpcq_tick_reset(mpcq_handle* h) {
     if (!h) return MPCQ_ERR_INVALID;
     if (!h->tick_state) return MPCQ_OK;
     DeviceGuard guard(h->cfg.device);
-    return cuda_ok(h, cudaMemset(h->tick_state, 0, h->tick_cap * 5 * sizeof(double)), "mpcq_tick_reset") ? MPCQ_OK : MPCQ_ERR_CUDA;
+    // on the stream mpcq_tick_host works on: ordered with the ticks before and after without a host synchronisation
+    for (int i = 1; i < kHostStreams; ++i) cudaStreamSynchronize(h->streams[i]);
+    return cuda_ok(h, cudaMemsetAsync(h->tick_state, 0, h->tick_cap * 5 * sizeof(double), h->streams[0]), "mpcq_tick_reset") ? MPCQ_OK : MPCQ_ERR_CUDA;
 }
 
 int mpcq_last_launch_count(const mpcq_handle* h) { return h ? h->last_launches : 0; }

@@ -146,11 +146,13 @@ class MpcqEngine:
         self._err(rc, "mpcq_solve_host")
         return res
 
-    def tick_host(self, state_cmd, gait_params, iterations_between_mpc: int, first_run: bool = False, out=None):
+    def tick_host(self, state_cmd, gait_params, iterations_between_mpc: int, first_run=False, out=None, validate=True):
         """One MPC update of B robots from HOST state through `mpcq_tick_host`: `state_cmd` [B,29] float64
         (quat 4 | pos 3 | omega 3 | vel 3 | pos_base_feet 12 | v_des_body 3 | yaw_rate), `gait_params` [B,10] int32
         (stance_offsets 4 | stance_durations 4 | num_segment | cur_iteration).  Gait table, state assembly, reference
         trajectory and the solve run on the device; the controller's integrator state lives in the handle.
+        `first_run`: False / True (mpc.py:84-88) / 2 (respawn: desired pose = current pose).  `validate=False` skips the
+        host-side pass over gait_params (num_segment >= 1) in hot loops.
         Returns dict(forces [B,12], status [B]) as numpy arrays (`out` may hold preallocated, e.g. page-locked, ones)."""
         rt = np.float64 if self.dtype == torch.float64 else np.float32
         state_cmd = np.ascontiguousarray(state_cmd, dtype=np.float64)
@@ -160,7 +162,7 @@ class MpcqEngine:
         gait_params = np.ascontiguousarray(gait_params, dtype=np.int32)
         if gait_params.shape != (B, 10):
             raise ValueError(f"gait_params must be [B,10], got {gait_params.shape}")
-        if np.any(gait_params[:, 8] < 1):
+        if validate and np.any(gait_params[:, 8] < 1):
             raise ValueError("num_segment must be >= 1")
         res = {}
         for key, shape, dt in (("forces", (B, 12), rt), ("status", (B,), np.int32)):
@@ -172,7 +174,7 @@ class MpcqEngine:
             else:
                 res[key] = np.empty(shape, dt)
         p = lambda a: a.ctypes.data_as(C.c_void_p)
-        rc = self.lib.mpcq_tick_host(self._h, B, p(state_cmd), p(gait_params), int(iterations_between_mpc), int(bool(first_run)),
+        rc = self.lib.mpcq_tick_host(self._h, B, p(state_cmd), p(gait_params), int(iterations_between_mpc), int(first_run),
                                      p(res["forces"]), p(res["status"]))
         self._err(rc, "mpcq_tick_host")
         return res
@@ -224,7 +226,7 @@ class MpcqEngine:
                 raise ValueError(f"{name} must be contiguous (it is written in place)")
         stream = torch.cuda.current_stream(self.device).cuda_stream
         rc = self.lib.mpcq_assemble(self._h, B, _ptr(quat), _ptr(pos), _ptr(omega), _ptr(vel), _ptr(R_base), _ptr(v_des_body),
-                                    _ptr(yaw_rate_des), _ptr(xy_des), _ptr(yaw_des), _ptr(rp_init), int(bool(first_run)),
+                                    _ptr(yaw_rate_des), _ptr(xy_des), _ptr(yaw_des), _ptr(rp_init), int(first_run),
                                     int(bool(do_mpc)), _ptr(x0), _ptr(yaw), _ptr(x_ref), C.c_void_p(stream))
         self._err(rc, "mpcq_assemble")
 

@@ -160,6 +160,19 @@ def test_tick_host_equals_the_controller_on_device_tensors(dtype):
         assert np.array_equal(r["forces"], f_dev.cpu().numpy()), t
         assert np.all(r["status"] & _capi.ST_VERIFIED)
     assert eng.last_launch_count >= 4
+    # respawn mode (first_run = 2): desired x / y / yaw = the current pose, roll / pitch integrators restart at zero
+    c = ctrl
+    x0 = torch.empty((B, 13), dtype=dtype, device="cuda:0"); yw = torch.empty(B, dtype=dtype, device="cuda:0")
+    xr = torch.empty((B, 13 * H), dtype=dtype, device="cuda:0")
+    xy, yd, rp = torch.full((B, 2), 7.0, dtype=torch.float64, device="cuda:0"), torch.zeros(B, dtype=torch.float64, device="cuda:0"), \
+        torch.full((B, 2), 0.2, dtype=torch.float64, device="cuda:0")
+    t64 = lambda a: torch.as_tensor(a, dtype=torch.float64, device="cuda:0").contiguous()
+    eng.assemble(c._quat, c._pos, c._omega, c._vel, t64(st["vel_cmd_body"][lo:hi]), t64(st["yaw_rate_cmd"][lo:hi]), xy, yd, rp, 2, True, x0, yw, xr)
+    torch.cuda.synchronize()
+    assert torch.equal(xr[:, 3:5], x0[:, 3:5]) and torch.equal(xr[:, 2].float(), yw.float()) and torch.equal(xy.float(), x0[:, 3:5].float())
+    assert float(rp.abs().max()) < 0.2                              # restarted from 0, one update
+    r2 = eng.tick_host(_tick_inputs(st, lo, hi), gp, ibm, first_run=2, validate=False)
+    assert np.all(r2["status"] & _capi.ST_VERIFIED)
     with pytest.raises(ValueError):
         eng.tick_host(np.zeros((4, 28)), np.ones((4, 10), np.int32), ibm)
     with pytest.raises(ValueError):
