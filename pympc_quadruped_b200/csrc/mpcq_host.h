@@ -25,7 +25,7 @@ struct SizeClass { int ncap, ns_lo, ns_hi, nw; };      // nw = warps of the team
 #define MPCQ_NW2 3
 #endif
 #ifndef MPCQ_NW3
-#define MPCQ_NW3 2
+#define MPCQ_NW3 12
 #endif
 static const SizeClass kClasses[4] = {{64, 0, class_ns_hi(64), MPCQ_NW0}, {128, class_ns_hi(64) + 1, class_ns_hi(128), MPCQ_NW1},
                                       {192, class_ns_hi(128) + 1, class_ns_hi(192), MPCQ_NW2}, {384, class_ns_hi(192) + 1, class_ns_hi(384), MPCQ_NW3}};
