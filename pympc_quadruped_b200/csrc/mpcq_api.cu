@@ -33,22 +33,26 @@ template <int NCAP> struct TeamWarps { static constexpr int value = NCAP <= 64 ?
 // path (model, factorisation, inversion - no data-dependent control flow there), so the SM's instruction caches serve one
 // copy of it instead of one per resident warp (measured: the kernel stalls on instruction fetch, profiles/r02_*).
 #ifndef MPCQ_EPC0
-#define MPCQ_EPC0 8
+#define MPCQ_EPC0 9
 #endif
-template <int NCAP> struct EnvsPerCta { static constexpr int value = TeamWarps<NCAP>::value == 1 ? MPCQ_EPC0 : 1; };
+#ifndef MPCQ_EPC1
+#define MPCQ_EPC1 1
+#endif
+template <int NCAP> struct EnvsPerCta { static constexpr int value = NCAP <= 64 ? MPCQ_EPC0 : (NCAP <= 128 ? MPCQ_EPC1 : 1); };
 
 template <class T, int NCAP, bool LGLOBAL>
-__global__ void __launch_bounds__(32 * TeamWarps<NCAP>::value * EnvsPerCta<NCAP>::value, NCAP <= 64 ? (sizeof(T) == 4 ? 8 / EnvsPerCta<NCAP>::value : 1) : 1)
+__global__ void __launch_bounds__(32 * TeamWarps<NCAP>::value * EnvsPerCta<NCAP>::value, NCAP <= 64 ? (sizeof(T) == 4 && EnvsPerCta<NCAP>::value <= 4 ? 8 / EnvsPerCta<NCAP>::value : 1) : 1)
 mpcq_solve_kernel(const __grid_constant__ Consts cs, const __grid_constant__ IO<T> io, T* gws, size_t gws_stride,
                   int ns_lo, int ns_hi, unsigned env_bytes) {
     extern __shared__ __align__(32) char smem[];
     constexpr int EPC = EnvsPerCta<NCAP>::value;
     if constexpr (EPC > 1) {
-        const int wq = threadIdx.x >> 5;
-        const int i = blockIdx.x * (blockDim.x >> 5) + wq;      // fewer warps than EPC when the workspace is large (long horizons)
+        constexpr int NT = 32 * TeamWarps<NCAP>::value;         // threads of one team (1 warp by default)
+        const int wq = threadIdx.x / NT;
+        const int i = blockIdx.x * (blockDim.x / NT) + wq;      // fewer teams than EPC when the workspace is large (long horizons)
         if (i < io.B) {
             const int b = io.perm ? io.perm[i] : i;
-            mpcq::solve_env<T, NCAP, 1>(cs, io, b, smem + (size_t)wq * env_bytes, nullptr, ns_lo, ns_hi);
+            mpcq::solve_env<T, NCAP, TeamWarps<NCAP>::value>(cs, io, b, smem + (size_t)wq * env_bytes, nullptr, ns_lo, ns_hi, 1 + wq);
         }
     } else {
         T* lg = LGLOBAL ? gws + (size_t)blockIdx.x * gws_stride : nullptr;

@@ -72,6 +72,7 @@ struct Consts {
     double tol_r_loose, tol_r_tight;   // reduced-gradient tolerances (relative to 1 + |g|_inf)
     double tol_active;     // slack tolerance of the reported constraint activity
     double tol_r_abs;      // absolute cap of the tight reduced-gradient tolerance: 2 min(R) * (force accuracy in N)
+    double tol_r_first;    // reduced-gradient tolerance of u0 = -H^-1 g (it only has to decide the first faces)
 };
 
 template <class T> struct IO {
@@ -145,11 +146,12 @@ struct Layout { size_t nd, nt, nb; int nvc, cw; };
 MPCQ_HD constexpr Layout layout(int H, int ncap, bool l_in_smem, bool with_md, int nmax, int nw) {
     Layout l{};
     l.nvc = nmax > 0 ? nmax : ncap;
-    l.cw = nw > 1 ? 256 : 128;
+    l.cw = nw > 1 ? 128 : 32;                                    // scratch of the team reductions (10 per warp) and of a 4x4 diagonal block
     const size_t nv = (size_t)l.nvc;
     l.nd = (with_md ? 288 : 0) + 72 + 9 * (size_t)H + 12 * (size_t)H + 6 * nv + nv / 3 + 1 + 12 + 40;
-    l.nt = (l_in_smem ? (size_t)ps_elems(l.nvc) : 0) + 3 * nv + nv + (size_t)l.cw + 288 + 12 + ((2 * (size_t)H * H + 3) & ~(size_t)3) +
-           4 * nv + 2 * nv + 2 * (nv + 4);
+    // (M00, M11) [288] is only read by the factorisation; u0f, tv, lam, rcf [4 nv + 8] are first written after it: one region
+    const size_t shared = 4 * nv + 8 > 288 ? 4 * nv + 8 : 288;
+    l.nt = (l_in_smem ? (size_t)ps_elems(l.nvc) : 0) + 3 * nv + nv + (size_t)l.cw + shared + 12 + ((2 * (size_t)H * H + 3) & ~(size_t)3) + 4 * nv;
     l.nb = (nv / 3 + 1) * 8 + 4 * (size_t)H + 16 + 4 * nv + 2 * 2 * (nv + 4) + 2 * (nv / 3 + 2) + 16;
     return l;
 }
@@ -191,14 +193,12 @@ MPCQ_DEV void carve(Work<T>& w, char* base, T* l_global, int H, int ncap, bool w
     w.dblk = t; t += 3 * nv;     // 12 values per block of 4 columns
     w.vec = t; t += nv;
     w.cw = t; t += l.cw;
-    w.Mf = t; t += 288;
+    w.Mf = t;                    // shares its space with u0f / tv / lam / rcf (see layout)
+    w.u0f = t; w.tv = t + nv; w.lam = t + 2 * nv; w.rcf = t + 3 * nv + 4;
+    t += 4 * nv + 8 > 288 ? 4 * nv + 8 : 288;
     w.r2 = t; t += 12;
     w.NS2 = t; t += (2 * H * H + 3) & ~3;
     w.stage = t; t += 4 * nv;
-    w.u0f = t; t += nv;
-    w.tv = t; t += nv;
-    w.lam = t; t += nv + 4;
-    w.rcf = t; t += nv + 4;
     uint8_t* b = reinterpret_cast<uint8_t*>(base + align_up(l.nd * 8, 16) + align_up(l.nt * sizeof(T), 16));
     w.fk = b; b += nv / 3 + 1;
     w.fo = b; b += nv / 3 + 1;
@@ -713,7 +713,7 @@ MPCQ_DEV bool chol_factor(const Consts& cs, Work<T>& w) {
 // "2" = rows/columns beyond J):
 //     T   = P22 L21                       (the O(n^3/3) part: one symmetric block-matvec per column block)
 //     P21 = -T M,   M = L11^-1           (the stored inverse diagonal block of the factor)
-//     P11 = M'(I + L21'T) M
+//     P11 = M'(I + L21'T) M = M'M - (L21 M)'(P21)     (the second form needs no 4x4 matrix product)
 // Storage: full symmetric, element (i, k) at P[k * ld + i] with ld = n + 1 (odd: a lane-per-row sweep down a column
 // and the transposed store along a row are both conflict-free).  P is written over the packed factor in place:
 // column block J of P lands at addresses >= j0 * ld + j0, above every factor column < j0 that is still to be read.
@@ -772,18 +772,32 @@ MPCQ_DEV void invert_factor(Work<T>& w) {
                 sg += 16;
             }
         }
-        // ---- G = L21'(-T): 10 sums over the trailing rows (every thread adds its rows, then the team reduces)
+        // ---- P21 rows: x = (-T) M, stored down the columns of J and along its rows; and the 10 sums of Y'X over the trailing
+        // rows (Y = L21 M), which give P11 = M'M - Y'X without any 4x4 matrix product: every thread adds its rows, then the
+        // team reduces
         T gp[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
         MPCQ_UNROLL
         for (int m = 0; m < NSLOT; ++m) {
             const int r = tid + NT * m;
             if (r >= j0 + 4 && r < n) {
+                const T x0 = (acc[m][0] * m00 + acc[m][1] * m10) + (acc[m][2] * m20 + acc[m][3] * m30);
+                const T x1 = acc[m][1] * m11 + acc[m][2] * m21 + acc[m][3] * m31;
+                const T x2 = acc[m][2] * m22 + acc[m][3] * m32;
+                const T x3 = acc[m][3] * m33;
+                T* pc = P + (size_t)j0 * ld + r;
+                pc[0] = x0; pc[ld] = x1; pc[2 * ld] = x2; pc[3 * ld] = x3;
+                T* pr = P + (size_t)r * ld + j0;
+                pr[0] = x0; pr[1] = x1; pr[2] = x2; pr[3] = x3;
                 T l0, l1, l2, l3;
                 load4(stage + 4 * r, l0, l1, l2, l3);
-                gp[0] += l0 * acc[m][0];
-                gp[1] += l1 * acc[m][0]; gp[2] += l1 * acc[m][1];
-                gp[3] += l2 * acc[m][0]; gp[4] += l2 * acc[m][1]; gp[5] += l2 * acc[m][2];
-                gp[6] += l3 * acc[m][0]; gp[7] += l3 * acc[m][1]; gp[8] += l3 * acc[m][2]; gp[9] += l3 * acc[m][3];
+                const T y0 = (l0 * m00 + l1 * m10) + (l2 * m20 + l3 * m30);
+                const T y1 = l1 * m11 + l2 * m21 + l3 * m31;
+                const T y2 = l2 * m22 + l3 * m32;
+                const T y3 = l3 * m33;
+                gp[0] += y0 * x0;
+                gp[1] += y1 * x0; gp[2] += y1 * x1;
+                gp[3] += y2 * x0; gp[4] += y2 * x1; gp[5] += y2 * x2;
+                gp[6] += y3 * x0; gp[7] += y3 * x1; gp[8] += y3 * x2; gp[9] += y3 * x3;
             }
         }
         MPCQ_UNROLL
@@ -805,40 +819,12 @@ MPCQ_DEV void invert_factor(Work<T>& w) {
                 gp[e] = sacc;
             }
         }
-        // ---- P21 rows: x = (-T) M, stored down the columns of J and along its rows
-        MPCQ_UNROLL
-        for (int m = 0; m < NSLOT; ++m) {
-            const int r = tid + NT * m;
-            if (r >= j0 + 4 && r < n) {
-                const T x0 = (acc[m][0] * m00 + acc[m][1] * m10) + (acc[m][2] * m20 + acc[m][3] * m30);
-                const T x1 = acc[m][1] * m11 + acc[m][2] * m21 + acc[m][3] * m31;
-                const T x2 = acc[m][2] * m22 + acc[m][3] * m32;
-                const T x3 = acc[m][3] * m33;
-                T* pc = P + (size_t)j0 * ld + r;
-                pc[0] = x0; pc[ld] = x1; pc[2 * ld] = x2; pc[3 * ld] = x3;
-                T* pr = P + (size_t)r * ld + j0;
-                pr[0] = x0; pr[1] = x1; pr[2] = x2; pr[3] = x3;
-            }
-        }
-        // ---- P11 = M'(I - G)M   (G symmetric: gp = g00 | g10 g11 | g20 g21 g22 | g30 g31 g32 g33), one thread stores it
+        // ---- P11 = M'M - Y'X (symmetric; lower entries p00 | p10 p11 | p20 p21 p22 | p30 p31 p32 p33), one thread stores it
         if (tid == 0) {
-            const T a00 = (T)1 - gp[0], a10 = -gp[1], a11 = (T)1 - gp[2], a20 = -gp[3], a21 = -gp[4], a22 = (T)1 - gp[5];
-            const T a30 = -gp[6], a31 = -gp[7], a32 = -gp[8], a33 = (T)1 - gp[9];
-            // B = A M  (M lower triangular: B[e][d] = sum_{f >= d} A[e][f] M[f][d])
-            const T b00 = a00 * m00 + a10 * m10 + a20 * m20 + a30 * m30, b01 = a10 * m11 + a20 * m21 + a30 * m31,
-                    b02 = a20 * m22 + a30 * m32, b03 = a30 * m33;
-            const T b10 = a10 * m00 + a11 * m10 + a21 * m20 + a31 * m30, b11 = a11 * m11 + a21 * m21 + a31 * m31,
-                    b12 = a21 * m22 + a31 * m32, b13 = a31 * m33;
-            const T b20 = a20 * m00 + a21 * m10 + a22 * m20 + a32 * m30, b21 = a21 * m11 + a22 * m21 + a32 * m31,
-                    b22 = a22 * m22 + a32 * m32, b23 = a32 * m33;
-            const T b30 = a30 * m00 + a31 * m10 + a32 * m20 + a33 * m30, b31 = a31 * m11 + a32 * m21 + a33 * m31,
-                    b32 = a32 * m22 + a33 * m32, b33 = a33 * m33;
-            // P11[c][d] = sum_{e >= c} M[e][c] B[e][d]
-            const T p00 = m00 * b00 + m10 * b10 + m20 * b20 + m30 * b30;
-            const T p10 = m11 * b10 + m21 * b20 + m31 * b30, p11 = m11 * b11 + m21 * b21 + m31 * b31;
-            const T p20 = m22 * b20 + m32 * b30, p21 = m22 * b21 + m32 * b31, p22 = m22 * b22 + m32 * b32;
-            const T p30 = m33 * b30, p31 = m33 * b31, p32 = m33 * b32, p33 = m33 * b33;
-            (void)b01; (void)b02; (void)b03; (void)b12; (void)b13; (void)b23;
+            const T p00 = ((m00 * m00 + m10 * m10) + (m20 * m20 + m30 * m30)) - gp[0];
+            const T p10 = (m11 * m10 + m21 * m20 + m31 * m30) - gp[1], p11 = (m11 * m11 + m21 * m21 + m31 * m31) - gp[2];
+            const T p20 = (m22 * m20 + m32 * m30) - gp[3], p21 = (m22 * m21 + m32 * m31) - gp[4], p22 = (m22 * m22 + m32 * m32) - gp[5];
+            const T p30 = m33 * m30 - gp[6], p31 = m33 * m31 - gp[7], p32 = m33 * m32 - gp[8], p33 = m33 * m33 - gp[9];
             T* pd = P + (size_t)j0 * ld + j0;
             pd[0] = p00; pd[1] = p10; pd[2] = p20; pd[3] = p30;
             pd[ld] = p10; pd[ld + 1] = p11; pd[ld + 2] = p21; pd[ld + 3] = p31;
@@ -1451,14 +1437,15 @@ MPCQ_DEV void blocked_step(const Consts& cs, Work<T>& w, double alpha, int tag) 
 // ---------------------------------------------------------------------------------------------
 // the whole path for environment b.  NCAP = slot capacity of this size class.
 template <class T, int NCAP, int NW>
-MPCQ_DEV void solve_env(const Consts& cs, const IO<T>& io, int b, char* smem, T* l_global, int ns_lo, int ns_hi) {
+MPCQ_DEV void solve_env(const Consts& cs, const IO<T>& io, int b, char* smem, T* l_global, int ns_lo, int ns_hi, int team_bar = 0) {
     MPCQ_PHASE(9);
     const int nmax = (3 * (ns_hi < NCAP / 3 ? ns_hi : NCAP / 3) + 3) & ~3;     // largest system of this size class
     const int H = cs.horizon;
     Work<T> w;
     carve(w, smem, l_global, H, NCAP, false, nmax, NW);
-    w.t.tid = NW == 1 ? wp::lane() : wp::team_tid();
+    w.t.tid = NW == 1 ? wp::lane() : wp::team_tid(32 * NW);
     w.t.nt = 32 * NW;
+    w.t.bar = team_bar;
     w.t.wid = NW == 1 ? 0 : (w.t.tid >> 5);
     const int lane = w.t.tid;                                   // thread index within the team
     // ---- K3a: stance list from the contact table (ub_fz = gait * fz_max > 0); every warp builds it redundantly
@@ -1561,7 +1548,7 @@ MPCQ_DEV void solve_env(const Consts& cs, const IO<T>& io, int b, char* smem, T*
         double rf_prev = 0.0, rf_rz = 0.0;
         // u0 is only refined to the loose tolerance: it is exact enough to decide the first faces, and in nine cases out of ten
         // it is infeasible anyway; a clean first test tightens it before it is accepted
-        double rf_tol = dmax(tol_tight, cs.tol_r_loose * gsc);
+        double rf_tol = dmax(tol_tight, cs.tol_r_first * gsc);
         double* const dcg = w.utrial;
         const double* hin = w.u;
         double* hout = w.gam;

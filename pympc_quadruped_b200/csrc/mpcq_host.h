@@ -63,6 +63,10 @@ inline bool consts_from_config(const mpcq_config& c, Consts& k, std::string& err
     k.tol_r_tight = c.tol_residual > 0 ? c.tol_residual : (f64 ? 1e-12 : 1e-9);
     k.tol_r_loose = c.tol_residual_loose > 0 ? c.tol_residual_loose : (f64 ? 1e-9 : 1e-6);
     if (k.tol_r_loose < k.tol_r_tight) k.tol_r_loose = k.tol_r_tight;
+    // u0 = -H^-1 g: the rounds build on it (u = u0 - P A' lam), so its residual is the starting residual of the fp64 finish;
+    // stopping after ONE application of the inverse (1e-4) saves a step here and costs it again there (measured: 3.96 vs 3.97
+    // operator applications per robot)
+    k.tol_r_first = k.tol_r_loose;
     k.tol_active = c.tol_active > 0 ? c.tol_active : 1e-6;
     double rmin = c.r_diag[0];
     for (int i = 1; i < 12; ++i) rmin = c.r_diag[i] < rmin ? c.r_diag[i] : rmin;

@@ -116,11 +116,12 @@ MPCQ_DEV void fma4_sub(float (&a)[4], float l, const float (&p)[4]) {
 #endif
 
 #ifdef MPCQ_HOST_EMU
-MPCQ_DEV int team_tid() { return mpcq_emu::thread_id(); }
-MPCQ_DEV void team_sync() { mpcq_emu::team_barrier(); }
+MPCQ_DEV int team_tid(int) { return mpcq_emu::thread_id(); }
+MPCQ_DEV void team_sync(int, int) { mpcq_emu::team_barrier(); }
 #else
-MPCQ_DEV int team_tid() { return threadIdx.x; }
-MPCQ_DEV void team_sync() { __syncthreads(); }
+MPCQ_DEV int team_tid(int nt) { return threadIdx.x % nt; }
+// a team is the whole CTA (barrier 0) or one of several teams sharing a CTA, each with its own named barrier (1..15)
+MPCQ_DEV void team_sync(int bar, int nt) { asm volatile("bar.sync %0, %1;" ::"r"(bar), "r"(nt) : "memory"); }
 #endif
 
 MPCQ_DEV bool any(bool p) { return ballot(p) != 0u; }
@@ -165,22 +166,23 @@ namespace team {
 
 struct Ctx {
     int tid, nt, wid;      // thread in team, team size, warp in team
+    int bar;               // hardware barrier of the team (0 = the whole CTA)
     double* red;           // [8] scratch
     int* redi;             // [8] scratch
 };
 
 MPCQ_DEV void sync(const Ctx& c) {
-    if (c.nt == 32) wp::sync(); else wp::team_sync();
+    if (c.nt == 32) wp::sync(); else wp::team_sync(c.bar, c.nt);
 }
 
 MPCQ_DEV double reduce_max(const Ctx& c, double v) {
     v = wp::reduce_max(v);
     if (c.nt == 32) return v;
     if (wp::lane() == 0) c.red[c.wid] = v;
-    wp::team_sync();
+    wp::team_sync(c.bar, c.nt);
     double r = c.red[0];
     for (int i = 1; i < (c.nt >> 5); ++i) r = (c.red[i] > r || c.red[i] != c.red[i]) ? c.red[i] : r;
-    wp::team_sync();
+    wp::team_sync(c.bar, c.nt);
     return r;
 }
 
@@ -188,10 +190,10 @@ MPCQ_DEV double reduce_sum(const Ctx& c, double v) {
     v = wp::reduce_sum(v);
     if (c.nt == 32) return v;
     if (wp::lane() == 0) c.red[c.wid] = v;
-    wp::team_sync();
+    wp::team_sync(c.bar, c.nt);
     double r = c.red[0];
     for (int i = 1; i < (c.nt >> 5); ++i) r += c.red[i];
-    wp::team_sync();
+    wp::team_sync(c.bar, c.nt);
     return r;
 }
 
@@ -199,10 +201,10 @@ MPCQ_DEV int reduce_sum(const Ctx& c, int v) {
     v = wp::reduce_sum(v);
     if (c.nt == 32) return v;
     if (wp::lane() == 0) c.redi[c.wid] = v;
-    wp::team_sync();
+    wp::team_sync(c.bar, c.nt);
     int r = c.redi[0];
     for (int i = 1; i < (c.nt >> 5); ++i) r += c.redi[i];
-    wp::team_sync();
+    wp::team_sync(c.bar, c.nt);
     return r;
 }
 
@@ -210,7 +212,7 @@ MPCQ_DEV void reduce_argmin(const Ctx& c, double& v, int& tag) {
     wp::reduce_argmin(v, tag);
     if (c.nt == 32) return;
     if (wp::lane() == 0) { c.red[c.wid] = v; c.redi[c.wid] = tag; }
-    wp::team_sync();
+    wp::team_sync(c.bar, c.nt);
     double rv = c.red[0];
     int rt = c.redi[0];
     for (int i = 1; i < (c.nt >> 5); ++i) {                  // same order as wp::reduce_argmin: a NaN wins (it must be noticed)
@@ -219,7 +221,7 @@ MPCQ_DEV void reduce_argmin(const Ctx& c, double& v, int& tag) {
         const bool o_nan = ov != ov, v_nan = rv != rv;
         if ((o_nan && !v_nan) || (o_nan == v_nan && (ov < rv || ((ov == rv || o_nan) && ot < rt)))) { rv = ov; rt = ot; }
     }
-    wp::team_sync();
+    wp::team_sync(c.bar, c.nt);
     v = rv;
     tag = rt;
 }
@@ -230,9 +232,9 @@ MPCQ_DEV bool any(const Ctx& c, bool p) { return reduce_sum(c, p ? 1 : 0) != 0; 
 MPCQ_DEV int bcast(const Ctx& c, int v) {
     if (c.nt == 32) { wp::sync(); return v; }
     if (c.tid == 0) c.redi[7] = v;
-    wp::team_sync();
+    wp::team_sync(c.bar, c.nt);
     const int r = c.redi[7];
-    wp::team_sync();
+    wp::team_sync(c.bar, c.nt);
     return r;
 }
 

@@ -19,7 +19,7 @@
 namespace mpcq_emu {
 // A team of NT threads (NT / 32 warps) runs as coroutines on one host thread, switched round-robin at every
 // collective.  Warp collectives exchange values among the 32 threads of one warp; the team barrier spans all.
-constexpr int MAXT = 256;
+constexpr int MAXT = 512;
 static ucontext_t main_ctx, ctx[MAXT];
 static int cur = 0, NT = 32;
 static uint64_t slots[2][MAXT];
