@@ -338,7 +338,10 @@ def run_ours(a):
     barrier()
     clocks = sampler.stop()
     total_ms = t_all0.elapsed_time(t_all1)
-    lat = sorted(e0.elapsed_time(e1) for e0, e1 in ev)
+    lat_seq = [e0.elapsed_time(e1) for e0, e1 in ev]
+    if os.environ.get("MPCQ_BENCH_DUMP_LAT"):
+        print("lat_ms_by_step", " ".join(f"{v:.3f}" for v in lat_seq), file=sys.stderr)
+    lat = sorted(lat_seq)
     launches_per_step = eng.last_launch_count
     tmax = torch.tensor([total_ms], dtype=torch.float64, device=dev)
     if world > 1:

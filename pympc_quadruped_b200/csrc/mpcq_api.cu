@@ -230,8 +230,11 @@ struct GaitArgs {
 
 __global__ void __launch_bounds__(128)
 mpcq_gait_kernel(GaitArgs a, float* table, double* swing_state, double* stance_state) {
-    const int b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= a.B) return;
+    __shared__ __align__(16) float stage[128 * 64];
+    const int b0 = blockIdx.x * blockDim.x;
+    const bool valid = b0 + (int)threadIdx.x < a.B;
+    const int b = valid ? b0 + (int)threadIdx.x : a.B - 1;         // idle threads shadow the last robot, their stores are masked
+    const int nvalid = a.B - b0 < (int)blockDim.x ? a.B - b0 : (int)blockDim.x;
     const int seg = a.num_segment[b], ibm = a.iterations_between_mpc;
     const int cur = a.cur_iteration[b];
     int off[4], dur[4];
@@ -239,16 +242,33 @@ mpcq_gait_kernel(GaitArgs a, float* table, double* swing_state, double* stance_s
     for (int j = 0; j < 4; ++j) { off[j] = a.offsets[4 * b + j]; dur[j] = a.durations[4 * b + j]; }
     // set_iteration (gait.py:76-79): iteration = floor(cur / ibm) % seg, phase = (cur % (ibm seg)) / (ibm seg)
     const int iteration = (cur / ibm) % seg;
-    float* t = table + (size_t)b * 4 * a.H;
-    for (int i = 0; i < a.H; ++i) {
-        const int ph = (i + 1 + iteration) % seg;
+    // the table rows are staged in shared memory (up to 16 horizon steps at a time) and written by the whole block in runs of
+    // 4 x steps consecutive floats per robot: one thread writing its own row touches 32 sectors per store instruction
+    for (int i0 = 0; i0 < a.H; i0 += 16) {
+        const int hc = a.H - i0 < 16 ? a.H - i0 : 16;
+        if (valid) {
+            float4* st4 = reinterpret_cast<float4*>(stage) + threadIdx.x * hc;
+            for (int i = 0; i < hc; ++i) {
+                const int ph = (i0 + i + 1 + iteration) % seg;
+                float v[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            int c = (ph - off[j]) % seg;
-            c += c < 0 ? seg : 0;                                  // Python's non-negative modulo (gait.py:93-97)
-            t[4 * i + j] = c < dur[j] ? 1.0f : 0.0f;
+                for (int j = 0; j < 4; ++j) {
+                    int c = (ph - off[j]) % seg;
+                    c += c < 0 ? seg : 0;                          // Python's non-negative modulo (gait.py:93-97)
+                    v[j] = c < dur[j] ? 1.0f : 0.0f;
+                }
+                st4[i] = make_float4(v[0], v[1], v[2], v[3]);
+            }
         }
+        __syncthreads();
+        const int run = 4 * hc;
+        for (int idx = threadIdx.x; idx < nvalid * run; idx += blockDim.x) {
+            const int rb = idx / run, c = idx - rb * run;
+            table[(size_t)(b0 + rb) * 4 * a.H + 4 * i0 + c] = stage[idx];
+        }
+        __syncthreads();
     }
+    if (!valid) return;
     if (!swing_state && !stance_state) return;
     const int period = ibm * seg;
     const double phase = (double)(float)((double)(cur % period) / (double)period);   // np.full(4, phase, dtype=np.float32)
@@ -291,7 +311,7 @@ __global__ void __launch_bounds__(128)
 mpcq_assemble_kernel(const __grid_constant__ AssembleArgs a, T* x0, T* yaw_out, T* x_ref) {
     // x_ref rows are staged per horizon step in shared memory and written by the whole block in runs of 13 consecutive values
     // per robot (one thread per robot writing its own 13H values touches 32 cache lines per store instruction)
-    __shared__ T stage[128 * 13];
+    __shared__ T stage[128 * 13 * (sizeof(T) == 4 ? 7 : 3)];
     const int b0 = blockIdx.x * blockDim.x;
     const bool valid = b0 + (int)threadIdx.x < a.B;
     const int b = valid ? b0 + (int)threadIdx.x : a.B - 1;         // idle threads shadow the last robot, their stores are masked
@@ -350,20 +370,26 @@ mpcq_assemble_kernel(const __grid_constant__ AssembleArgs a, T* x0, T* yaw_out, 
         if (valid) { a.rp_init[2 * b] = roll_init; a.rp_init[2 * b + 1] = pitch_init; }
         const float rc = (float)((double)st[10] * roll_init), pc = (float)((double)st[9] * pitch_init);
         float ry = (float)yawd, rx = (float)xd, rY = (float)yd;
-        for (int i = 0; i < a.H; ++i) {
-            if (i > 0) {                                        // float32 storage, float64 increments (mpc.py:163-166)
-                ry = (float)((double)ry + a.dt * rate);
-                rx = (float)((double)rx + a.dt * vx);
-                rY = (float)((double)rY + a.dt * vy);
+        // HC horizon steps per staging pass: the block then writes runs of 13 HC consecutive values per robot
+        constexpr int HC = sizeof(T) == 4 ? 7 : 3;
+        for (int i0 = 0; i0 < a.H; i0 += HC) {
+            const int hc = a.H - i0 < HC ? a.H - i0 : HC;
+            for (int ii = 0; ii < hc; ++ii) {
+                if (i0 + ii > 0) {                                  // float32 storage, float64 increments (mpc.py:163-166)
+                    ry = (float)((double)ry + a.dt * rate);
+                    rx = (float)((double)rx + a.dt * vx);
+                    rY = (float)((double)rY + a.dt * vy);
+                }
+                T* r = stage + (threadIdx.x * hc + ii) * 13;
+                r[0] = (T)rc; r[1] = (T)pc; r[2] = (T)ry; r[3] = (T)rx; r[4] = (T)rY; r[5] = (T)(float)a.com_height;
+                r[6] = (T)0; r[7] = (T)0; r[8] = (T)(float)rate; r[9] = (T)(float)vx; r[10] = (T)(float)vy; r[11] = (T)0;
+                r[12] = (T)(float)(-a.gravity);
             }
-            T* r = stage + threadIdx.x * 13;
-            r[0] = (T)rc; r[1] = (T)pc; r[2] = (T)ry; r[3] = (T)rx; r[4] = (T)rY; r[5] = (T)(float)a.com_height;
-            r[6] = (T)0; r[7] = (T)0; r[8] = (T)(float)rate; r[9] = (T)(float)vx; r[10] = (T)(float)vy; r[11] = (T)0;
-            r[12] = (T)(float)(-a.gravity);
             __syncthreads();
-            for (int idx = threadIdx.x; idx < nvalid * 13; idx += blockDim.x) {
-                const int rb = idx / 13, c = idx - 13 * rb;
-                x_ref[((size_t)(b0 + rb) * a.H + i) * 13 + c] = stage[idx];
+            const int run = 13 * hc;
+            for (int idx = threadIdx.x; idx < nvalid * run; idx += blockDim.x) {
+                const int rb = idx / run, c = idx - run * rb;
+                x_ref[((size_t)(b0 + rb) * a.H + i0) * 13 + c] = stage[idx];
             }
             __syncthreads();
         }
