@@ -242,6 +242,10 @@ mpcq_gait_kernel(GaitArgs a, float* table, double* swing_state, double* stance_s
     for (int j = 0; j < 4; ++j) { off[j] = a.offsets[4 * b + j]; dur[j] = a.durations[4 * b + j]; }
     // set_iteration (gait.py:76-79): iteration = floor(cur / ibm) % seg, phase = (cur % (ibm seg)) / (ibm seg)
     const int iteration = (cur / ibm) % seg;
+    int offm[4];                                                 // offsets reduced once (Python's non-negative modulo, gait.py:93-97)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { offm[j] = off[j] % seg; offm[j] += offm[j] < 0 ? seg : 0; }
+    int ph = (iteration + 1) % seg;                             // (i + 1 + iteration) % seg, advanced step by step
     // the table rows are staged in shared memory (up to 16 horizon steps at a time) and written by the whole block in runs of
     // 4 x steps consecutive floats per robot: one thread writing its own row touches 32 sectors per store instruction
     for (int i0 = 0; i0 < a.H; i0 += 16) {
@@ -249,21 +253,22 @@ mpcq_gait_kernel(GaitArgs a, float* table, double* swing_state, double* stance_s
         if (valid) {
             float4* st4 = reinterpret_cast<float4*>(stage) + threadIdx.x * hc;
             for (int i = 0; i < hc; ++i) {
-                const int ph = (i0 + i + 1 + iteration) % seg;
                 float v[4];
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                    int c = (ph - off[j]) % seg;
-                    c += c < 0 ? seg : 0;                          // Python's non-negative modulo (gait.py:93-97)
+                    int c = ph - offm[j];                          // both in [0, seg): one conditional add is the modulo
+                    c += c < 0 ? seg : 0;
                     v[j] = c < dur[j] ? 1.0f : 0.0f;
                 }
                 st4[i] = make_float4(v[0], v[1], v[2], v[3]);
+                ph = ph + 1 == seg ? 0 : ph + 1;
             }
         }
         __syncthreads();
         const int run = 4 * hc;
+        const unsigned inv = 0xFFFFFFFFu / (unsigned)run + 1u;   // idx / run = umulhi(idx, inv) for idx < 2^16
         for (int idx = threadIdx.x; idx < nvalid * run; idx += blockDim.x) {
-            const int rb = idx / run, c = idx - rb * run;
+            const int rb = (int)__umulhi((unsigned)idx, inv), c = idx - rb * run;
             table[(size_t)(b0 + rb) * 4 * a.H + 4 * i0 + c] = stage[idx];
         }
         __syncthreads();
@@ -387,8 +392,9 @@ mpcq_assemble_kernel(const __grid_constant__ AssembleArgs a, T* x0, T* yaw_out, 
             }
             __syncthreads();
             const int run = 13 * hc;
+            const unsigned inv = 0xFFFFFFFFu / (unsigned)run + 1u;  // idx / run = umulhi(idx, inv) for idx < 2^16
             for (int idx = threadIdx.x; idx < nvalid * run; idx += blockDim.x) {
-                const int rb = idx / run, c = idx - run * rb;
+                const int rb = (int)__umulhi((unsigned)idx, inv), c = idx - run * rb;
                 x_ref[((size_t)(b0 + rb) * a.H + i0) * 13 + c] = stage[idx];
             }
             __syncthreads();
