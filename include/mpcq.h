@@ -243,6 +243,16 @@ int mpcq_solve_host(mpcq_handle* h, int32_t B,
 int mpcq_tick_host(mpcq_handle* h, int32_t B, const double* state_cmd, const int32_t* gait_params,
                    int32_t iterations_between_mpc, int32_t first_run, void* f_out, int32_t* status);
 int mpcq_tick_reset(mpcq_handle* h);
+/*
+ * The same tick, asynchronous, on one of TWO independent pipelines (slot 0 / 1: own device buffers, own controller state, own
+ * stream): submit returns as soon as the copies and kernels are queued, wait returns when the results of that slot are in the
+ * caller's buffers.  Two groups of robots can thus alternate - the transfers and the small kernels of one group hide behind the
+ * solve of the other (e.g. two simulator instances stepping while the other one's forces are computed).  All four buffers must be
+ * page-locked (MPCQ_ERR_INVALID otherwise); mpcq_tick_host is submit + wait on slot 0.
+ */
+int mpcq_tick_host_submit(mpcq_handle* h, int32_t slot, int32_t B, const double* state_cmd, const int32_t* gait_params,
+                          int32_t iterations_between_mpc, int32_t first_run, void* f_out, int32_t* status);
+int mpcq_tick_host_wait(mpcq_handle* h, int32_t slot);
 
 /*
  * Stage entry point for parity tests: the QP data the reference would hand to the solver.

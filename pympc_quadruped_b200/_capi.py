@@ -87,6 +87,10 @@ def bind(lib: C.CDLL) -> C.CDLL:
     lib.mpcq_solve_host.restype = C.c_int
     lib.mpcq_tick_host.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]
     lib.mpcq_tick_host.restype = C.c_int
+    lib.mpcq_tick_host_submit.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]
+    lib.mpcq_tick_host_submit.restype = C.c_int
+    lib.mpcq_tick_host_wait.argtypes = [C.c_void_p, C.c_int32]
+    lib.mpcq_tick_host_wait.restype = C.c_int
     lib.mpcq_tick_reset.argtypes = [C.c_void_p]
     lib.mpcq_tick_reset.restype = C.c_int
     lib.mpcq_build_qp.argtypes = [C.c_void_p, C.c_int32] + [C.c_void_p] * 5 + [C.c_void_p] * 3 + [C.c_void_p]
@@ -115,7 +119,7 @@ def bind(lib: C.CDLL) -> C.CDLL:
 EXPORTS = ("mpcq_version", "mpcq_create", "mpcq_destroy", "mpcq_last_error", "mpcq_solve",
            "mpcq_solve_host", "mpcq_build_qp", "mpcq_assemble", "mpcq_last_launch_count", "mpcq_set_profiling",
            "mpcq_last_kernel_ms", "mpcq_measure_peaks", "mpcq_gait_tables", "mpcq_set_warm_start",
-           "mpcq_swing_targets", "mpcq_leg_torques", "mpcq_tick_host", "mpcq_tick_reset")
+           "mpcq_swing_targets", "mpcq_leg_torques", "mpcq_tick_host", "mpcq_tick_reset", "mpcq_tick_host_submit", "mpcq_tick_host_wait")
 
 _lib = None
 

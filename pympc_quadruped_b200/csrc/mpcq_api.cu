@@ -446,9 +446,9 @@ struct mpcq_handle {
     std::unordered_map<const void*, size_t> pinned_cache; // caller buffer -> bytes verified page-locked from that address (0 = pageable)
     // mpcq_tick_host: device arrays for `tick_cap` robots; the controller state (desired xy / yaw, roll / pitch compensation)
     // persists between calls
-    char* tick_dev = nullptr;
-    double* tick_state = nullptr;        // [cap,5]: xy_des 2 | yaw_des | rp_init 2
-    size_t tick_cap = 0;
+    char* tick_dev[2] = {nullptr, nullptr};
+    double* tick_state[2] = {nullptr, nullptr};   // [cap,5]: xy_des 2 | yaw_des | rp_init 2, per pipeline slot
+    size_t tick_cap[2] = {0, 0};
     // measurement hooks
     bool profiling = false;
     cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -723,8 +723,10 @@ void mpcq_destroy(mpcq_handle* h) {
     if (h->cta_hist) cudaFree(h->cta_hist);
     if (h->dev) cudaFree(h->dev);
     if (h->pin) cudaFreeHost(h->pin);
-    if (h->tick_dev) cudaFree(h->tick_dev);
-    if (h->tick_state) cudaFree(h->tick_state);
+    for (int sl = 0; sl < 2; ++sl) {
+        if (h->tick_dev[sl]) cudaFree(h->tick_dev[sl]);
+        if (h->tick_state[sl]) cudaFree(h->tick_state[sl]);
+    }
     delete h;
 }
 
@@ -1012,8 +1014,10 @@ int mpcq_solve_host(mpcq_handle* h, int32_t B, const void* x0, const void* yaw, 
     return MPCQ_OK;
 }
 
-int mpcq_tick_host(mpcq_handle* h, int32_t B, const double* state_cmd, const int32_t* gait_params, int32_t iterations_between_mpc,
-                   int32_t first_run, void* f_out, int32_t* status) {
+// slot: which of the two independent tick pipelines (device buffers, controller state, stream) the call uses; wait: synchronise
+// and finish staged copies before returning (the asynchronous entry points need page-locked buffers and skip it)
+static int tick_impl(mpcq_handle* h, int slot, bool wait, int32_t B, const double* state_cmd, const int32_t* gait_params,
+                     int32_t iterations_between_mpc, int32_t first_run, void* f_out, int32_t* status) {
     if (!h) return MPCQ_ERR_INVALID;
     if (B < 0 || iterations_between_mpc < 1 || (B > 0 && (!state_cmd || !gait_params || !f_out))) {
         h->err = "mpcq_tick_host: null pointer or iterations_between_mpc < 1";
@@ -1023,7 +1027,7 @@ int mpcq_tick_host(mpcq_handle* h, int32_t B, const double* state_cmd, const int
     if (B == 0) return MPCQ_OK;
     DeviceGuard guard(h->cfg.device);
     const size_t rs = h->real_size, H = (size_t)h->cs.horizon, b = (size_t)B;
-    cudaStream_t st = h->streams[0];
+    cudaStream_t st = h->streams[slot];
     // device layout (256-byte aligned sections): packed inputs | unpacked arrays | x0, yaw, x_ref, gait table, feet | results
     const size_t width[16] = {29 * 8, 10 * 4,                              // state_cmd, gait_params
                               4 * 8, 3 * 8, 3 * 8, 3 * 8, 3 * 8, 8,        // quat pos omega vel vdes yawrate
@@ -1033,22 +1037,22 @@ int mpcq_tick_host(mpcq_handle* h, int32_t B, const double* state_cmd, const int
     size_t off[17], cur = 0;
     for (int i = 0; i < 16; ++i) { off[i] = cur; cur += (b * width[i] + 255) / 256 * 256 + (i == 12 ? 5 * 256 : 0); }
     off[16] = cur;
-    if (b > h->tick_cap) {
+    if (b > h->tick_cap[slot]) {
         cudaStreamSynchronize(st);
-        if (h->tick_dev) cudaFree(h->tick_dev);
-        if (h->tick_state) cudaFree(h->tick_state);
-        h->tick_dev = nullptr; h->tick_state = nullptr; h->tick_cap = 0;
-        if (!cuda_ok(h, cudaMalloc(&h->tick_dev, cur), "cudaMalloc tick")) return MPCQ_ERR_CUDA;
-        if (!cuda_ok(h, cudaMalloc(&h->tick_state, b * 5 * sizeof(double)), "cudaMalloc tick state")) return MPCQ_ERR_CUDA;
-        if (!cuda_ok(h, cudaMemsetAsync(h->tick_state, 0, b * 5 * sizeof(double), st), "memset tick state")) return MPCQ_ERR_CUDA;
+        if (h->tick_dev[slot]) cudaFree(h->tick_dev[slot]);
+        if (h->tick_state[slot]) cudaFree(h->tick_state[slot]);
+        h->tick_dev[slot] = nullptr; h->tick_state[slot] = nullptr; h->tick_cap[slot] = 0;
+        if (!cuda_ok(h, cudaMalloc(&h->tick_dev[slot], cur), "cudaMalloc tick")) return MPCQ_ERR_CUDA;
+        if (!cuda_ok(h, cudaMalloc(&h->tick_state[slot], b * 5 * sizeof(double)), "cudaMalloc tick state")) return MPCQ_ERR_CUDA;
+        if (!cuda_ok(h, cudaMemsetAsync(h->tick_state[slot], 0, b * 5 * sizeof(double), st), "memset tick state")) return MPCQ_ERR_CUDA;
         cudaStreamSynchronize(st);                              // the chunks below run on several streams
-        h->tick_cap = b;
+        h->tick_cap[slot] = b;
     }
     {
-        const int rcp = ensure_perm(h, 1, b);
+        const int rcp = ensure_perm(h, 1, 2 * b);
         if (rcp != MPCQ_OK) return rcp;
     }
-    char* d = h->tick_dev;
+    char* d = h->tick_dev[slot];
     auto al = [](size_t x) { return (x + 255) / 256 * 256; };
     // page-locked caller buffers are DMA sources / are written in place by the kernels; pageable ones go through staging
     const size_t need_pin = al(b * width[0]) + al(b * width[1]) + al(b * width[13]) + al(b * width[14]);
@@ -1065,15 +1069,16 @@ int mpcq_tick_host(mpcq_handle* h, int32_t B, const double* state_cmd, const int
     // hide behind the solve of the other, and the solve kernels of neighbouring chunks fill each other's tails
     bool any_global = false;
     for (int ci = 0; ci < h->ncls; ++ci) any_global = any_global || h->lglobal[ci];
-    int nchunk = any_global ? 1 : (B >= 16384 ? kHostStreams : (B >= 8192 ? 2 : 1));   // measured at 4 096 robots: 1 / 2 / 3 chunks = 585 / 608 / 642 us
+    int nchunk = (any_global || !wait) ? 1 : (B >= 16384 ? kHostStreams : (B >= 8192 ? 2 : 1));   // measured at 4 096 robots: 1 / 2 / 3 chunks = 585 / 608 / 642 us
     if (const char* ov = getenv("MPCQ_HOST_CHUNKS")) {          // experiments only
         const int v = atoi(ov);
-        if (v >= 1 && v <= kHostStreams && !any_global) nchunk = v;
+        if (v >= 1 && v <= kHostStreams && !any_global && wait) nchunk = v;
     }
     const void* src[2] = {state_cmd, gait_params};
     bool src_pinned[2];
     size_t poffs[2] = {0, al(b * width[0])};
     for (int i = 0; i < 2; ++i) src_pinned[i] = host_range_pinned(h, src[i], b * width[i]);
+    if (!wait && (!src_pinned[0] || !src_pinned[1])) { h->err = "mpcq_tick_host_submit needs page-locked buffers"; return MPCQ_ERR_INVALID; }
     // results: in place into page-locked caller buffers, else staged
     void* dst[2] = {f_out, status};
     char* dres[2] = {d + off[13], d + off[14]};
@@ -1081,6 +1086,7 @@ int mpcq_tick_host(mpcq_handle* h, int32_t B, const double* state_cmd, const int
     for (int i = 0; i < 2; ++i) {
         if (!dst[i]) continue;
         dst_pinned[i] = host_range_pinned(h, dst[i], b * width[13 + i]);
+        if (!wait && !dst_pinned[i]) { h->err = "mpcq_tick_host_submit needs page-locked buffers"; return MPCQ_ERR_INVALID; }
         if (!h->direct_results || !dst_pinned[i]) continue;
         void* dptr = nullptr;
         if (cudaHostGetDevicePointer(&dptr, dst[i], 0) == cudaSuccess) { dres[i] = static_cast<char*>(dptr); direct[i] = true; }
@@ -1097,12 +1103,12 @@ int mpcq_tick_host(mpcq_handle* h, int32_t B, const double* state_cmd, const int
     char* feet = yaw + al(b * rs);
     char* xref = feet + al(b * 12 * rs);
     char* table = xref + al(b * 13 * H * rs);
-    double* cst = h->tick_state;
+    double* cst = h->tick_state[slot];
     int launches = 0;
     for (int c = 0; c < nchunk; ++c) {
         const size_t lo = b * c / nchunk, hi = b * (c + 1) / nchunk, nb = hi - lo;
         if (nb == 0) continue;
-        cudaStream_t st = h->streams[c % kHostStreams];
+        cudaStream_t st = h->streams[(slot + c) % kHostStreams];
         for (int i = 0; i < 2; ++i) {
             const char* from = static_cast<const char*>(src[i]) + lo * width[i];
             if (!src_pinned[i]) { memcpy(h->pin + poffs[i] + lo * width[i], from, nb * width[i]); from = h->pin + poffs[i] + lo * width[i]; }
@@ -1127,7 +1133,7 @@ int mpcq_tick_host(mpcq_handle* h, int32_t B, const double* state_cmd, const int
             mpcq_assemble_kernel<float><<<grid, 128, 0, st>>>(aa, reinterpret_cast<float*>(cx0), reinterpret_cast<float*>(cyaw), reinterpret_cast<float*>(cxref));
         if (!cuda_ok(h, cudaGetLastError(), "mpcq_tick_host launch")) return fail(MPCQ_ERR_CUDA);
         const int rc = solve_impl(h, nbi, cx0, cyaw, cfeet, ctab, cxref, dres[0] + lo * width[13], nullptr, nullptr, nullptr,
-                                  status ? reinterpret_cast<int32_t*>(dres[1] + lo * width[14]) : nullptr, nullptr, 1, lo, st, c % kHostStreams);
+                                  status ? reinterpret_cast<int32_t*>(dres[1] + lo * width[14]) : nullptr, nullptr, 1, slot * b + lo, st, (slot + c) % kHostStreams);
         if (rc != MPCQ_OK) return fail(rc);
         launches += h->last_launches + 3;
         for (int i = 0; i < 2; ++i) {
@@ -1136,21 +1142,42 @@ int mpcq_tick_host(mpcq_handle* h, int32_t B, const double* state_cmd, const int
             if (!cuda_ok(h, cudaMemcpyAsync(to, dres[i] + lo * width[13 + i], nb * width[13 + i], cudaMemcpyDeviceToHost, st), "D2H")) return fail(MPCQ_ERR_CUDA);
         }
     }
+    h->last_launches = launches;
+    if (!wait) return MPCQ_OK;
     for (int c = 0; c < nchunk && c < kHostStreams; ++c)
-        if (!cuda_ok(h, cudaStreamSynchronize(h->streams[c]), "mpcq_tick_host sync")) return fail(MPCQ_ERR_CUDA);
+        if (!cuda_ok(h, cudaStreamSynchronize(h->streams[(slot + c) % kHostStreams]), "mpcq_tick_host sync")) return fail(MPCQ_ERR_CUDA);
     for (int i = 0; i < 2; ++i)
         if (dst[i] && !direct[i] && !dst_pinned[i]) memcpy(dst[i], pres + (i ? al(b * width[13]) : 0), b * width[13 + i]);
     h->last_launches = launches;
     return MPCQ_OK;
 }
 
+int mpcq_tick_host(mpcq_handle* h, int32_t B, const double* state_cmd, const int32_t* gait_params, int32_t iterations_between_mpc,
+                   int32_t first_run, void* f_out, int32_t* status) {
+    return tick_impl(h, 0, true, B, state_cmd, gait_params, iterations_between_mpc, first_run, f_out, status);
+}
+
+int mpcq_tick_host_submit(mpcq_handle* h, int32_t slot, int32_t B, const double* state_cmd, const int32_t* gait_params,
+                          int32_t iterations_between_mpc, int32_t first_run, void* f_out, int32_t* status) {
+    if (!h) return MPCQ_ERR_INVALID;
+    if (slot < 0 || slot > 1) { h->err = "mpcq_tick_host_submit: slot must be 0 or 1"; return MPCQ_ERR_INVALID; }
+    return tick_impl(h, slot, false, B, state_cmd, gait_params, iterations_between_mpc, first_run, f_out, status);
+}
+
+int mpcq_tick_host_wait(mpcq_handle* h, int32_t slot) {
+    if (!h) return MPCQ_ERR_INVALID;
+    if (slot < 0 || slot > 1) { h->err = "mpcq_tick_host_wait: slot must be 0 or 1"; return MPCQ_ERR_INVALID; }
+    DeviceGuard guard(h->cfg.device);
+    return cuda_ok(h, cudaStreamSynchronize(h->streams[slot]), "mpcq_tick_host_wait") ? MPCQ_OK : MPCQ_ERR_CUDA;
+}
+
 int mpcq_tick_reset(mpcq_handle* h) {
     if (!h) return MPCQ_ERR_INVALID;
-    if (!h->tick_state) return MPCQ_OK;
     DeviceGuard guard(h->cfg.device);
-    // on the stream mpcq_tick_host works on: ordered with the ticks before and after without a host synchronisation
-    for (int i = 1; i < kHostStreams; ++i) cudaStreamSynchronize(h->streams[i]);
-    return cuda_ok(h, cudaMemsetAsync(h->tick_state, 0, h->tick_cap * 5 * sizeof(double), h->streams[0]), "mpcq_tick_reset") ? MPCQ_OK : MPCQ_ERR_CUDA;
+    for (int i = 0; i < kHostStreams; ++i) cudaStreamSynchronize(h->streams[i]);
+    for (int sl = 0; sl < 2; ++sl)
+        if (h->tick_state[sl] && !cuda_ok(h, cudaMemset(h->tick_state[sl], 0, h->tick_cap[sl] * 5 * sizeof(double)), "mpcq_tick_reset")) return MPCQ_ERR_CUDA;
+    return MPCQ_OK;
 }
 
 int mpcq_last_launch_count(const mpcq_handle* h) { return h ? h->last_launches : 0; }

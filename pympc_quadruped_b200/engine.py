@@ -179,6 +179,17 @@ class MpcqEngine:
         self._err(rc, "mpcq_tick_host")
         return res
 
+    def tick_submit(self, slot: int, state_cmd, gait_params, iterations_between_mpc: int, first_run, out):
+        """Asynchronous `tick_host` on pipeline `slot` (0 / 1): page-locked numpy arrays only (`out` = dict(forces, status)),
+        returns once the work is queued; `tick_wait(slot)` returns when `out` holds the results."""
+        B = state_cmd.shape[0]
+        p = lambda a: a.ctypes.data_as(C.c_void_p)
+        self._err(self.lib.mpcq_tick_host_submit(self._h, int(slot), B, p(state_cmd), p(gait_params), int(iterations_between_mpc),
+                                                 int(first_run), p(out["forces"]), p(out["status"])), "mpcq_tick_host_submit")
+
+    def tick_wait(self, slot: int):
+        self._err(self.lib.mpcq_tick_host_wait(self._h, int(slot)), "mpcq_tick_host_wait")
+
     def tick_reset(self):
         self._err(self.lib.mpcq_tick_reset(self._h), "mpcq_tick_reset")
 

@@ -173,6 +173,19 @@ def test_tick_host_equals_the_controller_on_device_tensors(dtype):
     assert float(rp.abs().max()) < 0.2                              # restarted from 0, one update
     r2 = eng.tick_host(_tick_inputs(st, lo, hi), gp, ibm, first_run=2, validate=False)
     assert np.all(r2["status"] & _capi.ST_VERIFIED)
+    # the asynchronous two-slot form (page-locked buffers): both slots in flight at once, same forces as the synchronous call
+    pin = lambda a: torch.empty(a.shape, dtype=torch.as_tensor(a).dtype, pin_memory=True).copy_(torch.as_tensor(a)).numpy()
+    sc_a, sc_b, gp_p = pin(_tick_inputs(st, lo, hi)), pin(_tick_inputs(st, 0, B)), pin(gp)
+    outs = [dict(forces=torch.empty((B, 12), dtype=dtype, pin_memory=True).numpy(), status=torch.empty((B,), dtype=torch.int32, pin_memory=True).numpy())
+            for _ in range(2)]
+    eng.tick_submit(0, sc_a, gp_p, ibm, 2, outs[0])
+    eng.tick_submit(1, sc_b, gp_p, ibm, 2, outs[1])
+    eng.tick_wait(1); eng.tick_wait(0)
+    assert np.array_equal(outs[0]["forces"], r2["forces"]) and np.all(outs[1]["status"] & _capi.ST_VERIFIED)
+    rb = eng.tick_host(_tick_inputs(st, 0, B), gp, ibm, first_run=2, validate=False)
+    assert np.array_equal(outs[1]["forces"], rb["forces"])
+    with pytest.raises(RuntimeError):
+        eng.tick_submit(0, _tick_inputs(st, 0, B), gp_p, ibm, 2, outs[0])            # pageable input
     with pytest.raises(ValueError):
         eng.tick_host(np.zeros((4, 28)), np.ones((4, 10), np.int32), ibm)
     with pytest.raises(ValueError):

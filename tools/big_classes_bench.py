@@ -24,3 +24,5 @@ if 'stand10' in which: bench(A1Config,10,4096,'mixed',(Gait.STANDING,),torch.flo
 if 'trot30' in which: bench(A1Config,30,4096,'mixed',(Gait.TROTTING10,),torch.float32)
 if 'stand30' in which: bench(A1Config,30,1024,'mixed',(Gait.STANDING,),torch.float32,reps=2)
 if 'trot30f64' in which: bench(A1Config,30,1024,'mixed',(Gait.TROTTING10,),torch.float64,reps=2)
+if 'trot16' in which: bench(A1Config,16,4096,'mixed',(Gait.TROTTING16,),torch.float32)
+if 'pace10' in which: bench(A1Config,10,4096,'mixed',(Gait.PACING10,),torch.float32)
