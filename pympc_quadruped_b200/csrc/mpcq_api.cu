@@ -630,7 +630,7 @@ cudaError_t configure(mpcq_handle* h) {
     if (e != cudaSuccess) return e;
     if (gws_elems) {
         h->gws_stride = gws_elems;
-        e = cudaMalloc(&h->gws, gws_elems * sizeof(T) * kGlobalCtas);
+        e = cudaMalloc(&h->gws, (gws_elems * kGlobalCtas + 4 * 512) * sizeof(T));   // slack: invert_factor reads up to 3 columns past a region
     }
     return e;
 }

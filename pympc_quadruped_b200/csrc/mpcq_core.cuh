@@ -581,15 +581,21 @@ MPCQ_DEV bool chol_factor(const Consts& cs, Work<T>& w) {
                 }
             } else {
             T pa[4][4], la[4][NSLOT], pb[4][4], lb[4][NSLOT];   // two register sets, used alternately (no copies)
-            auto fetch = [&](T (&p)[4][4], T (&l)[4][NSLOT], const T* cc, int st) {
+            // two running pointers (pivot rows, own rows) stepped by the column stride: one add each per column instead of
+            // an index computation per load - the multiply-add pipe also executes the integer multiply-adds
+            const T* pk = L + k0;
+            const T* pr = L + row0;
+            int st = n;
+            auto fetch = [&](T (&p)[4][4], T (&l)[4][NSLOT]) {
                 MPCQ_UNROLL
                 for (int t = 0; t < 4; ++t) {
-                    load4(cc + k0, p[t][0], p[t][1], p[t][2], p[t][3]);
+                    load4(pk, p[t][0], p[t][1], p[t][2], p[t][3]);
                     MPCQ_UNROLL
                     for (int m = 0; m < NSLOT; ++m)
-                        if (m >= m0) l[t][m] = cc[row0 + RSTEP * m];
-                    cc += st;
+                        if (m >= m0) l[t][m] = pr[RSTEP * m];
+                    pk += st; pr += st;
                 }
+                pk -= 4; pr -= 4; st -= 4;                      // next group of 4 columns: 4 rows shorter
             };
             auto apply = [&](const T (&p)[4][4], const T (&l)[4][NSLOT]) {
                 MPCQ_UNROLL
@@ -601,20 +607,16 @@ MPCQ_DEV bool chol_factor(const Consts& cs, Work<T>& w) {
                     }
                 }
             };
-            if (ng > 0) fetch(pa, la, col, stride);
+            if (ng > 0) fetch(pa, la);
             int g = 0;
             for (; g + 1 < ng; g += 2) {
-                col += 4 * stride - 4; stride -= 4;
-                fetch(pb, lb, col, stride);
+                fetch(pb, lb);
                 apply(pa, la);
-                col += 4 * stride - 4; stride -= 4;
-                if (g + 2 < ng) fetch(pa, la, col, stride);
+                fetch(pa, la);                                // past the last group this reads the panel's own (unwritten) columns: unused, but the body stays one basic block
                 apply(pb, lb);
             }
-            if (g < ng) {
-                apply(pa, la);
-                col += 4 * stride - 4; stride -= 4;
-            }
+            if (g < ng) apply(pa, la);
+            col = L + colbase(k0, n);
             }
             colg = col;                                       // == L + colbase(k0, n)
         }
@@ -753,7 +755,41 @@ MPCQ_DEV void invert_factor(Work<T>& w) {
         MPCQ_UNROLL
         for (int m = 0; m < NSLOT; ++m) { acc[m][0] = acc[m][1] = acc[m][2] = acc[m][3] = (T)0; }
         const int m0 = (j0 + 4) / NT;                          // slots below hold no row of the trailing block
-        {
+        if constexpr (NW > 1 && NSLOT == 2) {
+            // A team of lone warps (one per scheduler): nothing else hides the shared-memory pipe, which takes 4 cycles per
+            // load instruction of a warp.  Two register sets, the loads of group g + 1 issued between the multiply-adds of
+            // group g, no branch inside the body (the last fetch reads one group past the end: columns of the Schur block or
+            // the arrays behind the factor region, never used).
+            const T* pc = P + (size_t)(j0 + 4) * ld + tid;
+            const T* sg = stage + 4 * (j0 + 4);
+            T la[4][4], pa[4][2], lb[4][4], pb[4][2];
+            auto fetch = [&](T (&l)[4][4], T (&p)[4][2], const T* pcc, const T* sgg) {
+                MPCQ_UNROLL
+                for (int t = 0; t < 4; ++t) {
+                    load4(sgg + 4 * t, l[t][0], l[t][1], l[t][2], l[t][3]);
+                    p[t][0] = pcc[t * ld]; p[t][1] = pcc[t * ld + NT];
+                }
+            };
+            auto apply = [&](const T (&l)[4][4], const T (&p)[4][2]) {
+                MPCQ_UNROLL
+                for (int t = 0; t < 4; ++t) {
+                    if (m0 == 0) wp::fma4_sub(acc[0], p[t][0], l[t]);
+                    wp::fma4_sub(acc[1], p[t][1], l[t]);
+                }
+            };
+            const int ng = (n - j0 - 4) >> 2;
+            fetch(la, pa, pc, sg);
+            int g = 0;
+            MPCQ_NOUNROLL
+            for (; g + 1 < ng; g += 2) {
+                fetch(lb, pb, pc + 4 * ld, sg + 16);
+                apply(la, pa);
+                pc += 8 * ld; sg += 32;
+                fetch(la, pa, pc, sg);
+                apply(lb, pb);
+            }
+            if (g < ng) apply(la, pa);
+        } else {
             const T* pc = P + (size_t)(j0 + 4) * ld + tid;
             const T* sg = stage + 4 * (j0 + 4);
             MPCQ_UNROLL2                                         // two groups in flight: the loads of one hide behind the other's multiply-adds
