@@ -732,7 +732,10 @@ def run_ours(a):
                          "executed_tflops_model": exec_flops / 1e12, "frac_executed": (exec_flops / 1e12 / fma_peak) if fma_peak else None,
                          "note": "algorithmic = 2 n^2 k build + n^3/3 Cholesky + 2 n^2 per solve pair x rounds (n = 12H, k = 13H); executed = "
                                  "what the kernel does per robot (closed-form Hessian on the stance slots only, n_red^3/6 Cholesky + n_red^3/3 "
-                                 "inverse once, Schur rounds not counted)"},
+                                 "inverse once, Schur rounds not counted)"
+                                 + ("; frac > 1: the kernel does not execute the dense formulation's flops (at long horizons the stance-only "
+                                    "system is half the size, an eighth of the cubic work) - frac_executed is the honest occupancy of the pipe"
+                                    if fma_peak and algo_tflops > fma_peak else "")},
             "roofline_hbm": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                              "traffic": traffic, "algorithmic_bytes_per_launch": ALGO_BYTES(H) * (rs // 4) * B, "peak_source": peak_src,
                              "note": "not the binding roofline: the path moves 732 B per solve (H = 10, f32) and re-reads nothing"},

@@ -27,4 +27,5 @@ def probe(idx,label):
     for n,c in zip(names,v): print(f'   {n:20s} {c/ne:9.0f} cycles/env  {100*c/tot:5.1f}%')
 sel=np.flatnonzero(it==int(np.median(it)))[:1]
 probe(sel,'one env alone (median rounds)')
+probe(np.argsort(-it)[:1],'the env with the most rounds, alone')
 probe(np.arange(BB),'whole batch under load')
