@@ -248,7 +248,10 @@ int mpcq_tick_reset(mpcq_handle* h);
  * stream): submit returns as soon as the copies and kernels are queued, wait returns when the results of that slot are in the
  * caller's buffers.  Two groups of robots can thus alternate - the transfers and the small kernels of one group hide behind the
  * solve of the other (e.g. two simulator instances stepping while the other one's forces are computed).  All four buffers must be
- * page-locked (MPCQ_ERR_INVALID otherwise); mpcq_tick_host is submit + wait on slot 0.
+ * page-locked (MPCQ_ERR_INVALID otherwise); mpcq_tick_host is submit + wait on slot 0.  The two slots may carry different B.
+ * The caller's buffers of a slot belong to the library from submit to wait.  Submitting to a slot that is still in flight waits
+ * for it first; the synchronous host entry points (mpcq_tick_host, mpcq_solve_host) and mpcq_tick_reset first finish whatever is
+ * in flight on either slot.
  */
 int mpcq_tick_host_submit(mpcq_handle* h, int32_t slot, int32_t B, const double* state_cmd, const int32_t* gait_params,
                           int32_t iterations_between_mpc, int32_t first_run, void* f_out, int32_t* status);

@@ -449,6 +449,7 @@ struct mpcq_handle {
     char* tick_dev[2] = {nullptr, nullptr};
     double* tick_state[2] = {nullptr, nullptr};   // [cap,5]: xy_des 2 | yaw_des | rp_init 2, per pipeline slot
     size_t tick_cap[2] = {0, 0};
+    bool tick_inflight[2] = {false, false};        // submitted, not yet waited for
     // measurement hooks
     bool profiling = false;
     cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -746,6 +747,13 @@ static int ensure_perm(mpcq_handle* h, int slot, size_t envs) {
     return MPCQ_OK;
 }
 
+// the synchronous host entry points share staging, launch-order buffers and streams with the asynchronous tick slots:
+// whatever was submitted and not yet waited for is finished first (its results are then complete in the caller's buffers)
+static void drain_ticks(mpcq_handle* h) {
+    for (int sl = 0; sl < 2; ++sl)
+        if (h->tick_inflight[sl]) { cudaStreamSynchronize(h->streams[sl]); h->tick_inflight[sl] = false; }
+}
+
 // solve envs [0,B) of the given arrays; `slot`/`off` select the region of the launch-order buffers this call may use
 static int solve_impl(mpcq_handle* h, int32_t B, const void* x0, const void* yaw, const void* r_feet, const float* gait,
                       const void* x_ref, void* f_out, void* u_full, int32_t* iters, double* resid, int32_t* status,
@@ -919,6 +927,7 @@ int mpcq_solve_host(mpcq_handle* h, int32_t B, const void* x0, const void* yaw, 
     h->last_launches = 0;
     if (B == 0) return MPCQ_OK;
     DeviceGuard guard(h->cfg.device);
+    drain_ticks(h);
     const size_t rs = h->real_size, H = (size_t)h->cs.horizon, b = (size_t)B;
     // per-environment byte widths of the 5 inputs and 6 outputs
     const size_t width[11] = {13 * rs, yaw ? rs : 0, 12 * rs, 4 * H * 4, 13 * H * rs,
@@ -1026,6 +1035,8 @@ static int tick_impl(mpcq_handle* h, int slot, bool wait, int32_t B, const doubl
     h->last_launches = 0;
     if (B == 0) return MPCQ_OK;
     DeviceGuard guard(h->cfg.device);
+    if (wait) drain_ticks(h);                                   // the synchronous call may use several streams
+    else if (h->tick_inflight[slot]) { cudaStreamSynchronize(h->streams[slot]); h->tick_inflight[slot] = false; }   // submitted twice
     const size_t rs = h->real_size, H = (size_t)h->cs.horizon, b = (size_t)B;
     cudaStream_t st = h->streams[slot];
     // device layout (256-byte aligned sections): packed inputs | unpacked arrays | x0, yaw, x_ref, gait table, feet | results
@@ -1049,9 +1060,10 @@ static int tick_impl(mpcq_handle* h, int slot, bool wait, int32_t B, const doubl
         h->tick_cap[slot] = b;
     }
     {
-        const int rcp = ensure_perm(h, 1, 2 * b);
+        const int rcp = ensure_perm(h, 1, 2 * b);                // each slot owns one half of the launch-order buffers
         if (rcp != MPCQ_OK) return rcp;
     }
+    const size_t perm_off = slot ? h->perm_cap[1] / 2 : 0;
     char* d = h->tick_dev[slot];
     auto al = [](size_t x) { return (x + 255) / 256 * 256; };
     // page-locked caller buffers are DMA sources / are written in place by the kernels; pageable ones go through staging
@@ -1093,7 +1105,7 @@ static int tick_impl(mpcq_handle* h, int slot, bool wait, int32_t B, const doubl
         else cudaGetLastError();
     }
     char* pres = h->pin + al(b * width[0]) + al(b * width[1]);
-    auto fail = [&](int code) { for (int i = 0; i < kHostStreams; ++i) cudaStreamSynchronize(h->streams[i]); return code; };
+    auto fail = [&](int code) { for (int i = 0; i < kHostStreams; ++i) cudaStreamSynchronize(h->streams[i]); h->tick_inflight[0] = h->tick_inflight[1] = false; return code; };
     TickArrays ta{reinterpret_cast<double*>(d + off[2]), reinterpret_cast<double*>(d + off[3]), reinterpret_cast<double*>(d + off[4]),
                   reinterpret_cast<double*>(d + off[5]), reinterpret_cast<double*>(d + off[6]), reinterpret_cast<double*>(d + off[7]),
                   reinterpret_cast<int32_t*>(d + off[8]), reinterpret_cast<int32_t*>(d + off[9]), reinterpret_cast<int32_t*>(d + off[10]),
@@ -1133,7 +1145,7 @@ static int tick_impl(mpcq_handle* h, int slot, bool wait, int32_t B, const doubl
             mpcq_assemble_kernel<float><<<grid, 128, 0, st>>>(aa, reinterpret_cast<float*>(cx0), reinterpret_cast<float*>(cyaw), reinterpret_cast<float*>(cxref));
         if (!cuda_ok(h, cudaGetLastError(), "mpcq_tick_host launch")) return fail(MPCQ_ERR_CUDA);
         const int rc = solve_impl(h, nbi, cx0, cyaw, cfeet, ctab, cxref, dres[0] + lo * width[13], nullptr, nullptr, nullptr,
-                                  status ? reinterpret_cast<int32_t*>(dres[1] + lo * width[14]) : nullptr, nullptr, 1, slot * b + lo, st, (slot + c) % kHostStreams);
+                                  status ? reinterpret_cast<int32_t*>(dres[1] + lo * width[14]) : nullptr, nullptr, 1, perm_off + lo, st, (slot + c) % kHostStreams);
         if (rc != MPCQ_OK) return fail(rc);
         launches += h->last_launches + 3;
         for (int i = 0; i < 2; ++i) {
@@ -1143,7 +1155,7 @@ static int tick_impl(mpcq_handle* h, int slot, bool wait, int32_t B, const doubl
         }
     }
     h->last_launches = launches;
-    if (!wait) return MPCQ_OK;
+    if (!wait) { h->tick_inflight[slot] = true; return MPCQ_OK; }
     for (int c = 0; c < nchunk && c < kHostStreams; ++c)
         if (!cuda_ok(h, cudaStreamSynchronize(h->streams[(slot + c) % kHostStreams]), "mpcq_tick_host sync")) return fail(MPCQ_ERR_CUDA);
     for (int i = 0; i < 2; ++i)
@@ -1168,6 +1180,7 @@ int mpcq_tick_host_wait(mpcq_handle* h, int32_t slot) {
     if (!h) return MPCQ_ERR_INVALID;
     if (slot < 0 || slot > 1) { h->err = "mpcq_tick_host_wait: slot must be 0 or 1"; return MPCQ_ERR_INVALID; }
     DeviceGuard guard(h->cfg.device);
+    h->tick_inflight[slot] = false;
     return cuda_ok(h, cudaStreamSynchronize(h->streams[slot]), "mpcq_tick_host_wait") ? MPCQ_OK : MPCQ_ERR_CUDA;
 }
 
@@ -1175,6 +1188,7 @@ int mpcq_tick_reset(mpcq_handle* h) {
     if (!h) return MPCQ_ERR_INVALID;
     DeviceGuard guard(h->cfg.device);
     for (int i = 0; i < kHostStreams; ++i) cudaStreamSynchronize(h->streams[i]);
+    h->tick_inflight[0] = h->tick_inflight[1] = false;
     for (int sl = 0; sl < 2; ++sl)
         if (h->tick_state[sl] && !cuda_ok(h, cudaMemset(h->tick_state[sl], 0, h->tick_cap[sl] * 5 * sizeof(double)), "mpcq_tick_reset")) return MPCQ_ERR_CUDA;
     return MPCQ_OK;

@@ -46,6 +46,7 @@ class MpcqEngine:
         cfg = _capi.make_config(self.consts, _capi.MPCQ_F64 if dtype == torch.float64 else _capi.MPCQ_F32,
                                 self.device.index or 0, **knobs)
         self._h = C.c_void_p()
+        self._tick_refs = {}                                  # buffers of asynchronous ticks in flight, per slot
         rc = self.lib.mpcq_create(C.byref(cfg), C.byref(self._h))
         if rc != 0:
             msg = f"mpcq_create failed ({rc}): {self.lib.mpcq_last_error(None).decode()}"
@@ -181,14 +182,22 @@ class MpcqEngine:
 
     def tick_submit(self, slot: int, state_cmd, gait_params, iterations_between_mpc: int, first_run, out):
         """Asynchronous `tick_host` on pipeline `slot` (0 / 1): page-locked numpy arrays only (`out` = dict(forces, status)),
-        returns once the work is queued; `tick_wait(slot)` returns when `out` holds the results."""
+        returns once the work is queued; `tick_wait(slot)` returns when `out` holds the results.  The arrays are kept alive
+        by the engine until then."""
+        rt = np.float64 if self.dtype == torch.float64 else np.float32
         B = state_cmd.shape[0]
+        for name, a, shape, dt in (("state_cmd", state_cmd, (B, 29), np.float64), ("gait_params", gait_params, (B, 10), np.int32),
+                                   ("out['forces']", out["forces"], (B, 12), rt), ("out['status']", out["status"], (B,), np.int32)):
+            if not isinstance(a, np.ndarray) or a.shape != shape or a.dtype != dt or not a.flags.c_contiguous:
+                raise ValueError(f"{name}: expected a C-contiguous {np.dtype(dt).name} array of shape {shape}")
         p = lambda a: a.ctypes.data_as(C.c_void_p)
         self._err(self.lib.mpcq_tick_host_submit(self._h, int(slot), B, p(state_cmd), p(gait_params), int(iterations_between_mpc),
                                                  int(first_run), p(out["forces"]), p(out["status"])), "mpcq_tick_host_submit")
+        self._tick_refs[int(slot)] = (state_cmd, gait_params, out["forces"], out["status"])
 
     def tick_wait(self, slot: int):
         self._err(self.lib.mpcq_tick_host_wait(self._h, int(slot)), "mpcq_tick_host_wait")
+        self._tick_refs.pop(int(slot), None)
 
     def tick_reset(self):
         self._err(self.lib.mpcq_tick_reset(self._h), "mpcq_tick_reset")

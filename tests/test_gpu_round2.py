@@ -186,6 +186,16 @@ def test_tick_host_equals_the_controller_on_device_tensors(dtype):
     assert np.array_equal(outs[1]["forces"], rb["forces"])
     with pytest.raises(RuntimeError):
         eng.tick_submit(0, _tick_inputs(st, 0, B), gp_p, ibm, 2, outs[0])            # pageable input
+    # different batch sizes on the two slots, and a synchronous call while both are in flight (it finishes them first)
+    Bs = B // 2 + 1
+    small = dict(forces=torch.empty((Bs, 12), dtype=dtype, pin_memory=True).numpy(), status=torch.empty((Bs,), dtype=torch.int32, pin_memory=True).numpy())
+    for a_ in (outs[0]["forces"], small["forces"]): a_[:] = 0
+    eng.tick_submit(0, sc_a, gp_p, ibm, 2, outs[0])
+    eng.tick_submit(1, pin(_tick_inputs(st, 0, B)[:Bs]), pin(gp[:Bs]), ibm, 2, small)
+    r3 = eng.tick_host(_tick_inputs(st, lo, hi), gp, ibm, first_run=2, validate=False)
+    assert np.array_equal(outs[0]["forces"], r2["forces"]) and np.array_equal(small["forces"], rb["forces"][:Bs])
+    assert np.array_equal(r3["forces"], r2["forces"])
+    eng.tick_wait(0); eng.tick_wait(1)
     with pytest.raises(ValueError):
         eng.tick_host(np.zeros((4, 28)), np.ones((4, 10), np.int32), ibm)
     with pytest.raises(ValueError):
