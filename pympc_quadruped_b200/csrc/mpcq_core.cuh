@@ -148,7 +148,7 @@ MPCQ_HD constexpr Layout layout(int H, int ncap, bool l_in_smem, bool with_md, i
     l.nvc = nmax > 0 ? nmax : ncap;
     l.cw = nw > 1 ? 128 : 32;                                    // scratch of the team reductions (10 per warp) and of a 4x4 diagonal block
     const size_t nv = (size_t)l.nvc;
-    l.nd = (with_md ? 288 : 0) + 72 + 9 * (size_t)H + 12 * (size_t)H + 6 * nv + nv / 3 + 1 + 12 + 40;
+    l.nd = (with_md ? 288 : 0) + 72 + 9 * (size_t)H + 12 * (size_t)H + 6 * nv + nv / 3 + 1 + 24 + 40;   // 24 = team scratch: 16 doubles + 16 ints (one per warp, teams of up to 16 warps)
     // (M00, M11) [288] is only read by the factorisation; u0f, tv, lam, rcf [4 nv + 8] are first written after it: one region
     const size_t shared = 4 * nv + 8 > 288 ? 4 * nv + 8 : 288;
     l.nt = (l_in_smem ? (size_t)ps_elems(l.nvc) : 0) + 3 * nv + nv + (size_t)l.cw + shared + 12 + ((2 * (size_t)H * H + 3) & ~(size_t)3) + 4 * nv;
@@ -178,8 +178,8 @@ MPCQ_DEV void carve(Work<T>& w, char* base, T* l_global, int H, int ncap, bool w
     w.utrial = d; d += nv;
     w.hd = d; d += nv;
     w.fmax = d; d += nv / 3 + 1;
-    w.t.red = d; d += 8;
-    w.t.redi = reinterpret_cast<int*>(d); d += 4;
+    w.t.red = d; d += 16;                                  // one slot per warp of the team (up to 16 warps; the largest class runs 12)
+    w.t.redi = reinterpret_cast<int*>(d); d += 8;
     w.zero3 = d; d += 4;
     w.hs = d; d += 12;
     w.hq = d; d += 12;

@@ -27,6 +27,7 @@ struct SizeClass { int ncap, ns_lo, ns_hi, nw; };      // nw = warps of the team
 #ifndef MPCQ_NW3
 #define MPCQ_NW3 12
 #endif
+static_assert(MPCQ_NW0 <= 16 && MPCQ_NW1 <= 16 && MPCQ_NW2 <= 16 && MPCQ_NW3 <= 16, "team scratch (Ctx::red / redi) holds one slot per warp, 16 at most");
 static const SizeClass kClasses[4] = {{64, 0, class_ns_hi(64), MPCQ_NW0}, {128, class_ns_hi(64) + 1, class_ns_hi(128), MPCQ_NW1},
                                       {192, class_ns_hi(128) + 1, class_ns_hi(192), MPCQ_NW2}, {384, class_ns_hi(192) + 1, class_ns_hi(384), MPCQ_NW3}};
 inline int class_nmax(const SizeClass& c) { return (3 * c.ns_hi + 3) & ~3; }   // rows of the largest system in the class

@@ -167,8 +167,8 @@ namespace team {
 struct Ctx {
     int tid, nt, wid;      // thread in team, team size, warp in team
     int bar;               // hardware barrier of the team (0 = the whole CTA)
-    double* red;           // [8] scratch
-    int* redi;             // [8] scratch
+    double* red;           // [16] scratch, one slot per warp
+    int* redi;             // [16] scratch, one slot per warp (bcast uses the last)
 };
 
 MPCQ_DEV void sync(const Ctx& c) {
@@ -231,9 +231,9 @@ MPCQ_DEV bool any(const Ctx& c, bool p) { return reduce_sum(c, p ? 1 : 0) != 0; 
 // value held by warp 0 -> every thread (also a barrier: what warp 0 wrote before is visible after)
 MPCQ_DEV int bcast(const Ctx& c, int v) {
     if (c.nt == 32) { wp::sync(); return v; }
-    if (c.tid == 0) c.redi[7] = v;
+    if (c.tid == 0) c.redi[15] = v;
     wp::team_sync(c.bar, c.nt);
-    const int r = c.redi[7];
+    const int r = c.redi[15];
     wp::team_sync(c.bar, c.nt);
     return r;
 }

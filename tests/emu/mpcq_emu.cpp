@@ -181,6 +181,25 @@ int mpcq_emu_solve_f64(const mpcq_config* cs, int B, const double* x0, const dou
 }
 }
 
+// team collectives on their own: every thread of an nw-warp team contributes (vals[tid], tid) to team::reduce_argmin and
+// writes what it got back (all threads must agree; a NaN anywhere must win)
+namespace {
+struct ArgminJob { const double* vals; double* out_v; int* out_tag; int nt; double red[16]; int redi[16]; };
+void argmin_entry(void* p) {
+    ArgminJob* j = static_cast<ArgminJob*>(p);
+    team::Ctx c;
+    c.tid = wp::team_tid(j->nt); c.nt = j->nt; c.wid = c.tid >> 5; c.bar = 0; c.red = j->red; c.redi = j->redi;
+    double v = j->vals[c.tid];
+    int tag = c.tid;
+    team::reduce_argmin(c, v, tag);
+    j->out_v[c.tid] = v; j->out_tag[c.tid] = tag;
+}
+}  // namespace
+extern "C" void mpcq_emu_team_argmin(int nw, const double* vals, double* out_v, int* out_tag) {
+    ArgminJob j{vals, out_v, out_tag, 32 * nw, {}, {}};
+    mpcq_emu::run_team(32 * nw, argmin_entry, &j);
+}
+
 // the per-leg layer (mpcq_legs.cuh): the device bodies run over all (environment, leg) pairs in index order
 extern "C" {
 void mpcq_emu_swing_targets(int B, const mpcq_leg_params* lp, const double* pos_base, const double* lin_vel_base, const double* R_base,

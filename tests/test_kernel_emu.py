@@ -202,3 +202,30 @@ def test_leg_layer_device_code_reproduces_the_reference_sequence(emu_lib):
             assert dp <= 1e-8 and dv <= 1e-7, (r, t, dp, dv)
             worst[0], worst[1] = max(worst[0], dp), max(worst[1], dv)
     assert worst[2] <= 2e-6, worst            # relative torque error: float32 rounding level
+
+
+@pytest.mark.parametrize("nw", [1, 2, 3, 12])
+def test_team_argmin_lets_a_nan_win_in_any_warp(emu_lib, nw):
+    """team::reduce_argmin (the ratio test of the monotone fallback): the minimum with ties towards the smaller tag, the same
+    answer in every thread, and a NaN held by ANY warp of the team wins - it must be noticed (ST_NUMERIC), not skipped."""
+    import ctypes as C
+    nt = 32 * nw
+    p = lambda a, t: a.ctypes.data_as(C.POINTER(t))
+    rng = np.random.default_rng(5 + nw)
+    def run(vals):
+        out_v, out_tag = np.zeros(nt), np.zeros(nt, np.int32)
+        emu_lib.mpcq_emu_team_argmin(nw, p(vals, C.c_double), p(out_v, C.c_double), p(out_tag, C.c_int))
+        assert np.all(out_tag == out_tag[0])
+        assert np.all(out_v == out_v[0]) or np.all(np.isnan(out_v))
+        return out_v[0], int(out_tag[0])
+    vals = rng.uniform(1.0, 2.0, nt)
+    k = int(rng.integers(nt))
+    vals[k] = 0.5
+    assert run(vals) == (0.5, k)
+    vals[(k + 37) % nt] = 0.5                                        # a tie: the smaller tag
+    assert run(vals) == (0.5, min(k, (k + 37) % nt))
+    for where in sorted({0, nt - 1, nt // 2, 32 * (nw - 1) + 7}):    # a NaN in the first, the last and a middle warp
+        v2 = vals.copy()
+        v2[where] = np.nan
+        v, tag = run(v2)
+        assert np.isnan(v) and tag == where
