@@ -719,9 +719,6 @@ MPCQ_DEV bool chol_factor(const Consts& cs, Work<T>& w) {
 // Storage: full symmetric, element (i, k) at P[k * ld + i] with ld = n + 1 (odd: a lane-per-row sweep down a column
 // and the transposed store along a row are both conflict-free).  P is written over the packed factor in place:
 // column block J of P lands at addresses >= j0 * ld + j0, above every factor column < j0 that is still to be read.
-#ifndef MPCQ_TDB
-#define MPCQ_TDB (NW > 1)
-#endif
 template <class T, int NCAP, int NW>
 MPCQ_DEV void invert_factor(Work<T>& w) {
     MPCQ_PHASE(4);
@@ -758,7 +755,7 @@ MPCQ_DEV void invert_factor(Work<T>& w) {
         MPCQ_UNROLL
         for (int m = 0; m < NSLOT; ++m) { acc[m][0] = acc[m][1] = acc[m][2] = acc[m][3] = (T)0; }
         const int m0 = (j0 + 4) / NT;                          // slots below hold no row of the trailing block
-        if constexpr (MPCQ_TDB && NSLOT == 2) {
+        if constexpr (NW > 1 && NSLOT == 2) {        // (measured: no gain for the one-warp class, whose 9 warps per SM hide the pipe for each other)
             // A team of lone warps (one per scheduler): nothing else hides the shared-memory pipe, which takes 4 cycles per
             // load instruction of a warp.  Two register sets, the loads of group g + 1 issued between the multiply-adds of
             // group g, no branch inside the body (the last fetch reads one group past the end: columns of the Schur block or
